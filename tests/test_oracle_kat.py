@@ -1,0 +1,175 @@
+"""Pins the CPU oracle against every known-answer vector the reference tree physically holds for
+the compositor path.  CPU-only (`-m "not gpu"`)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+# ---- integration-tests/src/render_tests/yuv_tests.rs:32-132 -----------------------------------
+GRADIENT_YUV_EXPECTED = [
+    89, 0, 0, 255, 100, 5, 3, 255, 160, 0, 0, 255, 165, 2, 0, 255, 204, 0, 0, 255, 207, 1, 0, 255, 239, 0, 0, 255, 241, 1, 0, 255,
+    89, 0, 0, 255, 100, 5, 3, 255, 160, 0, 0, 255, 165, 2, 0, 255, 204, 0, 0, 255, 207, 1, 0, 255, 239, 0, 0, 255, 241, 1, 0, 255,
+]
+GRADIENT_RGBA_EXPECTED = [
+    71, 0, 0, 255, 120, 0, 0, 255, 152, 0, 0, 255, 177, 0, 0, 255, 198, 0, 0, 255, 216, 0, 0, 255, 233, 0, 0, 255, 248, 0, 0, 255,
+    71, 0, 0, 255, 120, 0, 0, 255, 152, 0, 0, 255, 177, 0, 0, 255, 198, 0, 0, 255, 216, 0, 0, 255, 233, 0, 0, 255, 248, 0, 0, 255,
+]
+UNIFORM_YUV_EXPECTED = [49, 0, 0, 255] * 16
+UNIFORM_RGBA_EXPECTED = [50, 0, 0, 255] * 16
+
+
+def _gradient_node_texture():
+    """What the shader node of yuv_test_gradient leaves in its Rgba8UnormSrgb target: the fragment
+    returns vec4(tex_coords.x, 0, 0, 1) with tex_coords.x = (i + .5)/8; the store encodes sRGB."""
+    w, h = 8, 2
+    img = np.zeros((h, w, 4), np.uint8)
+    for i in range(w):
+        lin = np.float32((i + 0.5) / 8.0)
+        img[:, i] = (orc.lib().orc_srgb_encode_u8(lin), orc.lib().orc_srgb_encode_u8(0.0),
+                     orc.lib().orc_srgb_encode_u8(0.0), orc.lib().orc_unorm8(1.0))
+    return img
+
+
+def test_yuv_test_gradient_rgba():
+    img = _gradient_node_texture()
+    assert img.reshape(-1).tolist() == GRADIENT_RGBA_EXPECTED  # reference tolerance is +-2; we are exact
+
+
+def test_yuv_test_gradient_yuv_roundtrip():
+    img = _gradient_node_texture()
+    y, u, v = orc.rgba_to_yuv420(img)
+    back = orc.harness_yuv420_to_rgba(y, u, v, 8, 2)
+    diff = np.abs(back.reshape(-1).astype(int) - np.array(GRADIENT_YUV_EXPECTED))
+    assert diff.max() <= 2, (back.reshape(-1).tolist(), GRADIENT_YUV_EXPECTED)  # yuv_tests.rs:25
+    assert diff.max() == 0  # and in fact identical
+
+
+def _uniform_color_scene(mode):
+    # View{background_color: (50,0,0,255)} at 8x2 flattens to one Color layout covering the output
+    L = orc.make_layout(orc.LAYOUT_COLOR, 0, 0, 8, 2, color=(50, 0, 0, 255))
+    return orc.apply_layouts(8, 2, [L], [None], mode=mode)
+
+
+@pytest.mark.parametrize("mode", [orc.MODE_GPU_OPTIMIZED, orc.MODE_CPU_OPTIMIZED])
+def test_yuv_test_uniform_color(mode):
+    img = _uniform_color_scene(mode)
+    assert img.reshape(-1).tolist() == UNIFORM_RGBA_EXPECTED
+    y, u, v = orc.rgba_to_yuv420(img)
+    back = orc.harness_yuv420_to_rgba(y, u, v, 8, 2)
+    assert back.reshape(-1).tolist() == UNIFORM_YUV_EXPECTED
+
+
+# ---- integration-tests/src/render_tests/pixel_input_format_tests.rs:31-152 --------------------
+def _through_default_view(node, mode=orc.MODE_GPU_OPTIMIZED):
+    """View{children:[InputStream]} at 8x2: transparent Color layout is culled, the child is a
+    Texture layout at (0,0) 8x2 with crop = whole texture and the View's overflow-hidden mask
+    (dropped by fix_final_render_layout because it contains the layout)."""
+    L = orc.make_layout(orc.LAYOUT_TEXTURE, 0, 0, 8, 2, child_index=0, crop=(0, 0, 8, 2))
+    return orc.render_layout_node(8, 2, [L], [node], mode=mode)
+
+
+def test_bgra_pixel_format_input():
+    data = np.arange(1, 65, dtype=np.uint8)
+    node = orc.bgra_to_rgba(data, 8, 2)
+    out = _through_default_view(node)
+    exp = []
+    for p in range(16):
+        b, g, r, a = data[p * 4:p * 4 + 4]
+        exp += [r, g, b, a]
+    assert out.reshape(-1).tolist() == [int(x) for x in exp]
+
+
+def test_argb_pixel_format_input():
+    data = np.arange(1, 65, dtype=np.uint8)
+    node = orc.argb_to_rgba(data, 8, 2)
+    out = _through_default_view(node)
+    exp = []
+    for p in range(16):
+        a, r, g, b = data[p * 4:p * 4 + 4]
+        exp += [r, g, b, a]
+    assert out.reshape(-1).tolist() == [int(x) for x in exp]
+
+
+# ---- smelter-render/src/transformations/layout/resampler.rs:402-468 ---------------------------
+H, V = 0, 1
+
+
+def test_plans_a_pass_for_every_non_direct_axis():
+    assert orc.plan_passes(0.0, 0.0, 640.0, 360.0, 640, 360) == []
+    assert orc.plan_passes(100.0, 40.0, 640.0, 360.0, 640, 360) == []
+    assert orc.plan_passes(100.0, 0.0, 640.0, 360.0, 640, 300) == [(V, 100)]
+    assert orc.plan_passes(0.0, 42.0, 640.0, 360.0, 320, 360) == [(H, 42)]
+    frac = orc.plan_passes(100.5, 0.0, 640.0, 360.0, 640, 300)
+    assert len(frac) == 2
+    sep = orc.plan_passes(0.0, 0.0, 1920.0, 1080.0, 960, 270)
+    assert [a for a, _ in sep] == [V, H]
+
+
+def test_degenerate_scales_do_not_overflow_predecimation():
+    assert orc.predecimate_levels(float("inf"), 10) == 16
+    assert orc.predecimate_levels(float("nan"), 10) == 0
+
+
+def test_predecimation_budget():
+    # KERNEL_BUDGET = 4 (resampler.rs:19): ratios <= 4 use the kernel alone
+    assert orc.predecimate_levels(3840.0, 960) == 0
+    assert orc.predecimate_levels(3840.0, 959) == 1
+    assert orc.predecimate_levels(7680.0, 480) == 2
+
+
+# ---- numeric-contract self checks --------------------------------------------------------------
+def test_srgb_roundtrip_is_identity():
+    L = orc.lib()
+    for b in range(256):
+        assert L.orc_srgb_encode_u8(L.orc_srgb_decode_u8(b)) == b
+
+
+def test_f16_matches_numpy():
+    L = orc.lib()
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.standard_normal(2000).astype(np.float32) * 2,
+                         (rng.random(2000).astype(np.float32) * 1e-4),
+                         np.array([0, -0.0, 1, 65504, 65519.9, 65520, 1e-8, 5.96e-8, 2.98e-8, 6.1e-5], np.float32)])
+    for x in xs:
+        h = L.orc_f32_to_f16(float(x))
+        ref = np.float32(x).astype(np.float16)
+        assert h == ref.view(np.uint16), (x, h, ref.view(np.uint16))
+        if np.isfinite(ref):
+            assert L.orc_f16_to_f32(h) == np.float32(ref)
+
+
+def test_lanczos_weights_scale4_single_phase():
+    # config 3 (3840 -> 960): every output coordinate has the same 25-tap kernel, last tap is 0
+    f0, w0, s0 = orc.resample_weights(4.0, 0.0, 0)
+    f7, w7, s7 = orc.resample_weights(4.0, 0.0, 7)
+    assert len(w0) == 25 and f0 == -10 and f7 == 18
+    assert np.array_equal(w0, w7) and s0 == s7
+    assert w0[24] == 0.0 and abs(s0 - 4.0) < 0.02
+    # symmetric kernel around its centre within float noise of the rotation recurrence
+    assert np.allclose(w0[:24], w0[:24][::-1], atol=2e-6)
+
+
+def test_lanczos_identity_at_unit_scale():
+    f, w, s = orc.resample_weights(1.0, 0.0, 5)
+    # centre = 5: tap at x=0 has weight 1, the others sit on the zeros of the sinc
+    assert f == 2 and len(w) == 7
+    assert w[3] == 1.0 and np.abs(np.delete(w, 3)).max() < 1e-6
+
+
+def test_black_frame_bytes():
+    # render_loop.rs:127-139 fills with RGBColor::BLACK.to_yuv()
+    assert orc.rgb_to_yuv_bytes(0, 0, 0) == (16, 128, 128)
+
+
+def test_chroma_upsample_phase_is_quarter():
+    """K1 on even sizes: taps .25/.75 exactly for every x of every even width
+    the renderer can see -- the CUDA kernels hard-code this phase."""
+    y = np.full((2, 16), 100, np.uint8)
+    u = np.full((1, 8), 128, np.uint8)
+    v = np.full((1, 8), 128, np.uint8)
+    u[0, 3] = 160
+    rgba = orc.yuv420_to_rgba(y, u, v, 16, 2)
+    # b channel follows u: pixels 6,7 (chroma texel 3) get .75 weight, 5 and 8 get .25
+    b = rgba[0, :, 2].astype(int)
+    assert b[6] == b[7] and b[5] == b[8] and b[4] == b[9] and b[6] > b[5] > b[4]
