@@ -1,0 +1,240 @@
+/*
+ * smelter_b200.h -- C ABI of the B200-native per-output-frame compositor.
+ *
+ * Drop-in boundary: this library replaces `smelter_render::Renderer`
+ * (reference: smelter-render/src/state.rs:95-193).  There is no C ABI in the reference (it is a Rust
+ * crate on wgpu); each entry point below names the Rust method it stands in for, so a Rust shim can
+ * re-implement `Renderer` 1:1 over these symbols.
+ *
+ * Conventions: plain C types only; every function returns smr_status (0 = ok) and never throws or
+ * aborts across the boundary; ids are NUL-terminated UTF-8 (the reference's `InputId`/`OutputId`
+ * are `Arc<str>`); all pointers are borrowed for the duration of the call only; a handle is
+ * internally synchronised exactly like the reference's `Arc<Mutex<InnerRenderer>>` (state.rs:54-55).
+ * The product path has NO CPU fallback: every pixel is produced by sm_100a CUDA kernels.
+ */
+#ifndef SMELTER_B200_H
+#define SMELTER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smr_renderer smr_renderer;
+
+/* error.rs:10-66 variants that exist on this path, flattened to status codes */
+typedef enum {
+    SMR_OK = 0,
+    SMR_ERR_INVALID_ARGUMENT = 1,
+    SMR_ERR_CUDA = 2,                 /* RenderSceneError::WgpuError / InitRendererEngineError analogue */
+    SMR_ERR_OUTPUT_NOT_REGISTERED = 3,/* UpdateSceneError::OutputNotRegistered / unknown output in render */
+    SMR_ERR_SCENE = 4,                /* UpdateSceneError::SceneError (duplicate ids, unknown root size) */
+    SMR_ERR_UNSUPPORTED = 5,          /* component / format outside the compositor hot path */
+    SMR_ERR_OUT_OF_MEMORY = 6,
+    SMR_ERR_BUFFER_TOO_SMALL = 7
+} smr_status;
+
+/* RenderingMode, types.rs:9-18 (WebGl is out of scope) */
+typedef enum { SMR_MODE_GPU_OPTIMIZED = 0, SMR_MODE_CPU_OPTIMIZED = 1 } smr_rendering_mode;
+
+/* RendererOptions, state.rs:43-52.  device/queue become a CUDA device ordinal. */
+typedef struct {
+    int32_t cuda_device;               /* SMELTER_GPU_DEVICE_ID analogue (src/config.rs:142); -1 = host-only
+                                          handle for scene/layout inspection (cannot render) */
+    int32_t rendering_mode;            /* smr_rendering_mode */
+    uint32_t max_layouts_count;        /* DEFAULT_MAX_LAYOUTS_COUNT = 100 (layout.rs:23); 0 = default */
+    uint64_t stream_fallback_timeout_ns;
+    uint32_t framerate_num, framerate_den;
+} smr_options;
+
+/* ------------------------------- scene::Component (scene/components.rs) ---------------------- */
+typedef enum {
+    SMR_COMPONENT_INPUT_STREAM = 0,
+    SMR_COMPONENT_VIEW = 1,
+    SMR_COMPONENT_TILES = 2,
+    SMR_COMPONENT_RESCALER = 3,
+    /* declared so a shim can forward them; smr_update_scene answers SMR_ERR_UNSUPPORTED */
+    SMR_COMPONENT_SHADER = 4,
+    SMR_COMPONENT_WEB_VIEW = 5,
+    SMR_COMPONENT_IMAGE = 6,
+    SMR_COMPONENT_TEXT = 7
+} smr_component_type;
+
+typedef struct { uint8_t r, g, b, a; } smr_rgba;                                  /* RGBAColor */
+typedef struct { float top_left, top_right, bottom_right, bottom_left; } smr_border_radius;
+typedef struct { float offset_x, offset_y, blur_radius; smr_rgba color; } smr_box_shadow;
+typedef struct { float top, right, bottom, left; } smr_padding;
+typedef struct { int32_t has_value; float value; } smr_opt_f32;                    /* Option<f32> */
+
+typedef enum { SMR_INTERP_LINEAR = 0, SMR_INTERP_BOUNCE = 1, SMR_INTERP_CUBIC_BEZIER = 2 } smr_interpolation_kind;
+typedef struct {                                                                   /* Option<Transition> */
+    int32_t present;
+    uint64_t duration_ns;
+    int32_t interpolation_kind;
+    double x1, y1, x2, y2;       /* CubicBezier control points */
+    int32_t should_interrupt;
+} smr_transition;
+
+typedef struct {                                                                   /* Position */
+    int32_t is_absolute;         /* 0: Static{width,height}; 1: Absolute(AbsolutePosition) */
+    smr_opt_f32 width, height;
+    int32_t horizontal_from_right; float horizontal_offset; /* LeftOffset / RightOffset */
+    int32_t vertical_from_bottom; float vertical_offset;    /* TopOffset / BottomOffset */
+    float rotation_degrees;
+} smr_position;
+
+typedef enum { SMR_DIRECTION_ROW = 0, SMR_DIRECTION_COLUMN = 1 } smr_direction;
+typedef enum { SMR_OVERFLOW_VISIBLE = 0, SMR_OVERFLOW_HIDDEN = 1, SMR_OVERFLOW_FIT = 2 } smr_overflow;
+typedef enum { SMR_RESCALE_FIT = 0, SMR_RESCALE_FILL = 1 } smr_rescale_mode;
+typedef enum { SMR_HALIGN_LEFT = 0, SMR_HALIGN_RIGHT = 1, SMR_HALIGN_JUSTIFIED = 2, SMR_HALIGN_CENTER = 3 } smr_horizontal_align;
+typedef enum { SMR_VALIGN_TOP = 0, SMR_VALIGN_CENTER = 1, SMR_VALIGN_BOTTOM = 2, SMR_VALIGN_JUSTIFIED = 3 } smr_vertical_align;
+
+/* One node of the Component tree.  Fields that do not apply to `type` are ignored.
+ * Use smr_component_default() to get the reference's `Default` values (components.rs:289-347). */
+typedef struct smr_component {
+    int32_t type;                          /* smr_component_type */
+    const char *id;                        /* Option<ComponentId>; NULL = None */
+    const struct smr_component *children;  /* View/Tiles: children; Rescaler: exactly one child */
+    uint32_t children_len;
+    const char *input_id;                  /* InputStream */
+
+    smr_position position;                 /* View, Rescaler */
+    smr_transition transition;             /* View, Rescaler, Tiles */
+    smr_border_radius border_radius;       /* View, Rescaler */
+    float border_width;
+    smr_rgba border_color;
+    const smr_box_shadow *box_shadow;
+    uint32_t box_shadow_len;
+
+    int32_t direction;                     /* View */
+    int32_t overflow;
+    smr_rgba background_color;             /* View, Tiles */
+    smr_padding padding;                   /* View */
+
+    int32_t rescale_mode;                  /* Rescaler */
+    int32_t horizontal_align;              /* Rescaler, Tiles */
+    int32_t vertical_align;
+
+    smr_opt_f32 tiles_width, tiles_height; /* Tiles */
+    uint32_t tile_aspect_ratio_w, tile_aspect_ratio_h;
+    float tiles_margin, tiles_padding;
+} smr_component;
+
+/* ------------------------------------ frames (types.rs:21-119) ------------------------------- */
+typedef enum {
+    SMR_FRAME_PLANAR_YUV420 = 0,   /* FrameData::PlanarYuv420: planes y,u,v */
+    SMR_FRAME_PLANAR_YUVJ420 = 1,  /* FrameData::PlanarYuvJ420 (full range) */
+    SMR_FRAME_NV12 = 2,            /* FrameData::Nv12: planes y, uv */
+    SMR_FRAME_BGRA = 3,            /* FrameData::Bgra */
+    SMR_FRAME_ARGB = 4,            /* FrameData::Argb */
+    SMR_FRAME_RGBA8 = 5            /* FrameData::Rgba8UnormWgpuTexture analogue: premultiplied RGBA8 */
+} smr_frame_format;
+
+typedef enum { SMR_MEM_HOST = 0, SMR_MEM_DEVICE = 1 } smr_mem_kind;
+
+typedef struct {                   /* one entry of FrameSet<InputId> */
+    const char *input_id;
+    int32_t format;                /* smr_frame_format */
+    uint32_t width, height;        /* Frame::resolution */
+    uint64_t pts_ns;               /* Frame::pts */
+    const void *planes[3];         /* tightly packed when pitch == 0 */
+    uint32_t pitch[3];             /* bytes per row */
+    int32_t mem_kind;              /* smr_mem_kind; DEVICE = zero-copy (Nv12WgpuTexture analogue) */
+} smr_input_frame;
+
+typedef enum {                     /* OutputFrameFormat, types.rs:187-194 */
+    SMR_OUT_PLANAR_YUV420 = 0,     /* PlanarYuv420Bytes */
+    SMR_OUT_RGBA8 = 3,             /* RgbaWgpuTexture analogue */
+    SMR_OUT_NV12 = 4               /* Nv12WgpuTexture analogue */
+} smr_output_format;
+
+typedef struct {                   /* one entry of FrameSet<OutputId>; caller owns the buffers */
+    const char *output_id;
+    void *planes[3];               /* capacity: see smr_output_plane_sizes() */
+    uint32_t pitch[3];             /* 0 = tightly packed */
+    int32_t mem_kind;              /* where the planes live */
+    /* filled by smr_render */
+    uint32_t width, height;
+    int32_t format;
+    uint64_t pts_ns;
+} smr_output_frame;
+
+/* Flattened layout (RenderLayout, transformations/layout.rs:59-98) -- debug/inspection channel
+ * used by the parity tests to feed the CPU oracle the very layouts the kernels drew. */
+#define SMR_MAX_MASKS 20           /* params.rs:15 */
+typedef struct { float radius[4]; float top, left, width, height; } smr_mask;
+typedef struct {
+    int32_t type;                  /* 0 texture, 1 color, 2 box shadow (apply_layouts.wgsl:66-71) */
+    float top, left, width, height, rotation_degrees;
+    float border_radius[4];        /* tl, tr, br, bl */
+    smr_rgba color, border_color;
+    float border_width, blur_radius;
+    int32_t child_index;
+    float crop_top, crop_left, crop_width, crop_height;
+    int32_t masks_len;
+    smr_mask masks[SMR_MAX_MASKS];
+} smr_render_layout;
+
+typedef struct {
+    uint64_t frames_rendered;       /* output frames produced */
+    uint64_t kernel_launches;       /* CUDA kernels launched by this handle */
+    uint64_t h2d_bytes, d2h_bytes;  /* bytes copied across PCIe by smr_render */
+    uint64_t last_render_kernel_launches;
+} smr_stats;
+
+/* ------------------------------------------ entry points ------------------------------------ */
+/* Renderer::new(RendererOptions)                                    state.rs:96-100,196-211 */
+smr_status smr_create(const smr_options *opts, smr_renderer **out);
+void smr_destroy(smr_renderer *r);
+
+/* Renderer::register_input / unregister_input                       state.rs:102-113 */
+smr_status smr_register_input(smr_renderer *r, const char *input_id);
+smr_status smr_unregister_input(smr_renderer *r, const char *input_id);
+
+/* Renderer::update_scene(output_id, resolution, output_format, scene_root)   state.rs:177-188 */
+smr_status smr_update_scene(smr_renderer *r, const char *output_id, uint32_t width, uint32_t height,
+                            int32_t output_format, const smr_component *scene_root);
+/* Renderer::unregister_output                                       state.rs:115-123 */
+smr_status smr_unregister_output(smr_renderer *r, const char *output_id);
+
+/* Renderer::render(FrameSet<InputId>) -> FrameSet<OutputId>         state.rs:173-175,220-252
+ * Renders every output listed in `outputs` at `pts_ns` (FrameSet::pts).  Blocks until the output
+ * planes are complete (the reference blocks in device.poll, render_loop.rs:177-183). */
+smr_status smr_render(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
+                      smr_output_frame *outputs, uint32_t n_outputs);
+
+/* The same with the waits split off, so a caller can overlap ticks:
+ * smr_render_begin enqueues uploads + kernels + downloads and returns; smr_render_end waits. */
+smr_status smr_render_begin(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
+                            smr_output_frame *outputs, uint32_t n_outputs);
+smr_status smr_render_end(smr_renderer *r);
+
+/* byte sizes of the planes smr_render writes for an output (0 for unused planes) */
+smr_status smr_output_plane_sizes(uint32_t width, uint32_t height, int32_t output_format, size_t sizes[3]);
+
+/* reference `Default` impls for each component type                 components.rs:289-347 */
+void smr_component_default(int32_t type, smr_component *out);
+
+/* inspection: flattened layouts of an output at pts (the input resolutions are those of the last
+ * smr_render).  Does not advance any scene state. */
+smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pts_ns,
+                             smr_render_layout *out, uint32_t capacity, uint32_t *n_out,
+                             uint32_t *root_width, uint32_t *root_height);
+
+/* inspection: record the pts / input resolutions of a FrameSet exactly as smr_render would
+ * (scene.register_render_event + populate_inputs bookkeeping) without touching any plane.  Together
+ * with smr_options.cuda_device = -1 (host-only handle: scene + layout engine, smr_render refuses) this
+ * lets the host logic be tested on a box without a GPU. */
+smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs);
+
+smr_status smr_get_stats(smr_renderer *r, smr_stats *out);
+void *smr_cuda_stream(smr_renderer *r);          /* cudaStream_t the handle launches on */
+const char *smr_last_error(smr_renderer *r);     /* ErrorStack::into_string analogue; valid until next call */
+const char *smr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMELTER_B200_H */

@@ -1,0 +1,48 @@
+"""Builds libsmelter_b200.so (C-ABI library: C++ host + sm_100a CUDA kernels) in-tree with nvcc.
+
+No torch, no JIT cache: the .so sits next to this file so that it travels to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsmelter_b200.so")
+SOURCES = ["kernels.cu", "renderer.cpp", "scene.cpp"]
+HEADERS = ["kernels.h", "scene.h", os.path.join("..", "..", "include", "smelter_b200.h")]
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",            # numeric contract: only explicit fmaf() is fused
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-ccbin", "/usr/bin/g++",
+    "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose=True, extra=sys.argv[1:])
+    print(LIB)

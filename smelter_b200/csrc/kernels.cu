@@ -1,0 +1,679 @@
+// kernels.cu -- hand-written sm_100a kernels of the per-output-frame compositor.
+//
+// Replaces the reference's WGSL shader set:
+//   k_convert     planar_yuv_to_rgba.wgsl / nv12_to_rgba.wgsl / bgra / argb           (K1,K2,K4)
+//   k_weights     the per-output-coordinate part of resample.wgsl:42-86               (K8 setup)
+//   k_resample    resample.wgsl (Lanczos3 pass) and downsample.wgsl (box pass)         (K7,K8)
+//   k_composite   apply_layouts.wgsl: every layout of an output in ONE launch, painter's order kept per
+//                 pixel in registers, fixed-function sRGB blend emulated per layer, fused with
+//                 rgba_to_yuv.wgsl / rgba_to_nv12.wgsl on the way out                   (K9,K10,K11)
+//   k_output      rgba_to_yuv / rgba_to_nv12 stand-alone (root size != output size, odd sizes)
+//   k_fill        r8/rg8_fill_value.wgsl (black frame)                                  (K6)
+//
+// Numeric contract: identical to oracle/smelter_oracle.c.  Compiled with
+// -fmad=false: only explicit fmaf() is fused, every other operation rounds separately, division and
+// sqrt are IEEE.  No tensor cores: there is no dense contraction on this path (HBM / FP32-ALU bound).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace smr {
+namespace dev {
+
+// ------------------------------------------------------------------------------------------------
+// tables (NC-1, NC-3, NC-4) -- pushed from the host so host and device agree bit-for-bit
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_u8n[256];
+__constant__ float c_dec[256];
+__constant__ float c_thr[256];  // 255 used
+
+static char g_err[256] = {0};
+const char *last_launch_error() { return g_err; }
+static bool check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return false;
+    }
+    return true;
+}
+
+void upload_tables(const float *u8n, const float *dec, const float *thr) {
+    float t[256];
+    for (int i = 0; i < 255; i++) t[i] = thr[i];
+    t[255] = 3.0e38f;
+    cudaMemcpyToSymbol(c_u8n, u8n, sizeof(float) * 256);
+    cudaMemcpyToSymbol(c_dec, dec, sizeof(float) * 256);
+    cudaMemcpyToSymbol(c_thr, t, sizeof(float) * 256);
+}
+
+struct Tables {  // per-block shared-memory copies (divergent indices would serialise in constant memory)
+    float u8n[256];
+    float dec[256];
+    float thr[256];
+};
+
+__device__ __forceinline__ void load_tables(Tables &t) {
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y) {
+        t.u8n[i] = c_u8n[i];
+        t.dec[i] = c_dec[i];
+        t.thr[i] = c_thr[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+__device__ __forceinline__ int unorm8(float x) { return __float2int_rn(clamp01(x) * 255.0f); }  // NC-2
+
+__device__ __forceinline__ int srgb_encode(const Tables &t, float lin) {  // NC-4
+    float x = clamp01(lin);
+    float g = x <= 0.0031308f ? 12.92f * x : 1.055f * __powf(x, 0.41666666f) - 0.055f;
+    int e = __float2int_rn(g * 255.0f);
+    e = min(max(e, 0), 255);
+    while (e < 255 && x >= t.thr[e]) e++;       // exact: count of thresholds <= x
+    while (e > 0 && x < t.thr[e - 1]) e--;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NC-6 sampler
+// ------------------------------------------------------------------------------------------------
+struct LinTap {
+    int i0, i1;
+    float f;
+};
+
+__device__ __forceinline__ LinTap linear_tap(float t, int dim) {
+    LinTap r;
+    float c = t * (float)dim - 0.5f;
+    if (!(c == c)) { r.i0 = r.i1 = 0; r.f = 0.0f; return r; }
+    c = fminf(fmaxf(c, -2.0f), (float)dim + 1.0f);
+    float fl = floorf(c);
+    float f = c - fl;
+    r.f = rintf(f * 256.0f) * (1.0f / 256.0f);
+    int i0 = (int)fl, i1 = i0 + 1;
+    r.i0 = min(max(i0, 0), dim - 1);
+    r.i1 = min(max(i1, 0), dim - 1);
+    return r;
+}
+
+__device__ __forceinline__ float bilerp(float t00, float t10, float t01, float t11, float fx, float fy) {
+    float h0 = fmaf(t10, fx, t00 * (1.0f - fx));
+    float h1 = fmaf(t11, fx, t01 * (1.0f - fx));
+    return fmaf(h1, fy, h0 * (1.0f - fy));
+}
+
+__device__ __forceinline__ float sample_plane(const Tables &T, const uint8_t *p, int pitch, int stride, int ch,
+                                              const LinTap &ax, const LinTap &ay) {
+    const uint8_t *r0 = p + (size_t)ay.i0 * pitch, *r1 = p + (size_t)ay.i1 * pitch;
+    // a zero weight multiplies a finite texel: skipping the tap is exact
+    float t00 = T.u8n[__ldg(r0 + ax.i0 * stride + ch)];
+    float t10 = ax.f != 0.0f ? T.u8n[__ldg(r0 + ax.i1 * stride + ch)] : t00;
+    if (ay.f == 0.0f) return fmaf(t10, ax.f, t00 * (1.0f - ax.f));
+    float t01 = T.u8n[__ldg(r1 + ax.i0 * stride + ch)];
+    float t11 = ax.f != 0.0f ? T.u8n[__ldg(r1 + ax.i1 * stride + ch)] : t01;
+    return bilerp(t00, t10, t01, t11, ax.f, ay.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K2/K4: one texel of the (possibly virtual) RGBA8 node texture of an input
+// planar_yuv_to_rgba.wgsl:35-58, nv12_to_rgba.wgsl:26-48, bgra_to_rgba.wgsl, argb_to_rgba.wgsl
+// ------------------------------------------------------------------------------------------------
+#define K16 (16.0f / 255.0f)
+#define RCP_Y (1.0f / 0.85882352941f)
+#define RCP_C (1.0f / 0.87843137254f)
+
+__device__ __forceinline__ uchar4 yuv_to_rgba8(float y, float u, float v, int full_range) {
+    if (!full_range) {
+        y = clamp01((y - K16) * RCP_Y);
+        u = clamp01((u - K16) * RCP_C);
+        v = clamp01((v - K16) * RCP_C);
+    }
+    float um = u - 0.5f, vm = v - 0.5f;
+    float r = fmaf(1.5748f, vm, y);
+    float g = fmaf(-0.4681f, vm, fmaf(-0.1873f, um, y));
+    float b = fmaf(1.8556f, um, y);
+    return make_uchar4((unsigned char)unorm8(r), (unsigned char)unorm8(g), (unsigned char)unorm8(b), 255);
+}
+
+__device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int x, int y) {
+    switch (s.kind) {
+        case TEX_RGBA8:
+            return __ldg(reinterpret_cast<const uchar4 *>(s.p0 + (size_t)y * s.pitch0) + x);
+        case TEX_BGRA: {
+            uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(s.p0 + (size_t)y * s.pitch0) + x);
+            return make_uchar4(v.z, v.y, v.x, v.w);
+        }
+        case TEX_ARGB: {
+            uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(s.p0 + (size_t)y * s.pitch0) + x);
+            return make_uchar4(v.y, v.z, v.w, v.x);
+        }
+        case TEX_YUV420:
+        case TEX_NV12: {
+            int cw = s.width / 2, ch = s.height / 2;
+            float tx = ((float)x + 0.5f) / (float)s.width, ty = ((float)y + 0.5f) / (float)s.height;
+            LinTap ax = linear_tap(tx, s.width), ay = linear_tap(ty, s.height);
+            LinTap cx = linear_tap(tx, cw), cy = linear_tap(ty, ch);
+            float yy = sample_plane(T, s.p0, s.pitch0, 1, 0, ax, ay);
+            float uu, vv;
+            if (s.kind == TEX_YUV420) {
+                uu = sample_plane(T, s.p1, s.pitch1, 1, 0, cx, cy);
+                vv = sample_plane(T, s.p2, s.pitch2, 1, 0, cx, cy);
+            } else {
+                uu = sample_plane(T, s.p1, s.pitch1, 2, 0, cx, cy);
+                vv = sample_plane(T, s.p1, s.pitch1, 2, 1, cx, cy);
+            }
+            return yuv_to_rgba8(yy, uu, vv, s.full_range);
+        }
+        default:
+            return make_uchar4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_convert(Tex src, uint8_t *dst, int dst_pitch) {
+    __shared__ Tables T;
+    load_tables(T);
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= src.width || y >= src.height) return;
+    reinterpret_cast<uchar4 *>(dst + (size_t)y * dst_pitch)[x] = node_texel(T, src, x, y);
+}
+
+int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s) {
+    dim3 b(32, 8), g((src.width + 31) / 32, (src.height + 7) / 8);
+    k_convert<<<g, b, 0, (cudaStream_t)s>>>(src, dst, dst_pitch);
+    return check_launch("k_convert") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 setup: Lanczos3 weights, resample.wgsl:42-86.  sin/cos are NC-8 (correctly rounded f32, through
+// the fp64 unit); the rotation recurrence is the shader's.
+// ------------------------------------------------------------------------------------------------
+#define PI_F 3.14159265359f
+
+__device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float cos_cr(float x) { return (float)cos((double)x); }
+
+__global__ void k_weights(const WeightJob *jobs) {
+    const WeightJob J = jobs[blockIdx.y];
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= J.n_out) return;
+    float kernel_scale = fmaxf(J.scale, 1.0f);
+    float inv_k = 1.0f / kernel_scale;
+    float support = 3.0f * kernel_scale;
+    float center = (J.offset + ((float)o + 0.5f) * J.scale) - 0.5f;
+    float first = ceilf(center - support);
+    float x0 = (first - center) * inv_k;
+    float s1 = sin_cr(PI_F * x0), c1 = cos_cr(PI_F * x0);
+    float s3 = sin_cr(PI_F * x0 / 3.0f), c3 = cos_cr(PI_F * x0 / 3.0f);
+    float sd1 = sin_cr(PI_F * inv_k), cd1 = cos_cr(PI_F * inv_k);
+    float sd3 = sin_cr(PI_F * inv_k / 3.0f), cd3 = cos_cr(PI_F * inv_k / 3.0f);
+    const float pi2 = PI_F * PI_F;
+    float wsum = 0.0f;
+    float *w = J.weights + (size_t)o * J.taps;
+    for (int t = 0; t < J.taps; t++) {
+        float x = x0 + (float)t * inv_k;
+        float wt = 0.0f;
+        if (fabsf(x) < 1e-5f) wt = 1.0f;
+        else if (fabsf(x) < 3.0f) wt = ((3.0f * s1) * s3) / ((pi2 * x) * x);
+        w[t] = wt;
+        wsum += wt;
+        float ns1 = s1 * cd1 + c1 * sd1;
+        c1 = c1 * cd1 - s1 * sd1;
+        s1 = ns1;
+        float ns3 = s3 * cd3 + c3 * sd3;
+        c3 = c3 * cd3 - s3 * sd3;
+        s3 = ns3;
+    }
+    J.inv_wsum[o] = 1.0f / wsum;
+    float fc = fminf(fmaxf(first, -1.0e9f), 1.0e9f);
+    J.first[o] = (int)fc;
+}
+
+int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n, Stream s) {
+    if (n <= 0) return 0;
+    int max_out = 1;
+    for (int i = 0; i < n; i++) max_out = jobs_host[i].n_out > max_out ? jobs_host[i].n_out : max_out;
+    dim3 b(128), g((max_out + 127) / 128, n);
+    k_weights<<<g, b, 0, (cudaStream_t)s>>>(jobs_dev);
+    return check_launch("k_weights") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7/K8: resampler passes.  One launch runs the same pass stage of every resampled child of the
+// frame (blockIdx.z = job).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 rs_load(const Tables &T, const Tex &s, int x, int y) {
+    if (s.kind == TEX_F16) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(s.p0 + (size_t)y * s.pitch0) + x);
+        __half2 a = *reinterpret_cast<const __half2 *>(&raw.x), b = *reinterpret_cast<const __half2 *>(&raw.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    uchar4 p = node_texel(T, s, x, y);  // fetched through the srgb view: decode rgb, alpha linear
+    return make_float4(T.dec[p.x], T.dec[p.y], T.dec[p.z], T.u8n[p.w]);
+}
+
+__device__ __forceinline__ void rs_store(const Tables &T, const ResampleJob &J, int x, int y, float4 r) {
+    if (J.dst_f16) {
+        __half2 a = __floats2half2_rn(r.x, r.y), b = __floats2half2_rn(r.z, r.w);  // NC-5
+        uint2 raw;
+        raw.x = *reinterpret_cast<unsigned int *>(&a);
+        raw.y = *reinterpret_cast<unsigned int *>(&b);
+        reinterpret_cast<uint2 *>(J.dst + (size_t)y * J.dst_pitch)[x] = raw;
+    } else {
+        uchar4 o = make_uchar4((unsigned char)srgb_encode(T, r.x), (unsigned char)srgb_encode(T, r.y),
+                               (unsigned char)srgb_encode(T, r.z), (unsigned char)unorm8(r.w));
+        reinterpret_cast<uchar4 *>(J.dst + (size_t)y * J.dst_pitch)[x] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resample(const ResampleJob *jobs) {
+    __shared__ Tables T;
+    load_tables(T);
+    const ResampleJob &J = jobs[blockIdx.z];
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= J.dst_w || py >= J.dst_h) return;
+    const Tex &S = J.src;
+    if (J.box_fx * J.box_fy > 1) {  // downsample.wgsl:28-41
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int dy = 0; dy < J.box_fy; dy++)
+            for (int dx = 0; dx < J.box_fx; dx++) {
+                int sx = min(px * J.box_fx + dx, S.width - 1), sy = min(py * J.box_fy + dy, S.height - 1);
+                float4 t = rs_load(T, S, sx, sy);
+                sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+            }
+        float d = (float)((unsigned)J.box_fx * (unsigned)J.box_fy);
+        rs_store(T, J, px, py, make_float4(sum.x / d, sum.y / d, sum.z / d, sum.w / d));
+        return;
+    }
+    int o = J.axis == 1 ? py : px;
+    int max_src = (J.axis == 1 ? S.height : S.width) - 1;
+    int max_perp = (J.axis == 1 ? S.width : S.height) - 1;
+    int perp = min(max((J.axis == 1 ? px : py) + J.perp_offset, 0), max_perp);
+    const float *w = J.weights + (size_t)o * J.taps;
+    int first = __ldg(J.first + o);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < J.taps; t++) {
+        float wt = __ldg(w + t);
+        if (wt == 0.0f) continue;  // exact: adds +-0 to a sum that is never -0
+        int src = min(max(first + t, 0), max_src);
+        float4 tx = J.axis == 1 ? rs_load(T, S, perp, src) : rs_load(T, S, src, perp);
+        sum.x = fmaf(tx.x, wt, sum.x);
+        sum.y = fmaf(tx.y, wt, sum.y);
+        sum.z = fmaf(tx.z, wt, sum.z);
+        sum.w = fmaf(tx.w, wt, sum.w);
+    }
+    float inv = __ldg(J.inv_wsum + o);
+    rs_store(T, J, px, py, make_float4(sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv));
+}
+
+int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n, Stream s) {
+    if (n <= 0) return 0;
+    int mw = 1, mh = 1;
+    for (int i = 0; i < n; i++) {
+        mw = jobs_host[i].dst_w > mw ? jobs_host[i].dst_w : mw;
+        mh = jobs_host[i].dst_h > mh ? jobs_host[i].dst_h : mh;
+    }
+    dim3 b(32, 8), g((mw + 31) / 32, (mh + 7) / 8, n);
+    k_resample<<<g, b, 0, (cudaStream_t)s>>>(jobs_dev);
+    return check_launch("k_resample") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 (+K10/K11): composite
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float smoothstep_f(float e0, float e1, float x) {
+    float t = clamp01((x - e0) / (e1 - e0));
+    return (t * t) * (3.0f - 2.0f * t);
+}
+
+// apply_layouts.wgsl:246-256; radius = [tl, tr, br, bl]
+__device__ __forceinline__ float rounded_rect_sdf(float dx, float dy, float sx, float sy, const float *radius) {
+    float hx = sx / 2.0f, hy = sy / 2.0f;
+    float rx, ry;
+    if (dx < 0.0f) { rx = radius[0]; ry = radius[3]; } else { rx = radius[1]; ry = radius[2]; }
+    if (dy < 0.0f) rx = ry;
+    float qx = (fabsf(dx) - hx) + rx, qy = (fabsf(dy) - hy) + rx;
+    float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    return (fminf(fmaxf(qx, qy), 0.0f) + sqrtf(mx * mx + my * my)) - rx;
+}
+
+__device__ __forceinline__ bool quad_covers(const LayerDev &L, int px, int py) {  // NC-7
+    if (px < L.px0 || px >= L.px1 || py < L.py0 || py >= L.py1) return false;
+    if (!L.rotated) return true;
+    long long X = (long long)px * 256 + 128, Y = (long long)py * 256 + 128;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        long long dx = L.vx[j] - L.vx[i], dy = L.vy[j] - L.vy[i];
+        long long e = dx * (Y - L.vy[i]) - dy * (X - L.vx[i]);
+        bool top_left = (dy < 0) || (dy == 0 && dx > 0);
+        if (e < 0 || (e == 0 && !top_left)) return false;
+    }
+    return true;
+}
+
+// textureSample of a child through NodeTextureState::view()
+__device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, int mode, float tx, float ty) {
+    if (tex == nullptr || tex->kind == TEX_NONE) return make_float4(0.f, 0.f, 0.f, 0.f);  // default_empty_view
+    const Tex &S = *tex;
+    LinTap ax = linear_tap(tx, S.width), ay = linear_tap(ty, S.height);
+    const float *lut = mode == 0 ? T.dec : T.u8n;
+    uchar4 p00 = node_texel(T, S, ax.i0, ay.i0);
+    if (ax.f == 0.0f && ay.f == 0.0f)  // exact texel hit: the other three weights are zero
+        return make_float4(lut[p00.x], lut[p00.y], lut[p00.z], T.u8n[p00.w]);
+    uchar4 p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
+    uchar4 p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
+    uchar4 p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
+    float4 r;
+    r.x = bilerp(lut[p00.x], lut[p10.x], lut[p01.x], lut[p11.x], ax.f, ay.f);
+    r.y = bilerp(lut[p00.y], lut[p10.y], lut[p01.y], lut[p11.y], ax.f, ay.f);
+    r.z = bilerp(lut[p00.z], lut[p10.z], lut[p01.z], lut[p11.z], ax.f, ay.f);
+    r.w = bilerp(T.u8n[p00.w], T.u8n[p10.w], T.u8n[p01.w], T.u8n[p11.w], ax.f, ay.f);
+    return r;
+}
+
+// vs_main + fs_main of apply_layouts.wgsl for one covered pixel
+__device__ __forceinline__ float4 shade(const Tables &T, const CompositeJob &J, const LayerDev &L, int px, int py) {
+    float pcx = (float)px + 0.5f, pcy = (float)py + 0.5f;
+    float lx, ly, u, v;
+    if (!L.rotated) {
+        lx = (pcx - L.left) - L.width * 0.5f;
+        ly = L.height * 0.5f - (pcy - L.top);
+        u = (pcx - L.left) / L.width;
+        v = (pcy - L.top) / L.height;
+    } else {
+        float dx = pcx - L.cx, dyu = L.cy - pcy;
+        lx = dx * L.cs + dyu * L.sn;
+        ly = dyu * L.cs - dx * L.sn;
+        u = lx / L.width + 0.5f;
+        v = 0.5f - ly / L.height;
+    }
+    float mask_alpha = 1.0f;
+    for (int i = 0; i < L.mask_count; i++) {
+        const MaskDev &m = J.masks[L.mask_begin + i];
+        float d = rounded_rect_sdf((m.left + m.width / 2.0f) - pcx, (m.top + m.height / 2.0f) - pcy, m.width,
+                                   m.height, m.radius);
+        mask_alpha = mask_alpha * smoothstep_f(-0.5f, 0.5f, -d);
+    }
+    float edge = -rounded_rect_sdf(lx, ly, L.content_w, L.content_h, L.border_radius);
+    float4 src = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L.type == 0) {
+        float tx = u * L.crop_sx + L.crop_ox;
+        float ty = v * L.crop_sy + L.crop_oy;
+        float4 sample = sample_node(T, L.tex >= 0 ? &J.textures[L.tex] : nullptr, J.mode, tx, ty);
+        float bw = L.border_width;
+        if (bw < 1.0f) {
+            float ca = smoothstep_f(-0.5f, 0.5f, edge);
+            src = make_float4((sample.x * ca) * mask_alpha, (sample.y * ca) * mask_alpha,
+                              (sample.z * ca) * mask_alpha, (sample.w * ca) * mask_alpha);
+        } else if (mask_alpha < 0.01f) {
+            // transparent
+        } else if (edge > bw / 2.0f) {
+            float ba = smoothstep_f(bw - 0.5f, bw + 0.5f, edge);
+            float ib = 1.0f - ba;
+            src = make_float4((L.border_color[0] * ib + sample.x * ba) * mask_alpha,
+                              (L.border_color[1] * ib + sample.y * ba) * mask_alpha,
+                              (L.border_color[2] * ib + sample.z * ba) * mask_alpha,
+                              (L.border_color[3] * ib + sample.w * ba) * mask_alpha);
+        } else {
+            float ca = smoothstep_f(-0.5f, 0.5f, edge);
+            src = make_float4((L.border_color[0] * ca) * mask_alpha, (L.border_color[1] * ca) * mask_alpha,
+                              (L.border_color[2] * ca) * mask_alpha, (L.border_color[3] * ca) * mask_alpha);
+        }
+    } else if (L.type == 1) {
+        float bw = L.border_width;
+        if (bw < 1.0f) {
+            float ca = smoothstep_f(-0.5f, 0.5f, edge);
+            src = make_float4((L.color[0] * ca) * mask_alpha, (L.color[1] * ca) * mask_alpha,
+                              (L.color[2] * ca) * mask_alpha, (L.color[3] * ca) * mask_alpha);
+        } else if (edge > bw / 2.0f) {
+            float ba = smoothstep_f(bw, bw + 1.0f, edge);
+            float ib = 1.0f - ba;
+            src = make_float4((L.border_color[0] * ib + L.color[0] * ba) * mask_alpha,
+                              (L.border_color[1] * ib + L.color[1] * ba) * mask_alpha,
+                              (L.border_color[2] * ib + L.color[2] * ba) * mask_alpha,
+                              (L.border_color[3] * ib + L.color[3] * ba) * mask_alpha);
+        } else {
+            float ca = smoothstep_f(-0.5f, 0.5f, edge);
+            src = make_float4((L.border_color[0] * ca) * mask_alpha, (L.border_color[1] * ca) * mask_alpha,
+                              (L.border_color[2] * ca) * mask_alpha, (L.border_color[3] * ca) * mask_alpha);
+        }
+    } else {
+        float br = L.blur_radius;
+        float ba = smoothstep_f(-br / 2.0f, br / 2.0f, edge) * mask_alpha;
+        src = make_float4(L.color[0] * ba, L.color[1] * ba, L.color[2] * ba, L.color[3] * ba);
+    }
+    return src;
+}
+
+// PREMULTIPLIED_ALPHA_BLENDING through the target's view: decode dst -> blend -> encode (per layer)
+__device__ __forceinline__ uchar4 blend(const Tables &T, int mode, uchar4 dst, float4 s) {
+    s.x = clamp01(s.x); s.y = clamp01(s.y); s.z = clamp01(s.z); s.w = clamp01(s.w);
+    if (s.x == 0.0f && s.y == 0.0f && s.z == 0.0f && s.w == 0.0f) return dst;  // encode(decode(b)) == b
+    float ia = 1.0f - s.w;
+    uchar4 o;
+    if (mode == 0) {
+        o.x = (unsigned char)srgb_encode(T, fmaf(T.dec[dst.x], ia, s.x));
+        o.y = (unsigned char)srgb_encode(T, fmaf(T.dec[dst.y], ia, s.y));
+        o.z = (unsigned char)srgb_encode(T, fmaf(T.dec[dst.z], ia, s.z));
+    } else {
+        o.x = (unsigned char)unorm8(fmaf(T.u8n[dst.x], ia, s.x));
+        o.y = (unsigned char)unorm8(fmaf(T.u8n[dst.y], ia, s.y));
+        o.z = (unsigned char)unorm8(fmaf(T.u8n[dst.z], ia, s.z));
+    }
+    o.w = (unsigned char)unorm8(fmaf(T.u8n[dst.w], ia, s.w));
+    return o;
+}
+
+// rgba_to_yuv.wgsl:26-54 on raw stored bytes
+__device__ __forceinline__ float to_y(float r, float g, float b) {
+    float y = fmaf(b, 0.0722f, fmaf(g, 0.7152f, r * 0.2126f));
+    return fmaf(y, 0.85882352941f, K16);
+}
+__device__ __forceinline__ float to_u(float r, float g, float b) {
+    float u = fmaf(b, 0.5f, fmaf(g, -0.3854f, r * -0.1146f));
+    return fmaf(u + 0.5f, 0.87843137254f, K16);
+}
+__device__ __forceinline__ float to_v(float r, float g, float b) {
+    float v = fmaf(b, -0.0458f, fmaf(g, -0.4542f, r * 0.5f));
+    return fmaf(v + 0.5f, 0.87843137254f, K16);
+}
+
+#define CT_W 4           // pixels per thread, x
+#define CT_H 2           // pixels per thread, y
+#define CB_X 32          // threads per block, x
+#define CB_Y 8
+#define MAX_TILE_LAYERS 1024
+
+__global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
+    __shared__ Tables T;
+    __shared__ unsigned short s_list[MAX_TILE_LAYERS];
+    __shared__ int s_count;
+    load_tables(T);
+    const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H);
+    const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H, J.height);
+    // per-tile layer culling, painter's order preserved
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int c = 0;
+        for (int i = 0; i < J.n_layers && c < MAX_TILE_LAYERS; i++) {
+            const LayerDev &L = J.layers[i];
+            if (L.px0 < tile_x1 && L.px1 > tile_x0 && L.py0 < tile_y1 && L.py1 > tile_y0) s_list[c++] = (unsigned short)i;
+        }
+        s_count = c;
+    }
+    __syncthreads();
+
+    const int x0 = tile_x0 + threadIdx.x * CT_W, y0 = tile_y0 + threadIdx.y * CT_H;
+    uchar4 px[CT_H][CT_W];
+#pragma unroll
+    for (int j = 0; j < CT_H; j++)
+#pragma unroll
+        for (int i = 0; i < CT_W; i++) px[j][i] = make_uchar4(0, 0, 0, 0);  // LoadOp::Clear(TRANSPARENT)
+
+    const int n = s_count;
+    for (int li = 0; li < n; li++) {
+        const LayerDev &L = J.layers[s_list[li]];
+        if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
+#pragma unroll
+        for (int j = 0; j < CT_H; j++)
+#pragma unroll
+            for (int i = 0; i < CT_W; i++) {
+                int X = x0 + i, Y = y0 + j;
+                if (X < J.width && Y < J.height && quad_covers(L, X, Y))
+                    px[j][i] = blend(T, J.mode, px[j][i], shade(T, J, L, X, Y));
+            }
+    }
+
+    if (x0 >= J.width || y0 >= J.height) return;
+    if (J.out_format < 0 || J.out_format == 3) {  // RGBA8 node texture / RgbaWgpuTexture analogue
+#pragma unroll
+        for (int j = 0; j < CT_H; j++) {
+            int Y = y0 + j;
+            if (Y >= J.height) break;
+            uchar4 *row = reinterpret_cast<uchar4 *>(J.out0 + (size_t)Y * J.out_pitch0);
+            if (x0 + CT_W <= J.width && (J.out_pitch0 & 15) == 0) {
+                uint4 v;
+                v.x = *reinterpret_cast<unsigned int *>(&px[j][0]);
+                v.y = *reinterpret_cast<unsigned int *>(&px[j][1]);
+                v.z = *reinterpret_cast<unsigned int *>(&px[j][2]);
+                v.w = *reinterpret_cast<unsigned int *>(&px[j][3]);
+                *reinterpret_cast<uint4 *>(row + x0) = v;
+            } else {
+                for (int i = 0; i < CT_W && x0 + i < J.width; i++) row[x0 + i] = px[j][i];
+            }
+        }
+        return;
+    }
+    // fused K10/K11 (host guarantees even width/height): Y per pixel, chroma = 2x2 box of raw bytes
+    unsigned char yv[CT_H][CT_W];
+#pragma unroll
+    for (int j = 0; j < CT_H; j++)
+#pragma unroll
+        for (int i = 0; i < CT_W; i++)
+            yv[j][i] = (unsigned char)unorm8(to_y(T.u8n[px[j][i].x], T.u8n[px[j][i].y], T.u8n[px[j][i].z]));
+    const bool full = (x0 + CT_W <= J.width) && ((J.out_pitch0 & 3) == 0);
+#pragma unroll
+    for (int j = 0; j < CT_H; j++) {
+        int Y = y0 + j;
+        if (Y >= J.height) break;
+        unsigned char *row = J.out0 + (size_t)Y * J.out_pitch0;
+        if (full) *reinterpret_cast<uchar4 *>(row + x0) = make_uchar4(yv[j][0], yv[j][1], yv[j][2], yv[j][3]);
+        else
+            for (int i = 0; i < CT_W && x0 + i < J.width; i++) row[x0 + i] = yv[j][i];
+    }
+    unsigned char uo[2], vo[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const uchar4 a = px[0][2 * c], b = px[0][2 * c + 1], d = px[1][2 * c], e = px[1][2 * c + 1];
+        float r = bilerp(T.u8n[a.x], T.u8n[b.x], T.u8n[d.x], T.u8n[e.x], 0.5f, 0.5f);
+        float g = bilerp(T.u8n[a.y], T.u8n[b.y], T.u8n[d.y], T.u8n[e.y], 0.5f, 0.5f);
+        float bb = bilerp(T.u8n[a.z], T.u8n[b.z], T.u8n[d.z], T.u8n[e.z], 0.5f, 0.5f);
+        uo[c] = (unsigned char)unorm8(to_u(r, g, bb));
+        vo[c] = (unsigned char)unorm8(to_v(r, g, bb));
+    }
+    const int cx = x0 / 2, cy = y0 / 2, cw = J.width / 2;
+    if (J.out_format == 4) {  // NV12
+        unsigned char *row = J.out1 + (size_t)cy * J.out_pitch1 + cx * 2;
+        if (cx + 1 < cw && (J.out_pitch1 & 3) == 0) *reinterpret_cast<uchar4 *>(row) = make_uchar4(uo[0], vo[0], uo[1], vo[1]);
+        else
+            for (int c = 0; c < 2 && cx + c < cw; c++) { row[2 * c] = uo[c]; row[2 * c + 1] = vo[c]; }
+    } else {  // planar 4:2:0
+        unsigned char *ru = J.out1 + (size_t)cy * J.out_pitch1 + cx, *rv = J.out2 + (size_t)cy * J.out_pitch2 + cx;
+        if (cx + 1 < cw && (J.out_pitch1 & 1) == 0 && (J.out_pitch2 & 1) == 0) {
+            *reinterpret_cast<uchar2 *>(ru) = make_uchar2(uo[0], uo[1]);
+            *reinterpret_cast<uchar2 *>(rv) = make_uchar2(vo[0], vo[1]);
+        } else
+            for (int c = 0; c < 2 && cx + c < cw; c++) { ru[c] = uo[c]; rv[c] = vo[c]; }
+    }
+}
+
+int launch_composite(const CompositeJob &job, Stream s) {
+    dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H - 1) / (CB_Y * CT_H));
+    k_composite<<<g, b, 0, (cudaStream_t)s>>>(job);
+    return check_launch("k_composite") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10/K11 stand-alone: the general form (linear sampler from a src of any size)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sample_raw_rgb(const Tables &T, const Tex &S, float tx, float ty, float &r, float &g,
+                                               float &b) {
+    LinTap ax = linear_tap(tx, S.width), ay = linear_tap(ty, S.height);
+    uchar4 p00 = node_texel(T, S, ax.i0, ay.i0);
+    uchar4 p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
+    uchar4 p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
+    uchar4 p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
+    r = bilerp(T.u8n[p00.x], T.u8n[p10.x], T.u8n[p01.x], T.u8n[p11.x], ax.f, ay.f);
+    g = bilerp(T.u8n[p00.y], T.u8n[p10.y], T.u8n[p01.y], T.u8n[p11.y], ax.f, ay.f);
+    b = bilerp(T.u8n[p00.z], T.u8n[p10.z], T.u8n[p01.z], T.u8n[p11.z], ax.f, ay.f);
+}
+
+__global__ void __launch_bounds__(256) k_output(OutputJob J) {
+    __shared__ Tables T;
+    load_tables(T);
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= J.out_w || y >= J.out_h) return;
+    if (J.out_format == 3) {  // RGBA copy of the root texture (size must match; host checks)
+        reinterpret_cast<uchar4 *>(J.out0 + (size_t)y * J.out_pitch0)[x] = node_texel(T, J.src, x, y);
+        return;
+    }
+    float r, g, b;
+    sample_raw_rgb(T, J.src, ((float)x + 0.5f) / (float)J.out_w, ((float)y + 0.5f) / (float)J.out_h, r, g, b);
+    J.out0[(size_t)y * J.out_pitch0 + x] = (unsigned char)unorm8(to_y(r, g, b));
+    int cw = J.out_w / 2, ch = J.out_h / 2;
+    if (x < cw && y < ch) {  // chroma target texel (x, y)
+        sample_raw_rgb(T, J.src, ((float)x + 0.5f) / (float)cw, ((float)y + 0.5f) / (float)ch, r, g, b);
+        unsigned char u = (unsigned char)unorm8(to_u(r, g, b)), v = (unsigned char)unorm8(to_v(r, g, b));
+        if (J.out_format == 4) {
+            J.out1[(size_t)y * J.out_pitch1 + 2 * x] = u;
+            J.out1[(size_t)y * J.out_pitch1 + 2 * x + 1] = v;
+        } else {
+            J.out1[(size_t)y * J.out_pitch1 + x] = u;
+            J.out2[(size_t)y * J.out_pitch2 + x] = v;
+        }
+    }
+}
+
+int launch_output(const OutputJob &job, Stream s) {
+    dim3 b(32, 8), g((job.out_w + 31) / 32, (job.out_h + 7) / 8);
+    k_output<<<g, b, 0, (cudaStream_t)s>>>(job);
+    return check_launch("k_output") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: black frame (render_loop.rs:127-173)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,
+                       int fmt, uint8_t yv, uint8_t uv, uint8_t vv) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    if (fmt == 3) {
+        reinterpret_cast<uchar4 *>(p0 + (size_t)y * pitch0)[x] = make_uchar4(0, 0, 0, 0);
+        return;
+    }
+    p0[(size_t)y * pitch0 + x] = yv;
+    if (x < w / 2 && y < h / 2) {
+        if (fmt == 4) {
+            p1[(size_t)y * pitch1 + 2 * x] = uv;
+            p1[(size_t)y * pitch1 + 2 * x + 1] = vv;
+        } else {
+            p1[(size_t)y * pitch1 + x] = uv;
+            p2[(size_t)y * pitch2 + x] = vv;
+        }
+    }
+}
+
+int launch_fill_yuv(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h, int fmt,
+                    uint8_t y, uint8_t u, uint8_t v, Stream s) {
+    dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
+    k_fill<<<g, b, 0, (cudaStream_t)s>>>(p0, p1, p2, pitch0, pitch1, pitch2, w, h, fmt, y, u, v);
+    return check_launch("k_fill") ? 1 : -1;
+}
+
+}  // namespace dev
+}  // namespace smr

@@ -1,0 +1,117 @@
+// kernels.h -- device-side job descriptors + launchers of the sm_100a compositor kernels.
+// Host code (renderer.cpp, g++) and kernels.cu (nvcc) share this header; it is plain C++.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+namespace smr {
+namespace dev {
+
+// A texture a kernel can read.  Everything the reference keeps in wgpu textures lives in plain
+// pitched device buffers: input planes as uploaded, RGBA8 node textures, f16 resampler scratch.
+enum TexKind : int32_t {
+    TEX_NONE = 0,
+    TEX_RGBA8 = 1,   // premultiplied RGBA8; `srgb` says whether fetches decode (srgb view) or not
+    TEX_YUV420 = 2,  // planes y,u,v (K1 fused into the consumer)
+    TEX_NV12 = 3,    // planes y,uv  (K2 fused into the consumer)
+    TEX_F16 = 4,     // Rgba16Float scratch
+    TEX_BGRA = 5,
+    TEX_ARGB = 6,
+};
+
+struct Tex {
+    int32_t kind = TEX_NONE;
+    int32_t width = 0, height = 0;
+    int32_t full_range = 0;
+    const uint8_t *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    int32_t pitch0 = 0, pitch1 = 0, pitch2 = 0;  // bytes per row
+};
+
+struct MaskDev {
+    float radius[4];
+    float top, left, width, height;
+};
+
+// One flattened RenderLayout, prepared on the host for the composite kernel
+// (uniform blocks of layout/params.rs:199-317 + the vertex stage of apply_layouts.wgsl:174-243).
+struct LayerDev {
+    int32_t type;       // 0 texture, 1 color, 2 box shadow
+    int32_t rotated;
+    float left, top, width, height;  // the quad (box shadow: grown by blur_radius)
+    float content_w, content_h;      // size passed to roundedRectSDF
+    float cx, cy, cs, sn;            // quad centre (fb coords), cos/sin of rotation
+    int32_t px0, px1, py0, py1;      // unrotated: exactly covered pixels [px0,px1)x[py0,py1); rotated: bbox
+    long long vx[4], vy[4];          // rotated: vertices snapped to 1/256 px, clockwise on screen
+    float border_radius[4];
+    float color[4];                  // premultiplied shader colour (wgpu/utils.rs:51-71)
+    float border_color[4];
+    float border_width, blur_radius;
+    int32_t tex;                     // index into the texture table; -1 = empty 1x1 texture
+    float crop_sx, crop_ox, crop_sy, crop_oy;  // crop_w/dim, crop_left/dim, crop_h/dim, crop_top/dim
+    int32_t mask_begin, mask_count;
+    int32_t opaque_fast;             // host hint: no masks/radius/border/rotation -> cheap interior test
+};
+
+struct CompositeJob {
+    int32_t width, height;           // render target (root node texture) size
+    int32_t mode;                    // 0 GpuOptimized (sRGB target, linear blend), 1 CpuOptimized
+    int32_t n_layers;
+    const LayerDev *layers;
+    const MaskDev *masks;
+    const Tex *textures;
+    // outputs: RGBA8 target and/or fused YUV planes (K10/K11)
+    int32_t out_format;              // smr_output_format, or -1: RGBA8 node texture only
+    uint8_t *out0, *out1, *out2;
+    int32_t out_pitch0, out_pitch1, out_pitch2;
+};
+
+// one Lanczos pass (resample.wgsl) or box pass (downsample.wgsl)
+struct ResampleJob {
+    Tex src;                // TEX_RGBA8 (decoded through the srgb view), TEX_F16, or a YUV kind (fused K1/K2)
+    int32_t axis;           // 0 horizontal, 1 vertical
+    int32_t perp_offset;
+    int32_t taps;
+    int32_t dst_w, dst_h;
+    int32_t dst_f16;        // 1: Rgba16Float target, 0: sRGB8 target
+    uint8_t *dst;
+    int32_t dst_pitch;      // bytes
+    const float *weights;   // [n_out][taps]
+    const float *inv_wsum;  // [n_out]
+    const int32_t *first;   // [n_out]
+    int32_t box_fx, box_fy; // box pass when box_fx*box_fy > 1 (then weights unused)
+};
+
+struct WeightJob {          // resample.wgsl:42-86 evaluated once per output coordinate
+    float scale, offset;
+    int32_t n_out, taps;
+    float *weights;
+    float *inv_wsum;
+    int32_t *first;
+};
+
+struct OutputJob {          // K10/K11 stand-alone (root size != output size, or odd sizes)
+    Tex src;                // TEX_RGBA8 raw bytes, or a YUV kind when the root is an InputStream
+    int32_t out_w, out_h;
+    int32_t out_format;
+    uint8_t *out0, *out1, *out2;
+    int32_t out_pitch0, out_pitch1, out_pitch2;
+};
+
+// host tables pushed once per device (numeric contract NC-1/3/4)
+void upload_tables(const float *u8n, const float *srgb_dec, const float *srgb_enc_thr);
+
+typedef void *Stream;  // cudaStream_t
+
+// each returns the number of kernels it launched (for smr_stats / bench gpu_launches)
+int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s);
+int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n_jobs, Stream s);
+int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n_jobs, Stream s);
+int launch_composite(const CompositeJob &job, Stream s);
+int launch_output(const OutputJob &job, Stream s);
+int launch_fill_yuv(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,
+                    int out_format, uint8_t y, uint8_t u, uint8_t v, Stream s);
+const char *last_launch_error();
+
+}  // namespace dev
+}  // namespace smr

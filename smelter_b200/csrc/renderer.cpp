@@ -1,0 +1,1048 @@
+// renderer.cpp -- the Renderer behind the C ABI (include/smelter_b200.h).
+//
+// Replaces smelter-render/src/state.rs (Renderer/InnerRenderer), state/render_loop.rs
+// (populate_inputs / run_transforms / read_outputs), state/render_graph.rs, state/{input,node,output}_texture.rs
+// and transformations/layout.rs (LayoutNode::render, resample_scaled_children) + layout/params.rs.
+//
+// B200 design: no per-node textures and no per-pass submits.  Per tick the host flattens every
+// output's scene (CPU, as in the reference), packs ALL device-side descriptors of the tick into one
+// pinned arena, ships it with one async copy, and issues a fixed short sequence of launches on one
+// stream: [convert inputs that feed a Lanczos pass] -> [weights for new mappings] -> [box passes] ->
+// [first passes] -> [last passes] -> one composite(+YUV writeback) launch per output.  All transient
+// textures live in a frame arena in HBM that is recycled every tick.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/smelter_b200.h"
+#include "kernels.h"
+#include "scene.h"
+
+namespace smr {
+
+#define CUDA_OK(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+            return SMR_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+static const float kPiF = 3.14159265359f;
+
+// ------------------------------------------------------------------------------------------------
+// resampler planning (transformations/layout/resampler.rs:43-145)
+// ------------------------------------------------------------------------------------------------
+struct AxisMapping {
+    int axis;  // 0 horizontal, 1 vertical
+    float crop_offset, crop_len;
+    int dst_len;
+    float scale() const { return crop_len / (float)dst_len; }
+    int predecimate_levels() const {  // :56-58
+        float l = std::ceil(std::log2(scale() / 4.0f));
+        l = (l > 0.0f) ? l : 0.0f;
+        uint32_t lv = (l >= 4294967296.0f) ? 0xffffffffu : (uint32_t)l;
+        return (int)std::min<uint32_t>(lv, 16u);
+    }
+    AxisMapping on_reduced_source(int levels) const {  // :60-67
+        float factor = (float)(1u << levels);
+        AxisMapping m = *this;
+        m.crop_offset = crop_offset / factor;
+        m.crop_len = crop_len / factor;
+        return m;
+    }
+    bool as_direct(int &off) const {  // :72-76
+        auto same = [](float a, float b) { return std::fabs(a - b) < 0.001f; };
+        float r = std::round(crop_offset);
+        if (same(crop_len, (float)dst_len) && same(crop_offset, r)) {
+            off = (int)r;
+            return true;
+        }
+        return false;
+    }
+};
+
+struct KernelPass {
+    AxisMapping mapping;
+    int perp_offset;
+};
+
+// returns number of passes (0 = direct)
+static int plan_passes(const AxisMapping &h, const AxisMapping &v, KernelPass out[2]) {  // :122-145
+    int ho = 0, vo = 0;
+    bool hd = h.as_direct(ho), vd = v.as_direct(vo);
+    if (hd && vd) return 0;
+    if (!hd && vd) { out[0] = {h, vo}; return 1; }
+    if (hd && !vd) { out[0] = {v, ho}; return 1; }
+    if (v.scale() > h.scale()) { out[0] = {v, 0}; out[1] = {h, 0}; }
+    else { out[0] = {h, 0}; out[1] = {v, 0}; }
+    return 2;
+}
+
+static int resample_taps(float scale) {  // resample.wgsl:43-48
+    float ks = std::fmax(scale, 1.0f);
+    return (int)std::ceil(2.0f * (3.0f * ks)) + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small RAII helpers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+
+struct PinnedBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        uint8_t *np = nullptr;
+        size_t want = n * 2 + 4096;
+        cudaError_t e = cudaMallocHost(&np, want);
+        if (e != cudaSuccess) return e;
+        if (p) { memcpy(np, p, cap); cudaFreeHost(p); }
+        p = np; cap = want;
+        return cudaSuccess;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+class Renderer {
+  public:
+    explicit Renderer(const smr_options &o) : opts_(o) {}
+    ~Renderer();
+    smr_status init();
+
+    smr_status register_input(const char *id);
+    smr_status unregister_input(const char *id);
+    smr_status update_scene(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, const smr_component *root);
+    smr_status unregister_output(const char *id);
+    smr_status render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out, uint32_t n_out);
+    smr_status render_end();
+    smr_status debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
+    smr_status debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap, uint32_t *n,
+                             uint32_t *rw, uint32_t *rh);
+    void stats(smr_stats *s) { std::lock_guard<std::mutex> g(mu_); *s = stats_; }
+    void *stream() { return (void *)stream_; }
+    const char *last_error() { return err_.c_str(); }
+    void set_error(const std::string &e) { err_ = e; }
+    std::mutex mu_;
+
+  private:
+    struct Input {
+        bool has_frame = false;
+        dev::Tex tex;           // planes as they sit in HBM
+        DevBuf planes[3];       // owned copies of host frames
+        Resolution res;
+        int node_tex = -1;      // index in the tick's texture table of the materialised RGBA8 node texture
+        int raw_tex = -1;       // index of the virtual (fused K1/K2) texture
+    };
+    struct Output {
+        OutputNode node;
+        int32_t format = 0;
+        Resolution res;
+        DevBuf planes[3];       // device staging for host outputs
+    };
+    struct WeightKey {
+        uint32_t scale_bits, offset_bits;
+        int32_t n_out;
+        bool operator<(const WeightKey &o) const {
+            return std::tie(scale_bits, offset_bits, n_out) < std::tie(o.scale_bits, o.offset_bits, o.n_out);
+        }
+    };
+    struct WeightEntry {
+        float *weights = nullptr, *inv = nullptr;
+        int32_t *first = nullptr;
+        int taps = 0;
+        uint64_t last_used = 0;
+    };
+
+    // arenas ----------------------------------------------------------------------------------
+    size_t param_alloc(size_t bytes) {  // returns offset in the param arena
+        size_t off = (param_used_ + 255) & ~(size_t)255;
+        param_used_ = off + bytes;
+        return off;
+    }
+    size_t frame_alloc(size_t bytes) {
+        size_t off = (frame_used_ + 511) & ~(size_t)511;
+        frame_used_ = off + bytes;
+        return off;
+    }
+
+    smr_status populate_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
+    smr_status plan_output(Output &o, smr_output_frame &of, uint64_t pts);
+    smr_status get_weights(const KernelPass &p, WeightEntry &out);
+    int materialised_input(Input &in);
+    void prepare_layer(const RenderLayout &l, int W, int H, int tex_index, int tex_w, int tex_h, dev::LayerDev &d, bool &skip);
+    void shader_color(const RGBA &c, float out[4]) const;
+
+    smr_options opts_;
+    cudaStream_t stream_ = nullptr;
+    SceneState scene_;
+    std::map<std::string, Input> inputs_;
+    std::map<std::string, Output> outputs_;
+    std::string err_;
+    smr_stats stats_ = {};
+    uint64_t tick_ = 0;
+
+    // per-tick build state (host mirrors; device addresses = base + offset, fixed up before launch)
+    struct PendingComposite { dev::CompositeJob job; size_t layers_off, masks_off; };
+    struct PendingCopy { void *dst; size_t dpitch; const void *src; size_t spitch; size_t width, height; };
+    std::vector<dev::Tex> tex_table_;
+    std::vector<size_t> tex_frame_off_;       // for textures living in the frame arena: offset of p0 (else SIZE_MAX)
+    std::vector<dev::ResampleJob> stage_jobs_[3];
+    std::vector<std::pair<size_t, size_t>> stage_frame_off_[3];  // (src offset or SIZE_MAX, dst offset)
+    std::vector<int> stage_src_tex_[3];       // texture-table index of the source, or -1 when src is a frame-arena f16
+    std::vector<dev::WeightJob> weight_jobs_;
+    std::vector<std::pair<int, size_t>> convert_jobs_;  // (raw tex index, frame offset of RGBA8)
+    std::vector<PendingComposite> composites_;
+    std::vector<dev::OutputJob> output_jobs_;
+    std::vector<int> output_src_tex_;
+    struct Fill { uint8_t *p[3]; int pitch[3]; int w, h, fmt; uint8_t yuv[3]; };
+    std::vector<Fill> fills_;
+    std::vector<PendingCopy> d2h_;
+    std::map<std::tuple<int, uint32_t, uint32_t, uint32_t, uint32_t, int, int>, int> resample_cache_;
+
+    std::vector<uint8_t> param_host_;  // built here, copied to pinned, then to device
+    size_t param_used_ = 0;
+    PinnedBuf param_pinned_;
+    DevBuf param_dev_;
+    size_t frame_used_ = 0;
+    DevBuf frame_dev_;
+    std::map<WeightKey, WeightEntry> weights_;
+    bool in_flight_ = false;
+    bool host_only_ = false;
+};
+
+Renderer::~Renderer() {
+    if (stream_) {
+        cudaSetDevice(opts_.cuda_device);
+        cudaStreamSynchronize(stream_);
+        for (auto &kv : weights_) {
+            cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
+        }
+        cudaStreamDestroy(stream_);
+    }
+}
+
+static double srgb_to_linear_f64(uint8_t c) {  // wgpu/utils.rs:74-81
+    double x = (double)c / 255.0;
+    return x < 0.04045 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4);
+}
+static double eotf_f64(double c) { return c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4); }
+
+smr_status Renderer::init() {
+    if (opts_.max_layouts_count == 0) opts_.max_layouts_count = 100;  // DEFAULT_MAX_LAYOUTS_COUNT
+    if (opts_.max_layouts_count > 1024) opts_.max_layouts_count = 1024;
+    if (opts_.cuda_device == -1) { host_only_ = true; return SMR_OK; }  // scene/layout inspection only
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no CUDA device: the B200 compositor has no CPU fallback");
+        return SMR_ERR_CUDA;
+    }
+    if (opts_.cuda_device < 0 || opts_.cuda_device >= n) {
+        set_error("cuda_device out of range");
+        return SMR_ERR_INVALID_ARGUMENT;
+    }
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    float u8n[256], dec[256], thr[255];
+    for (int b = 0; b < 256; b++) {
+        u8n[b] = (float)b / 255.0f;
+        dec[b] = (float)eotf_f64((double)b / 255.0);
+    }
+    for (int k = 0; k < 255; k++) thr[k] = (float)eotf_f64(((double)k + 0.5) / 255.0);
+    dev::upload_tables(u8n, dec, thr);
+    CUDA_OK(cudaGetLastError());
+    return SMR_OK;
+}
+
+smr_status Renderer::register_input(const char *id) {
+    if (!id) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    inputs_.emplace(std::piecewise_construct, std::forward_as_tuple(id), std::forward_as_tuple());
+    return SMR_OK;
+}
+
+smr_status Renderer::unregister_input(const char *id) {
+    if (!id) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (in_flight_) { cudaSetDevice(opts_.cuda_device); cudaStreamSynchronize(stream_); in_flight_ = false; }
+    inputs_.erase(id);
+    return SMR_OK;
+}
+
+smr_status Renderer::unregister_output(const char *id) {
+    if (!id) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (in_flight_) { cudaSetDevice(opts_.cuda_device); cudaStreamSynchronize(stream_); in_flight_ = false; }
+    outputs_.erase(id);
+    scene_.unregister_output(id);
+    return SMR_OK;
+}
+
+smr_status Renderer::update_scene(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, const smr_component *root) {
+    if (!output_id || !root) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (fmt != SMR_OUT_PLANAR_YUV420 && fmt != SMR_OUT_RGBA8 && fmt != SMR_OUT_NV12) {
+        set_error("unsupported output format");
+        return SMR_ERR_UNSUPPORTED;
+    }
+    if (w == 0 || h == 0 || w > 16384 || h > 16384) {
+        set_error("output resolution out of range");
+        return SMR_ERR_INVALID_ARGUMENT;
+    }
+    Component c;
+    std::string err;
+    if (!component_from_c(root, c, err)) {
+        set_error(err);
+        return err.find("outside") != std::string::npos ? SMR_ERR_UNSUPPORTED : SMR_ERR_INVALID_ARGUMENT;
+    }
+    OutputNode node;
+    if (!scene_.update_scene(output_id, c, {w, h}, node, err)) {
+        set_error(err);
+        return SMR_ERR_SCENE;
+    }
+    Output &o = outputs_[output_id];
+    o.node = std::move(node);
+    o.format = fmt;
+    o.res = {w, h};
+    return SMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// populate_inputs (state/render_loop.rs:19-42, state/input_texture.rs:69-201)
+// ------------------------------------------------------------------------------------------------
+static bool plane_layout(int fmt, uint32_t w, uint32_t h, int plane, size_t &row_bytes, size_t &rows) {
+    uint32_t cw = w / 2, ch = h / 2;
+    switch (fmt) {
+        case SMR_FRAME_PLANAR_YUV420:
+        case SMR_FRAME_PLANAR_YUVJ420:
+            if (plane == 0) { row_bytes = w; rows = h; return true; }
+            if (plane <= 2) { row_bytes = cw; rows = ch; return true; }
+            return false;
+        case SMR_FRAME_NV12:
+            if (plane == 0) { row_bytes = w; rows = h; return true; }
+            if (plane == 1) { row_bytes = (size_t)cw * 2; rows = ch; return true; }
+            return false;
+        case SMR_FRAME_BGRA:
+        case SMR_FRAME_ARGB:
+        case SMR_FRAME_RGBA8:
+            if (plane == 0) { row_bytes = (size_t)w * 4; rows = h; return true; }
+            return false;
+        default: return false;
+    }
+}
+
+smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in) {
+    for (auto &kv : inputs_) {
+        Input &I = kv.second;
+        I.has_frame = false;
+        I.node_tex = I.raw_tex = -1;
+        const smr_input_frame *f = nullptr;
+        for (uint32_t i = 0; i < n_in; i++)
+            if (in[i].input_id && kv.first == in[i].input_id) f = &in[i];
+        if (!f) continue;
+        // Duration::saturating_sub(frame_set.pts, timeout) > frame.pts  => stale, render_loop.rs:29-32
+        uint64_t lim = pts > opts_.stream_fallback_timeout_ns ? pts - opts_.stream_fallback_timeout_ns : 0;
+        if (lim > f->pts_ns) continue;
+        if (f->width < 2 || f->height < 2 || f->width > 16384 || f->height > 16384) {
+            set_error("input frame resolution out of range");
+            return SMR_ERR_INVALID_ARGUMENT;
+        }
+        dev::Tex t;
+        switch (f->format) {
+            case SMR_FRAME_PLANAR_YUV420: t.kind = dev::TEX_YUV420; break;
+            case SMR_FRAME_PLANAR_YUVJ420: t.kind = dev::TEX_YUV420; t.full_range = 1; break;
+            case SMR_FRAME_NV12: t.kind = dev::TEX_NV12; break;
+            case SMR_FRAME_BGRA: t.kind = dev::TEX_BGRA; break;
+            case SMR_FRAME_ARGB: t.kind = dev::TEX_ARGB; break;
+            case SMR_FRAME_RGBA8: t.kind = dev::TEX_RGBA8; break;
+            default: set_error("unsupported input frame format"); return SMR_ERR_UNSUPPORTED;
+        }
+        t.width = (int)f->width; t.height = (int)f->height;
+        const uint8_t *ptrs[3] = {nullptr, nullptr, nullptr};
+        int pitches[3] = {0, 0, 0};
+        for (int p = 0; p < 3; p++) {
+            size_t row_bytes = 0, rows = 0;
+            if (!plane_layout(f->format, f->width, f->height, p, row_bytes, rows)) continue;
+            if (!f->planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
+            size_t spitch = f->pitch[p] ? f->pitch[p] : row_bytes;
+            if (f->mem_kind == SMR_MEM_DEVICE) {
+                ptrs[p] = (const uint8_t *)f->planes[p];
+                pitches[p] = (int)spitch;
+            } else {
+                CUDA_OK(I.planes[p].ensure(row_bytes * rows));
+                CUDA_OK(cudaMemcpy2DAsync(I.planes[p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
+                                          cudaMemcpyHostToDevice, stream_));
+                stats_.h2d_bytes += row_bytes * rows;
+                ptrs[p] = I.planes[p].p;
+                pitches[p] = (int)row_bytes;
+            }
+        }
+        t.p0 = ptrs[0]; t.p1 = ptrs[1]; t.p2 = ptrs[2];
+        t.pitch0 = pitches[0]; t.pitch1 = pitches[1]; t.pitch2 = pitches[2];
+        I.tex = t;
+        I.res = {f->width, f->height};
+        I.has_frame = true;
+        I.raw_tex = (int)tex_table_.size();
+        tex_table_.push_back(t);
+        tex_frame_off_.push_back(SIZE_MAX);
+    }
+    return SMR_OK;
+}
+
+// K1/K2 materialised once per tick for inputs that feed a resampler pass (taps x conversion is wasteful)
+int Renderer::materialised_input(Input &in) {
+    if (in.node_tex >= 0) return in.node_tex;
+    if (in.tex.kind == dev::TEX_RGBA8) { in.node_tex = in.raw_tex; return in.node_tex; }
+    size_t pitch = (size_t)in.tex.width * 4;
+    size_t off = frame_alloc(pitch * in.tex.height);
+    dev::Tex t;
+    t.kind = dev::TEX_RGBA8;
+    t.width = in.tex.width; t.height = in.tex.height;
+    t.pitch0 = (int)pitch;
+    in.node_tex = (int)tex_table_.size();
+    tex_table_.push_back(t);
+    tex_frame_off_.push_back(off);
+    convert_jobs_.push_back({in.raw_tex, off});
+    return in.node_tex;
+}
+
+void Renderer::shader_color(const RGBA &c, float out[4]) const {  // wgpu/utils.rs:51-71 + params.rs:353-361
+    double a = (double)c.a / 255.0;
+    if (opts_.rendering_mode == SMR_MODE_GPU_OPTIMIZED) {
+        out[0] = (float)(a * srgb_to_linear_f64(c.r));
+        out[1] = (float)(a * srgb_to_linear_f64(c.g));
+        out[2] = (float)(a * srgb_to_linear_f64(c.b));
+    } else {
+        out[0] = (float)(a * (double)c.r / 255.0);
+        out[1] = (float)(a * (double)c.g / 255.0);
+        out[2] = (float)(a * (double)c.b / 255.0);
+    }
+    out[3] = (float)a;
+}
+
+static inline long long snap256(float v) { return (long long)std::rint(v * 256.0f); }
+static inline long long ceil_div256(long long a) {  // ceil(a / 256)
+    long long q = a / 256, r = a % 256;
+    return q + (r > 0 ? 1 : 0);
+}
+
+// vertex stage of apply_layouts.wgsl:174-243 + rasteriser (numeric contract NC-7), on the host
+void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index, int tex_w, int tex_h,
+                             dev::LayerDev &d, bool &skip) {
+    memset(&d, 0, sizeof(d));
+    skip = true;
+    float left = l.left, top = l.top, w = l.width, h = l.height;
+    if (l.kind == RenderLayout::BoxShadow) {
+        float bw = l.width + 2.0f * l.blur_radius, bh = l.height + 2.0f * l.blur_radius;
+        left = l.left - l.blur_radius; top = l.top - l.blur_radius; w = bw; h = bh;
+    }
+    float rot = l.rotation_degrees;
+    if (!(left == left) || !(top == top) || !(w == w) || !(h == h) || !(rot == rot)) return;
+    if (std::fabs(left) > 1e7f || std::fabs(top) > 1e7f || std::fabs(w) > 1e7f || std::fabs(h) > 1e7f) return;
+    d.type = (int)l.kind;
+    d.left = left; d.top = top; d.width = w; d.height = h;
+    d.content_w = l.width; d.content_h = l.height;
+    float hw = w / 2.0f, hh = h / 2.0f;
+    d.cx = left + hw; d.cy = top + hh;
+    d.rotated = rot != 0.0f;
+    float minx, maxx, miny, maxy;
+    if (!d.rotated) {
+        d.cs = 1.0f; d.sn = 0.0f;
+        long long x0 = snap256(d.cx - hw), x1 = snap256(d.cx + hw), y0 = snap256(d.cy - hh), y1 = snap256(d.cy + hh);
+        long long px0 = ceil_div256(x0 - 128), px1 = ceil_div256(x1 - 128);
+        long long py0 = ceil_div256(y0 - 128), py1 = ceil_div256(y1 - 128);
+        d.px0 = (int)std::max<long long>(px0, 0); d.px1 = (int)std::min<long long>(px1, W);
+        d.py0 = (int)std::max<long long>(py0, 0); d.py1 = (int)std::min<long long>(py1, H);
+    } else {
+        float ang = rot * (kPiF / 180.0f);
+        d.cs = (float)std::cos((double)ang); d.sn = (float)std::sin((double)ang);
+        const float lx[4] = {-hw, hw, hw, -hw}, ly[4] = {hh, hh, -hh, -hh};
+        minx = miny = 1e30f; maxx = maxy = -1e30f;
+        for (int i = 0; i < 4; i++) {
+            float xr = lx[i] * d.cs - ly[i] * d.sn, yr = lx[i] * d.sn + ly[i] * d.cs;
+            float X = d.cx + xr, Y = d.cy - yr;
+            d.vx[i] = snap256(X); d.vy[i] = snap256(Y);
+            minx = std::fmin(minx, X); maxx = std::fmax(maxx, X);
+            miny = std::fmin(miny, Y); maxy = std::fmax(maxy, Y);
+        }
+        float fx0 = std::floor(minx) - 1.0f, fx1 = std::ceil(maxx) + 1.0f;
+        float fy0 = std::floor(miny) - 1.0f, fy1 = std::ceil(maxy) + 1.0f;
+        d.px0 = (int)std::fmax(fx0, 0.0f); d.py0 = (int)std::fmax(fy0, 0.0f);
+        d.px1 = (int)std::fmin(fx1, (float)W); d.py1 = (int)std::fmin(fy1, (float)H);
+    }
+    if (d.px0 >= d.px1 || d.py0 >= d.py1) return;
+    d.border_radius[0] = l.border_radius.top_left; d.border_radius[1] = l.border_radius.top_right;
+    d.border_radius[2] = l.border_radius.bottom_right; d.border_radius[3] = l.border_radius.bottom_left;
+    shader_color(l.color, d.color);
+    shader_color(l.border_color, d.border_color);
+    d.border_width = l.border_width;
+    d.blur_radius = l.blur_radius;
+    d.tex = tex_index;
+    if (l.kind == RenderLayout::ChildNode) {
+        d.crop_sx = l.crop.width / (float)tex_w; d.crop_ox = l.crop.left / (float)tex_w;
+        d.crop_sy = l.crop.height / (float)tex_h; d.crop_oy = l.crop.top / (float)tex_h;
+    }
+    skip = false;
+}
+
+smr_status Renderer::get_weights(const KernelPass &p, WeightEntry &out) {
+    WeightKey key;
+    float scale = p.mapping.scale(), offset = p.mapping.crop_offset;
+    memcpy(&key.scale_bits, &scale, 4);
+    memcpy(&key.offset_bits, &offset, 4);
+    key.n_out = p.mapping.dst_len;
+    auto it = weights_.find(key);
+    if (it != weights_.end()) {
+        it->second.last_used = tick_;
+        out = it->second;
+        return SMR_OK;
+    }
+    if (weights_.size() > 4096) {  // bound the cache: drop entries not used this tick
+        cudaStreamSynchronize(stream_);
+        for (auto i = weights_.begin(); i != weights_.end();) {
+            if (i->second.last_used != tick_) {
+                cudaFree(i->second.weights); cudaFree(i->second.inv); cudaFree(i->second.first);
+                i = weights_.erase(i);
+            } else ++i;
+        }
+    }
+    WeightEntry e;
+    e.taps = resample_taps(scale);
+    if (e.taps < 1 || e.taps > 4096) { set_error("resampler tap count out of range"); return SMR_ERR_INVALID_ARGUMENT; }
+    e.last_used = tick_;
+    CUDA_OK(cudaMalloc(&e.weights, sizeof(float) * (size_t)e.taps * key.n_out));
+    CUDA_OK(cudaMalloc(&e.inv, sizeof(float) * key.n_out));
+    CUDA_OK(cudaMalloc(&e.first, sizeof(int32_t) * key.n_out));
+    dev::WeightJob j;
+    j.scale = scale; j.offset = offset; j.n_out = key.n_out; j.taps = e.taps;
+    j.weights = e.weights; j.inv_wsum = e.inv; j.first = e.first;
+    weight_jobs_.push_back(j);
+    weights_[key] = e;
+    out = e;
+    return SMR_OK;
+}
+
+static void black_yuv(uint8_t out[3]) {  // RGBColor::BLACK.to_yuv() through an R8Unorm store
+    auto q = [](float x) { return (uint8_t)std::rint(std::fmin(std::fmax(x, 0.0f), 1.0f) * 255.0f); };
+    float y = 0.0f, u = 0.0f, v = 0.0f;
+    out[0] = q((y * 0.85882354f) + (16.0f / 255.0f));
+    out[1] = q(((u + 0.5f) * 0.8784314f) + (16.0f / 255.0f));
+    out[2] = q(((v + 0.5f) * 0.8784314f) + (16.0f / 255.0f));
+}
+
+static void out_plane_layout(int fmt, uint32_t w, uint32_t h, size_t row_bytes[3], size_t rows[3]) {
+    for (int i = 0; i < 3; i++) row_bytes[i] = rows[i] = 0;
+    uint32_t cw = w / 2, ch = h / 2;
+    if (fmt == SMR_OUT_RGBA8) { row_bytes[0] = (size_t)w * 4; rows[0] = h; }
+    else if (fmt == SMR_OUT_NV12) { row_bytes[0] = w; rows[0] = h; row_bytes[1] = (size_t)cw * 2; rows[1] = ch; }
+    else { row_bytes[0] = w; rows[0] = h; row_bytes[1] = row_bytes[2] = cw; rows[1] = rows[2] = ch; }
+}
+
+// LayoutNode::render (transformations/layout.rs:169-278) + read_outputs (render_loop.rs:59-230) for one output
+smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) {
+    const int mode = opts_.rendering_mode;
+    of.width = (uint32_t)o.res.width; of.height = (uint32_t)o.res.height;
+    of.format = o.format; of.pts_ns = pts;
+
+    // where the kernels write: caller's device planes, or our device staging + D2H
+    size_t row_bytes[3], rows[3];
+    out_plane_layout(o.format, of.width, of.height, row_bytes, rows);
+    uint8_t *dst[3] = {nullptr, nullptr, nullptr};
+    int pitch[3] = {0, 0, 0};
+    for (int p = 0; p < 3; p++) {
+        if (!row_bytes[p]) continue;
+        if (!of.planes[p]) { set_error("output plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
+        size_t user_pitch = of.pitch[p] ? of.pitch[p] : row_bytes[p];
+        if (of.mem_kind == SMR_MEM_DEVICE) {
+            dst[p] = (uint8_t *)of.planes[p];
+            pitch[p] = (int)user_pitch;
+        } else {
+            size_t dp = (row_bytes[p] + 15) & ~(size_t)15;  // 16-B rows: vector stores
+            CUDA_OK(o.planes[p].ensure(dp * rows[p]));
+            dst[p] = o.planes[p].p;
+            pitch[p] = (int)dp;
+            d2h_.push_back({of.planes[p], user_pitch, dst[p], dp, row_bytes[p], rows[p]});
+            stats_.d2h_bytes += row_bytes[p] * rows[p];
+        }
+    }
+    auto push_fill = [&]() {
+        Fill f;
+        for (int p = 0; p < 3; p++) { f.p[p] = dst[p]; f.pitch[p] = pitch[p]; }
+        f.w = (int)of.width; f.h = (int)of.height; f.fmt = o.format;
+        black_yuv(f.yuv);
+        fills_.push_back(f);
+    };
+    auto push_output_job = [&](int src_tex, size_t /*unused*/) {
+        dev::OutputJob j;
+        j.out_w = (int)of.width; j.out_h = (int)of.height; j.out_format = o.format;
+        j.out0 = dst[0]; j.out1 = dst[1]; j.out2 = dst[2];
+        j.out_pitch0 = pitch[0]; j.out_pitch1 = pitch[1]; j.out_pitch2 = pitch[2];
+        output_jobs_.push_back(j);
+        output_src_tex_.push_back(src_tex);
+    };
+
+    if (o.node.root_is_input) {  // pass-through: the root texture IS the input's node texture
+        auto it = inputs_.find(o.node.root_input_id);
+        if (it == inputs_.end() || !it->second.has_frame) { push_fill(); return SMR_OK; }
+        Input &in = it->second;
+        if (o.format == SMR_OUT_RGBA8 && (in.res.width != o.res.width || in.res.height != o.res.height)) {
+            // the reference hands out a clone of the node texture at ITS resolution (render_loop.rs:81-103)
+            set_error("RGBA output of a pass-through root must match the input resolution");
+            return SMR_ERR_UNSUPPORTED;
+        }
+        push_output_job(in.raw_tex, 0);
+        return SMR_OK;
+    }
+
+    // child node resolutions (sources[i].resolution(), layout.rs:176-179)
+    std::vector<std::optional<Resolution>> child_res;
+    std::vector<Input *> child_in;
+    for (const std::string &id : o.node.child_input_ids) {
+        auto it = inputs_.find(id);
+        if (it != inputs_.end() && it->second.has_frame) { child_res.push_back(it->second.res); child_in.push_back(&it->second); }
+        else { child_res.push_back(std::nullopt); child_in.push_back(nullptr); }
+    }
+    Resolution root = o.node.layout_resolution(pts);
+    if (root.width == 0 || root.height == 0 || root.width > 16384 || root.height > 16384) { push_fill(); return SMR_OK; }
+    std::vector<RenderLayout> layouts = o.node.layouts(pts, child_res).flatten(child_res, root);
+    if (layouts.size() > opts_.max_layouts_count) layouts.resize(opts_.max_layouts_count);  // params.rs:176-182
+
+    const int W = (int)root.width, H = (int)root.height;
+    std::vector<dev::LayerDev> layers;
+    std::vector<dev::MaskDev> masks;
+    for (RenderLayout &l : layouts) {
+        int tex_index = -1, tex_w = 1, tex_h = 1;
+        if (l.kind == RenderLayout::ChildNode) {
+            Input *in = l.index < child_in.size() ? child_in[l.index] : nullptr;
+            if (in) {
+                tex_index = in->raw_tex; tex_w = in->tex.width; tex_h = in->tex.height;
+                if (mode == SMR_MODE_GPU_OPTIMIZED) {  // resample_scaled_children, layout.rs:238-278
+                    float rw = std::round(l.width), rh = std::round(l.height);
+                    int dw = rw >= 1.0f ? (rw > 16384.0f ? 16384 : (int)rw) : 1;
+                    int dh = rh >= 1.0f ? (rh > 16384.0f ? 16384 : (int)rh) : 1;
+                    AxisMapping hm{0, l.crop.left, l.crop.width, dw}, vm{1, l.crop.top, l.crop.height, dh};
+                    KernelPass passes[2];
+                    if (plan_passes(hm, vm, passes) != 0) {
+                        uint32_t cb[4];
+                        memcpy(&cb[0], &l.crop.left, 4); memcpy(&cb[1], &l.crop.top, 4);
+                        memcpy(&cb[2], &l.crop.width, 4); memcpy(&cb[3], &l.crop.height, 4);
+                        auto key = std::make_tuple(in->raw_tex, cb[0], cb[1], cb[2], cb[3], dw, dh);
+                        auto hit = resample_cache_.find(key);
+                        if (hit != resample_cache_.end()) {
+                            tex_index = hit->second;  // same input/crop/size already resampled this tick
+                        } else {
+                            int src_tex = materialised_input(*in);
+                            int levels[2] = {hm.predecimate_levels(), vm.predecimate_levels()};
+                            int fac[2] = {1 << levels[0], 1 << levels[1]};
+                            int cur_w = in->tex.width, cur_h = in->tex.height;
+                            size_t cur_off = SIZE_MAX;  // SIZE_MAX: source is tex_table_[src_tex]
+                            if (fac[0] != 1 || fac[1] != 1) {
+                                int rwid = (cur_w + fac[0] - 1) / fac[0], rhei = (cur_h + fac[1] - 1) / fac[1];
+                                size_t off = frame_alloc((size_t)rwid * rhei * 8);
+                                dev::ResampleJob j{};
+                                j.box_fx = fac[0]; j.box_fy = fac[1];
+                                j.dst_w = rwid; j.dst_h = rhei; j.dst_f16 = 1; j.dst_pitch = rwid * 8;
+                                stage_jobs_[0].push_back(j);
+                                stage_frame_off_[0].push_back({SIZE_MAX, off});
+                                stage_src_tex_[0].push_back(src_tex);
+                                cur_w = rwid; cur_h = rhei; cur_off = off;
+                            }
+                            AxisMapping rh_ = hm.on_reduced_source(levels[0]), rv_ = vm.on_reduced_source(levels[1]);
+                            int np = plan_passes(rh_, rv_, passes);
+                            if (np == 0) { set_error("resampler planning failed"); return SMR_ERR_INVALID_ARGUMENT; }
+                            size_t dst_off = frame_alloc((size_t)dw * dh * 4);
+                            for (int pi = 0; pi < np; pi++) {
+                                const KernelPass &kp = passes[pi];
+                                bool last = pi == np - 1;
+                                WeightEntry we;
+                                smr_status st = get_weights(kp, we);
+                                if (st != SMR_OK) return st;
+                                dev::ResampleJob j{};
+                                j.axis = kp.mapping.axis; j.perp_offset = kp.perp_offset; j.taps = we.taps;
+                                j.weights = we.weights; j.inv_wsum = we.inv; j.first = we.first;
+                                j.box_fx = j.box_fy = 1;
+                                size_t out_off;
+                                if (last) {
+                                    j.dst_w = dw; j.dst_h = dh; j.dst_f16 = 0; j.dst_pitch = dw * 4;
+                                    out_off = dst_off;
+                                } else {
+                                    j.dst_w = kp.mapping.axis == 0 ? kp.mapping.dst_len : cur_w;  // output_size
+                                    j.dst_h = kp.mapping.axis == 1 ? kp.mapping.dst_len : cur_h;
+                                    j.dst_f16 = 1; j.dst_pitch = j.dst_w * 8;
+                                    out_off = frame_alloc((size_t)j.dst_w * j.dst_h * 8);
+                                }
+                                // f16 sources carry their geometry in the job; RGBA8/YUV sources come from the table
+                                if (cur_off != SIZE_MAX) {
+                                    j.src.kind = dev::TEX_F16; j.src.width = cur_w; j.src.height = cur_h; j.src.pitch0 = cur_w * 8;
+                                }
+                                int stage = last ? 2 : 1;
+                                stage_jobs_[stage].push_back(j);
+                                stage_frame_off_[stage].push_back({cur_off, out_off});
+                                stage_src_tex_[stage].push_back(cur_off == SIZE_MAX ? src_tex : -1);
+                                if (!last) { cur_w = j.dst_w; cur_h = j.dst_h; cur_off = out_off; }
+                            }
+                            dev::Tex t;
+                            t.kind = dev::TEX_RGBA8; t.width = dw; t.height = dh; t.pitch0 = dw * 4;
+                            tex_index = (int)tex_table_.size();
+                            tex_table_.push_back(t);
+                            tex_frame_off_.push_back(dst_off);
+                            resample_cache_[key] = tex_index;
+                        }
+                        tex_w = dw; tex_h = dh;
+                        l.crop = {0.0f, 0.0f, (float)dw, (float)dh};  // ResampledChild::output_crop
+                    }
+                }
+            }
+        }
+        dev::LayerDev d;
+        bool skip;
+        prepare_layer(l, W, H, tex_index, tex_w, tex_h, d, skip);
+        if (skip) continue;
+        d.mask_begin = (int)masks.size();
+        size_t nm = std::min<size_t>(l.masks.size(), SMR_MAX_MASKS);  // params.rs:284-294
+        for (size_t i = 0; i < nm; i++) {
+            const Mask &m = l.masks[i];
+            dev::MaskDev md;
+            md.radius[0] = m.radius.top_left; md.radius[1] = m.radius.top_right;
+            md.radius[2] = m.radius.bottom_right; md.radius[3] = m.radius.bottom_left;
+            md.top = m.top; md.left = m.left; md.width = m.width; md.height = m.height;
+            masks.push_back(md);
+        }
+        d.mask_count = (int)nm;
+        layers.push_back(d);
+    }
+
+    PendingComposite pc;
+    memset(&pc.job, 0, sizeof(pc.job));
+    pc.job.width = W; pc.job.height = H; pc.job.mode = mode;
+    pc.job.n_layers = (int)layers.size();
+    pc.layers_off = param_alloc(sizeof(dev::LayerDev) * std::max<size_t>(layers.size(), 1));
+    pc.masks_off = param_alloc(sizeof(dev::MaskDev) * std::max<size_t>(masks.size(), 1));
+    if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
+    if (!layers.empty()) memcpy(param_host_.data() + pc.layers_off, layers.data(), sizeof(dev::LayerDev) * layers.size());
+    if (!masks.empty()) memcpy(param_host_.data() + pc.masks_off, masks.data(), sizeof(dev::MaskDev) * masks.size());
+
+    bool same_size = (size_t)W == o.res.width && (size_t)H == o.res.height;
+    bool fusable = same_size && (o.format == SMR_OUT_RGBA8 || ((W % 2 == 0) && (H % 2 == 0)));
+    if (fusable) {
+        pc.job.out_format = o.format;
+        pc.job.out0 = dst[0]; pc.job.out1 = dst[1]; pc.job.out2 = dst[2];
+        pc.job.out_pitch0 = pitch[0]; pc.job.out_pitch1 = pitch[1]; pc.job.out_pitch2 = pitch[2];
+        composites_.push_back(pc);
+    } else {
+        if (o.format == SMR_OUT_RGBA8) { set_error("RGBA output must match the root layout resolution"); return SMR_ERR_UNSUPPORTED; }
+        size_t off = frame_alloc((size_t)W * H * 4);
+        pc.job.out_format = -1;
+        pc.job.out0 = (uint8_t *)(uintptr_t)off;  // frame offset, fixed up in render_begin
+        pc.job.out_pitch0 = W * 4;
+        pc.job.out1 = (uint8_t *)(uintptr_t)1;      // marker: out0 is a frame offset
+        composites_.push_back(pc);
+        dev::Tex t;
+        t.kind = dev::TEX_RGBA8; t.width = W; t.height = H; t.pitch0 = W * 4;
+        int ti = (int)tex_table_.size();
+        tex_table_.push_back(t);
+        tex_frame_off_.push_back(off);
+        push_output_job(ti, 0);
+    }
+    return SMR_OK;
+}
+
+smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,
+                                  uint32_t n_out) {
+    if ((n_in && !in) || (n_out && !out)) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (host_only_) { set_error("host-only handle (cuda_device = -1) cannot render: no CPU fallback"); return SMR_ERR_CUDA; }
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    if (in_flight_) { CUDA_OK(cudaStreamSynchronize(stream_)); in_flight_ = false; }
+    tick_++;
+    tex_table_.clear(); tex_frame_off_.clear();
+    for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
+    weight_jobs_.clear(); convert_jobs_.clear(); composites_.clear(); output_jobs_.clear(); output_src_tex_.clear();
+    fills_.clear(); d2h_.clear(); resample_cache_.clear();
+    param_used_ = 0; frame_used_ = 0;
+    uint64_t launches = 0;
+
+    // scene.register_render_event(pts, input_resolutions), state.rs:233-239
+    std::map<std::string, Resolution> res_map;
+    for (uint32_t i = 0; i < n_in; i++)
+        if (in[i].input_id) res_map[in[i].input_id] = {in[i].width, in[i].height};
+    scene_.register_render_event(pts, std::move(res_map));
+
+    smr_status st = populate_inputs(pts, in, n_in);
+    if (st != SMR_OK) return st;
+    for (uint32_t i = 0; i < n_out; i++) {
+        if (!out[i].output_id) return SMR_ERR_INVALID_ARGUMENT;
+        auto it = outputs_.find(out[i].output_id);
+        if (it == outputs_.end()) {
+            set_error(std::string("Output \"") + out[i].output_id + "\" does not exist, register it first");
+            return SMR_ERR_OUTPUT_NOT_REGISTERED;
+        }
+        st = plan_output(it->second, out[i], pts);
+        if (st != SMR_OK) return st;
+    }
+
+    // ---- resolve frame-arena addresses --------------------------------------------------------
+    CUDA_OK(frame_dev_.ensure(frame_used_ + 512));
+    uint8_t *fb = frame_dev_.p;
+    for (size_t i = 0; i < tex_table_.size(); i++)
+        if (tex_frame_off_[i] != SIZE_MAX) tex_table_[i].p0 = fb + tex_frame_off_[i];
+    for (int s = 0; s < 3; s++)
+        for (size_t i = 0; i < stage_jobs_[s].size(); i++) {
+            dev::ResampleJob &j = stage_jobs_[s][i];
+            if (stage_src_tex_[s][i] >= 0) j.src = tex_table_[stage_src_tex_[s][i]];
+            else j.src.p0 = fb + stage_frame_off_[s][i].first;
+            j.dst = fb + stage_frame_off_[s][i].second;
+        }
+    for (size_t i = 0; i < output_jobs_.size(); i++) output_jobs_[i].src = tex_table_[output_src_tex_[i]];
+
+    // ---- pack the parameter arena and ship it in one copy -------------------------------------
+    size_t tex_off = param_alloc(sizeof(dev::Tex) * std::max<size_t>(tex_table_.size(), 1));
+    size_t stage_off[3], wj_off;
+    for (int s = 0; s < 3; s++) stage_off[s] = param_alloc(sizeof(dev::ResampleJob) * std::max<size_t>(stage_jobs_[s].size(), 1));
+    wj_off = param_alloc(sizeof(dev::WeightJob) * std::max<size_t>(weight_jobs_.size(), 1));
+    if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
+    if (!tex_table_.empty()) memcpy(param_host_.data() + tex_off, tex_table_.data(), sizeof(dev::Tex) * tex_table_.size());
+    for (int s = 0; s < 3; s++)
+        if (!stage_jobs_[s].empty())
+            memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
+    if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
+    CUDA_OK(param_pinned_.ensure(param_used_));
+    CUDA_OK(param_dev_.ensure(param_used_));
+    memcpy(param_pinned_.p, param_host_.data(), param_used_);
+    CUDA_OK(cudaMemcpyAsync(param_dev_.p, param_pinned_.p, param_used_, cudaMemcpyHostToDevice, stream_));
+    uint8_t *pd = param_dev_.p;
+
+    // ---- launches -----------------------------------------------------------------------------
+    auto launched = [&](int n) -> bool { if (n < 0) return false; launches += (uint64_t)n; return true; };
+    for (auto &cj : convert_jobs_) {
+        const dev::Tex &src = tex_table_[cj.first];
+        if (!launched(dev::launch_convert_to_rgba(src, fb + cj.second, src.width * 4, stream_))) goto fail;
+    }
+    if (!launched(dev::launch_weights((const dev::WeightJob *)(pd + wj_off), weight_jobs_.data(), (int)weight_jobs_.size(), stream_))) goto fail;
+    for (int s = 0; s < 3; s++)
+        if (!launched(dev::launch_resample((const dev::ResampleJob *)(pd + stage_off[s]), stage_jobs_[s].data(),
+                                           (int)stage_jobs_[s].size(), stream_))) goto fail;
+    for (PendingComposite &pc : composites_) {
+        pc.job.layers = (const dev::LayerDev *)(pd + pc.layers_off);
+        pc.job.masks = (const dev::MaskDev *)(pd + pc.masks_off);
+        pc.job.textures = (const dev::Tex *)(pd + tex_off);
+        if (pc.job.out_format == -1 && pc.job.out1 == (uint8_t *)(uintptr_t)1) {
+            pc.job.out0 = fb + (size_t)(uintptr_t)pc.job.out0;
+            pc.job.out1 = nullptr;
+        }
+        if (!launched(dev::launch_composite(pc.job, stream_))) goto fail;
+    }
+    for (dev::OutputJob &oj : output_jobs_)
+        if (!launched(dev::launch_output(oj, stream_))) goto fail;
+    for (Fill &f : fills_)
+        if (!launched(dev::launch_fill_yuv(f.p[0], f.p[1], f.p[2], f.pitch[0], f.pitch[1], f.pitch[2], f.w, f.h, f.fmt,
+                                           f.yuv[0], f.yuv[1], f.yuv[2], stream_))) goto fail;
+    for (PendingCopy &c : d2h_)
+        CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, stream_));
+    stats_.kernel_launches += launches;
+    stats_.last_render_kernel_launches = launches;
+    stats_.frames_rendered += n_out;
+    in_flight_ = true;
+    return SMR_OK;
+fail:
+    set_error(dev::last_launch_error());
+    cudaStreamSynchronize(stream_);
+    return SMR_ERR_CUDA;
+}
+
+// inspection: what populate_inputs + register_render_event would record for this FrameSet (no copies)
+smr_status Renderer::debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in) {
+    if (n_in && !in) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    std::map<std::string, Resolution> res_map;
+    for (uint32_t i = 0; i < n_in; i++)
+        if (in[i].input_id) res_map[in[i].input_id] = {in[i].width, in[i].height};
+    scene_.register_render_event(pts, std::move(res_map));
+    for (auto &kv : inputs_) {
+        Input &I = kv.second;
+        I.has_frame = false;
+        for (uint32_t i = 0; i < n_in; i++) {
+            if (!in[i].input_id || kv.first != in[i].input_id) continue;
+            uint64_t lim = pts > opts_.stream_fallback_timeout_ns ? pts - opts_.stream_fallback_timeout_ns : 0;
+            if (lim > in[i].pts_ns) continue;
+            I.has_frame = true;
+            I.res = {in[i].width, in[i].height};
+        }
+    }
+    return SMR_OK;
+}
+
+smr_status Renderer::render_end() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!in_flight_) return SMR_OK;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    in_flight_ = false;
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    return SMR_OK;
+}
+
+smr_status Renderer::debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap,
+                                   uint32_t *n, uint32_t *rw, uint32_t *rh) {
+    if (!output_id || !n) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = outputs_.find(output_id);
+    if (it == outputs_.end()) { set_error("output not registered"); return SMR_ERR_OUTPUT_NOT_REGISTERED; }
+    Output &o = it->second;
+    *n = 0;
+    if (o.node.root_is_input) { if (rw) *rw = 0; if (rh) *rh = 0; return SMR_OK; }
+    OutputNode copy = o.node;  // do not advance Tiles::last_layout
+    std::vector<std::optional<Resolution>> child_res;
+    for (const std::string &id : copy.child_input_ids) {
+        auto ii = inputs_.find(id);
+        if (ii != inputs_.end() && ii->second.has_frame) child_res.push_back(ii->second.res);
+        else child_res.push_back(std::nullopt);
+    }
+    Resolution root = copy.layout_resolution(pts);
+    if (rw) *rw = (uint32_t)root.width;
+    if (rh) *rh = (uint32_t)root.height;
+    std::vector<RenderLayout> layouts = copy.layouts(pts, child_res).flatten(child_res, root);
+    *n = (uint32_t)layouts.size();
+    if (!out) return SMR_OK;
+    if (cap < layouts.size()) return SMR_ERR_BUFFER_TOO_SMALL;
+    for (size_t i = 0; i < layouts.size(); i++) {
+        const RenderLayout &l = layouts[i];
+        smr_render_layout &d = out[i];
+        memset(&d, 0, sizeof(d));
+        d.type = (int)l.kind;
+        d.top = l.top; d.left = l.left; d.width = l.width; d.height = l.height;
+        d.rotation_degrees = l.rotation_degrees;
+        d.border_radius[0] = l.border_radius.top_left; d.border_radius[1] = l.border_radius.top_right;
+        d.border_radius[2] = l.border_radius.bottom_right; d.border_radius[3] = l.border_radius.bottom_left;
+        d.color = {l.color.r, l.color.g, l.color.b, l.color.a};
+        d.border_color = {l.border_color.r, l.border_color.g, l.border_color.b, l.border_color.a};
+        d.border_width = l.border_width; d.blur_radius = l.blur_radius;
+        d.child_index = (int)l.index;
+        d.crop_top = l.crop.top; d.crop_left = l.crop.left; d.crop_width = l.crop.width; d.crop_height = l.crop.height;
+        d.masks_len = (int)std::min<size_t>(l.masks.size(), SMR_MAX_MASKS);
+        for (int m = 0; m < d.masks_len; m++) {
+            const Mask &mk = l.masks[m];
+            d.masks[m].radius[0] = mk.radius.top_left; d.masks[m].radius[1] = mk.radius.top_right;
+            d.masks[m].radius[2] = mk.radius.bottom_right; d.masks[m].radius[3] = mk.radius.bottom_left;
+            d.masks[m].top = mk.top; d.masks[m].left = mk.left; d.masks[m].width = mk.width; d.masks[m].height = mk.height;
+        }
+    }
+    return SMR_OK;
+}
+
+}  // namespace smr
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+struct smr_renderer {
+    smr::Renderer impl;
+    explicit smr_renderer(const smr_options &o) : impl(o) {}
+};
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+smr_status smr_create(const smr_options *opts, smr_renderer **out) {
+    if (!opts || !out) return SMR_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    smr_renderer *r = nullptr;
+    try { r = new smr_renderer(*opts); } catch (...) { return SMR_ERR_OUT_OF_MEMORY; }
+    smr_status st;
+    try { st = r->impl.init(); } catch (...) { st = SMR_ERR_OUT_OF_MEMORY; }
+    if (st != SMR_OK) {
+        g_create_error = r->impl.last_error();
+        delete r;
+        return st;
+    }
+    *out = r;
+    return SMR_OK;
+}
+
+void smr_destroy(smr_renderer *r) { delete r; }
+
+#define SMR_GUARD(call)                                                       \
+    if (!r) return SMR_ERR_INVALID_ARGUMENT;                                  \
+    try { return call; }                                                      \
+    catch (const std::bad_alloc &) { return SMR_ERR_OUT_OF_MEMORY; }          \
+    catch (...) { r->impl.set_error("internal error"); return SMR_ERR_INVALID_ARGUMENT; }
+
+smr_status smr_register_input(smr_renderer *r, const char *id) { SMR_GUARD(r->impl.register_input(id)) }
+smr_status smr_unregister_input(smr_renderer *r, const char *id) { SMR_GUARD(r->impl.unregister_input(id)) }
+smr_status smr_update_scene(smr_renderer *r, const char *output_id, uint32_t w, uint32_t h, int32_t fmt,
+                            const smr_component *root) { SMR_GUARD(r->impl.update_scene(output_id, w, h, fmt, root)) }
+smr_status smr_unregister_output(smr_renderer *r, const char *id) { SMR_GUARD(r->impl.unregister_output(id)) }
+smr_status smr_render_begin(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in,
+                            smr_output_frame *out, uint32_t n_out) { SMR_GUARD(r->impl.render_begin(pts, in, n_in, out, n_out)) }
+smr_status smr_render_end(smr_renderer *r) { SMR_GUARD(r->impl.render_end()) }
+smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,
+                      uint32_t n_out) {
+    if (!r) return SMR_ERR_INVALID_ARGUMENT;
+    smr_status st = smr_render_begin(r, pts, in, n_in, out, n_out);
+    if (st != SMR_OK) return st;
+    return smr_render_end(r);
+}
+smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap,
+                             uint32_t *n, uint32_t *rw, uint32_t *rh) { SMR_GUARD(r->impl.debug_layouts(output_id, pts, out, cap, n, rw, rh)) }
+smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in) { SMR_GUARD(r->impl.debug_set_inputs(pts, in, n_in)) }
+smr_status smr_get_stats(smr_renderer *r, smr_stats *out) {
+    if (!r || !out) return SMR_ERR_INVALID_ARGUMENT;
+    r->impl.stats(out);
+    return SMR_OK;
+}
+void *smr_cuda_stream(smr_renderer *r) { return r ? r->impl.stream() : nullptr; }
+const char *smr_last_error(smr_renderer *r) { return r ? r->impl.last_error() : g_create_error.c_str(); }
+const char *smr_version(void) { return "smelter_b200 0.1 (sm_100a)"; }
+
+smr_status smr_output_plane_sizes(uint32_t w, uint32_t h, int32_t fmt, size_t sizes[3]) {
+    if (!sizes) return SMR_ERR_INVALID_ARGUMENT;
+    if (fmt != SMR_OUT_PLANAR_YUV420 && fmt != SMR_OUT_RGBA8 && fmt != SMR_OUT_NV12) return SMR_ERR_UNSUPPORTED;
+    size_t rb[3], rows[3];
+    smr::out_plane_layout(fmt, w, h, rb, rows);
+    for (int i = 0; i < 3; i++) sizes[i] = rb[i] * rows[i];
+    return SMR_OK;
+}
+
+void smr_component_default(int32_t type, smr_component *c) {  // components.rs:289-347
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->type = type;
+    c->direction = SMR_DIRECTION_ROW;
+    c->overflow = SMR_OVERFLOW_HIDDEN;
+    c->rescale_mode = SMR_RESCALE_FIT;
+    c->horizontal_align = SMR_HALIGN_CENTER;
+    c->vertical_align = SMR_VALIGN_CENTER;
+    c->tile_aspect_ratio_w = 16;
+    c->tile_aspect_ratio_h = 9;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+"""Host logic (scene -> NestedLayout -> flatten) through the C ABI on a host-only handle
+(smr_options.cuda_device = -1).  Expected values are hand-derived from the reference's scene maths
+and render-test scenes (integration-tests/src/render_tests/{tiles,view,rescaler,transition}.rs).
+CPU-only."""
+import math
+
+import pytest
+
+import smelter_b200 as s
+from smelter_b200 import _ffi as F
+
+RES = s.Resolution(640, 360)
+BG = s.RGBAColor(0x33, 0x33, 0x33, 255)
+
+
+def host_renderer(mode=s.RenderingMode.GpuOptimized, **kw):
+    return s.Renderer(s.RendererOptions(rendering_mode=mode, cuda_device=-1, **kw))
+
+
+def inputs(n):
+    return [s.InputStreamComponent(input_id=f"input_{i}") for i in range(1, n + 1)]
+
+
+def setup(scene, n_inputs, res=RES, in_res=RES, pts=0.0, r=None):
+    r = r or host_renderer()
+    for i in range(1, n_inputs + 1):
+        r.register_input(f"input_{i}")
+    r.update_scene("output_1", res, s.OutputFrameFormat.PlanarYuv420Bytes, scene)
+    r.debug_set_inputs(pts, {f"input_{i}": in_res for i in range(1, n_inputs + 1)})
+    return r
+
+
+def rect(l):
+    return (l.left, l.top, l.width, l.height)
+
+
+def test_exports_every_declared_symbol():
+    L = F.lib()
+    for name in F.EXPORTS:
+        assert hasattr(L, name), name
+
+
+def test_header_and_ffi_agree_on_symbols():
+    import os, re
+    hdr = open(os.path.join(os.path.dirname(F._HERE), "include", "smelter_b200.h")).read()
+    declared = set(re.findall(r"\b(smr_[a-z_]+)\s*\(", hdr)) - {"smr_status"}
+    assert declared == set(F.EXPORTS), declared ^ set(F.EXPORTS)
+
+
+def test_render_without_gpu_fails_loudly():
+    r = host_renderer()
+    r.update_scene("output_1", RES, s.OutputFrameFormat.PlanarYuv420Bytes, s.ViewComponent())
+    with pytest.raises(s.RenderSceneError) as e:
+        r.render(s.FrameSet(pts=0.0))
+    assert e.value.status == 2  # SMR_ERR_CUDA: no CPU fallback
+
+
+def test_tiles_02_inputs():
+    """tiles.rs:85-95 (BASELINE config 1): two 320x180 tiles at (0,90) and (320,90), grey elsewhere."""
+    r = setup(s.TilesComponent(children=inputs(2), background_color=BG), 2)
+    ls, root = r.debug_layouts("output_1")
+    assert root == (640, 360)
+    assert [l.type for l in ls] == [1, 0, 0]
+    assert rect(ls[0]) == (0, 0, 640, 360) and (ls[0].color.r, ls[0].color.a) == (0x33, 255)
+    assert rect(ls[1]) == (0, 90, 320, 180) and ls[1].child_index == 0
+    assert rect(ls[2]) == (320, 90, 320, 180) and ls[2].child_index == 1
+    assert (ls[1].crop_left, ls[1].crop_top, ls[1].crop_width, ls[1].crop_height) == (0, 0, 640, 360)
+    assert ls[1].masks_len == 0
+
+
+@pytest.mark.parametrize("n,rows,cols", [(1, 1, 1), (2, 1, 2), (3, 2, 2), (4, 2, 2), (5, 2, 3), (15, 4, 4)])
+def test_tiles_grid_shape(n, rows, cols):
+    """tiles.rs:73-143: optimal_row_column_count for 16:9 tiles on a 16:9 output."""
+    r = setup(s.TilesComponent(children=inputs(n), background_color=BG), n)
+    ls, _ = r.debug_layouts("output_1")
+    tiles = [l for l in ls if l.type == 0]
+    assert len(tiles) == n
+    tw = 640 / cols
+    assert all(abs(t.width - tw) < 1e-3 and abs(t.height - tw * 9 / 16) < 1e-3 for t in tiles)
+    assert len({round(t.top, 2) for t in tiles}) == rows
+    # last row is centred (HorizontalAlign::Center default)
+    last = [t for t in tiles if abs(t.top - max(x.top for x in tiles)) < 1e-3]
+    used = len(last) * tw
+    assert abs(min(t.left for t in last) - (640 - used) / 2) < 1e-3
+
+
+def test_tiles_margin_and_padding():
+    """tiles.rs margin_and_padding_with_03_inputs flavour: tile_size / tiles_positions arithmetic."""
+    r = setup(s.TilesComponent(children=inputs(3), background_color=BG, margin=10.0, padding=5.0), 3)
+    ls, _ = r.debug_layouts("output_1")
+    tiles = [l for l in ls if l.type == 0]
+    # 2x2 grid: x_scale=(640-20-30)/2/16=18.4375, y_scale=(360-20-30)/2/9=17.2222 -> scale=17.2222
+    scale = (360 - 20 - 30) / 2 / 9
+    tw, th = 16 * scale, 9 * scale
+    assert abs(tiles[0].width - tw) < 1e-3 and abs(tiles[0].height - th) < 1e-3
+    add_x = 640 - (tw + 10) * 2 - 30
+    assert abs(tiles[0].left - (add_x / 2 + 15)) < 1e-3
+    assert abs(tiles[1].left - (add_x / 2 + 15 + tw + 20)) < 1e-3
+    assert abs(tiles[0].top - 15) < 1e-3  # additional_y == 0 for the limiting axis
+    add_x3 = 640 - (tw + 10) * 1 - 20
+    assert abs(tiles[2].left - (add_x3 / 2 + 15)) < 1e-3
+
+
+def test_tiles_portrait_input_is_fitted_into_tile():
+    """tiles_component/layout.rs:107-128 fit_into_tile: 360x640 input in a 640x360 tile."""
+    r = setup(s.TilesComponent(children=inputs(1), background_color=BG), 1, in_res=s.Resolution(360, 640))
+    ls, _ = r.debug_layouts("output_1")
+    t = [l for l in ls if l.type == 0][0]
+    assert abs(t.height - 360) < 1e-3 and abs(t.width - 202.5) < 1e-3 and abs(t.left - 218.75) < 1e-3
+
+
+def test_simple_pass_through_view():
+    """simple.rs:18-30: View{children:[InputStream]} -> one texture layout, mask removed as redundant."""
+    r = setup(s.ViewComponent(children=inputs(1)), 1)
+    ls, _ = r.debug_layouts("output_1")
+    assert len(ls) == 1 and ls[0].type == 0
+    assert rect(ls[0]) == (0, 0, 640, 360) and ls[0].masks_len == 0 and ls[0].border_width == 0
+
+
+def test_view_row_with_static_and_dynamic_children():
+    """view/layout.rs static_child_size: fixed 100 px + two flexible children share the rest."""
+    V = s.ViewComponent
+    kids = [V(position=s.Position.Static(width=100.0), background_color=s.RGBAColor(255, 0, 0, 255)),
+            V(background_color=s.RGBAColor(0, 255, 0, 255)), V(background_color=s.RGBAColor(0, 0, 255, 255))]
+    r = setup(V(children=kids, background_color=BG), 0)
+    ls, _ = r.debug_layouts("output_1")
+    cols = [l for l in ls if l.type == 1]
+    assert [rect(c) for c in cols] == [(0, 0, 640, 360), (0, 0, 100, 360), (100, 0, 270, 360), (370, 0, 270, 360)]
+
+
+def test_view_column_border_and_padding():
+    """view_component.rs:63-69 + layout.rs:129-160: border offsets children, padding adds to position."""
+    V = s.ViewComponent
+    child = V(position=s.Position.Static(height=50.0), background_color=s.RGBAColor(255, 0, 0, 255))
+    root = V(children=[child], direction=s.ViewChildrenDirection.Column, border_width=10.0,
+             border_color=s.RGBAColor(255, 255, 255, 255), padding=s.Padding(5, 6, 7, 8), background_color=BG)
+    r = setup(root, 0)
+    ls, _ = r.debug_layouts("output_1")
+    assert rect(ls[0]) == (0, 0, 640, 360) and ls[0].border_width == 10.0
+    # content = 620x340; child width = 620 - (6+8); top = border + padding.top; left = border + padding.left
+    assert rect(ls[1]) == (18, 15, 606, 50)
+    assert ls[1].masks_len == 0  # parent mask (10,10,620,340) contains the child -> dropped
+
+
+def test_view_absolute_child_and_overflow_mask():
+    V = s.ViewComponent
+    child = V(position=s.Position.Absolute(width=200.0, height=100.0, right=-50.0, bottom=20.0),
+              background_color=s.RGBAColor(255, 0, 0, 255))
+    r = setup(V(children=[child], background_color=BG), 0)
+    ls, _ = r.debug_layouts("output_1")
+    # left = 640 - (-50) - 200 = 490, top = 360 - 20 - 100 = 240; sticks out to the right -> mask kept
+    assert rect(ls[1]) == (490, 240, 200, 100)
+    assert ls[1].masks_len == 1
+    m = ls[1].masks[0]
+    assert (m.left, m.top, m.width, m.height) == (0, 0, 640, 360)
+
+
+def test_view_border_radius_box_shadow_order():
+    """flatten.rs:78-81: own shadows first, then [self, children shadows, children]."""
+    V = s.ViewComponent
+    sh = s.BoxShadow(offset_x=10, offset_y=20, blur_radius=8, color=s.RGBAColor(0, 0, 0, 255))
+    child = V(position=s.Position.Absolute(width=100.0, height=100.0, left=50.0, top=60.0),
+              background_color=s.RGBAColor(255, 0, 0, 255), border_radius=s.BorderRadius.new_with_radius(20.0),
+              box_shadow=[sh])
+    r = setup(V(children=[child], background_color=BG), 0)
+    ls, _ = r.debug_layouts("output_1")
+    assert [l.type for l in ls] == [1, 2, 1]
+    assert rect(ls[1]) == (60, 80, 100, 100) and ls[1].blur_radius == 8
+    assert list(ls[1].border_radius) == [24.0] * 4  # radius + blur/2, flatten.rs:354
+    assert list(ls[2].border_radius) == [20.0] * 4
+
+
+def test_rescaler_fit_and_fill():
+    """rescaler_component/layout.rs:14-57: 640x360 input into a 320x320 rescaler."""
+    for mode, exp in [(s.RescaleMode.Fit, (0, 70, 320, 180)), (s.RescaleMode.Fill, (-124.44444, 0, 568.8889, 320))]:
+        resc = s.RescalerComponent(child=inputs(1)[0], mode=mode,
+                                   position=s.Position.Absolute(width=320.0, height=320.0, left=0.0, top=0.0))
+        r = setup(s.ViewComponent(children=[resc], background_color=BG), 1)
+        ls, _ = r.debug_layouts("output_1")
+        tex = [l for l in ls if l.type == 0][0]
+        assert all(abs(a - b) < 1e-2 for a, b in zip(rect(tex), exp)), rect(tex)
+        if mode == s.RescaleMode.Fill:
+            assert tex.masks_len == 2  # root View mask + rescaler mask both cut the overflow
+
+
+def test_rescaler_align_and_border():
+    resc = s.RescalerComponent(child=inputs(1)[0], horizontal_align=s.HorizontalAlign.Right,
+                               vertical_align=s.VerticalAlign.Bottom, border_width=10.0,
+                               border_color=s.RGBAColor(255, 255, 255, 255),
+                               position=s.Position.Absolute(width=300.0, height=300.0, left=20.0, top=30.0))
+    r = setup(s.ViewComponent(children=[resc], background_color=BG), 1)
+    ls, _ = r.debug_layouts("output_1")
+    # position.with_border: 320x320 at (20,30); content 300x300; scale = 300/640; child 300x168.75 bottom-right
+    frame = [l for l in ls if l.type == 1 and l.border_width == 10.0][0]
+    assert rect(frame) == (20, 30, 320, 320)
+    tex = [l for l in ls if l.type == 0][0]
+    assert all(abs(a - b) < 1e-3 for a, b in zip(rect(tex), (30, 40 + 300 - 168.75, 300, 168.75)))
+
+
+def test_rescaler_scales_view_subtree():
+    """rescaler.rs:76-187: rescaling a View with fixed size scales borders/children through flatten_child."""
+    V = s.ViewComponent
+    inner = V(position=s.Position.Static(width=1280.0, height=720.0), background_color=s.RGBAColor(255, 0, 0, 255),
+              border_width=20.0, border_color=s.RGBAColor(255, 255, 255, 255),
+              children=[V(position=s.Position.Static(width=640.0), background_color=s.RGBAColor(0, 255, 0, 255))])
+    r = setup(s.RescalerComponent(child=inner), 0)
+    ls, _ = r.debug_layouts("output_1")
+    cols = [l for l in ls if l.type == 1]
+    # inner view external size = 1320x760 -> scale = min(640/1320, 360/760) = 0.47368
+    sc = min(640 / 1320, 360 / 760)
+    outer = [c for c in cols if c.border_width > 0][0]
+    assert abs(outer.width - 1320 * sc) < 1e-2 and abs(outer.border_width - 20 * sc) < 1e-3
+    green = [c for c in cols if c.color.g == 255][0]
+    assert abs(green.width - 640 * sc) < 1e-2
+
+
+def test_overflow_fit_scales_children():
+    V = s.ViewComponent
+    kids = [V(position=s.Position.Static(width=400.0, height=100.0), background_color=s.RGBAColor(255, 0, 0, 255)),
+            V(position=s.Position.Static(width=400.0, height=100.0), background_color=s.RGBAColor(0, 255, 0, 255))]
+    r = setup(V(children=kids, overflow=s.Overflow.Fit, background_color=BG), 0)
+    ls, _ = r.debug_layouts("output_1")
+    cols = [l for l in ls if l.type == 1]
+    assert rect(cols[1]) == (0, 0, 320, 80) and rect(cols[2]) == (320, 0, 320, 80)  # scale = 640/800
+
+
+def test_missing_input_is_culled_but_keeps_its_tile():
+    r = host_renderer()
+    for i in (1, 2):
+        r.register_input(f"input_{i}")
+    r.update_scene("output_1", RES, 0, s.TilesComponent(children=inputs(2), background_color=BG))
+    r.debug_set_inputs(0.0, {"input_1": RES})  # input_2 has no frame
+    ls, _ = r.debug_layouts("output_1")
+    # the empty child goes through fit_into_tile with 0x0 -> inf scale -> NaN geometry;
+    # should_render compares false on NaN so the layout survives flatten but rasterises nothing
+    tex = [l for l in ls if l.type == 0]
+    assert len(tex) == 2 and rect(tex[0]) == (0, 90, 320, 180)
+    assert math.isnan(tex[1].width) and math.isnan(tex[1].left)
+
+
+def test_stale_input_is_dropped():
+    """render_loop.rs:29-32: frame older than stream_fallback_timeout (3 s in the harness) is cleared."""
+    r = host_renderer()
+    r.register_input("input_1")
+    r.update_scene("output_1", RES, 0, s.TilesComponent(children=inputs(1), background_color=BG))
+    r.debug_set_inputs(10.0, {"input_1": RES}, frame_pts=6.9)
+    live = lambda: [l for l in r.debug_layouts("output_1", 10.0)[0] if l.type == 0 and not math.isnan(l.width)]
+    assert len(live()) == 0
+    r.debug_set_inputs(10.0, {"input_1": RES}, frame_pts=7.0)
+    assert len(live()) == 1
+
+
+def _transition_scene(width, transition=None):
+    return s.ViewComponent(background_color=BG, children=[
+        s.ViewComponent(id="box", position=s.Position.Absolute(width=width, height=100.0, left=0.0, top=0.0),
+                        background_color=s.RGBAColor(255, 0, 0, 255), transition=transition)])
+
+
+def test_linear_transition_midpoint_and_end():
+    """transition.rs:39-106: a 2 s linear width transition 100 -> 300 starting at the last render pts."""
+    r = setup(_transition_scene(100.0), 0)
+    r.debug_set_inputs(1.0, {})  # last render at pts = 1 s
+    r.update_scene("output_1", RES, 0, _transition_scene(300.0, s.Transition(duration=2.0)))
+    w = lambda pts: [l for l in r.debug_layouts("output_1", pts)[0] if l.color.r == 255][0].width
+    assert w(1.0) == 100.0 and abs(w(2.0) - 200.0) < 1e-3 and w(3.0) == 300.0 and w(9.0) == 300.0
+
+
+def test_cubic_bezier_transition_matches_reference_kat():
+    """cubic_bezier.rs:140-147: easing(0.294; .25,.1,.25,1) = 0.5014012915764126."""
+    r = setup(_transition_scene(100.0), 0)
+    r.debug_set_inputs(0.0, {})
+    tr = s.Transition(duration=1.0, interpolation_kind=s.InterpolationKind.CubicBezier(0.25, 0.1, 0.25, 1.0))
+    r.update_scene("output_1", RES, 0, _transition_scene(200.0, tr))
+    w = [l for l in r.debug_layouts("output_1", 0.294)[0] if l.color.r == 255][0].width
+    assert abs(w - (100.0 + 100.0 * 0.5014012915764126)) < 1e-4
+    tr2 = s.Transition(duration=1.0, interpolation_kind=s.InterpolationKind.CubicBezier(0.85, 0.0, 0.15, 1.0))
+    r2 = setup(_transition_scene(100.0), 0)
+    r2.debug_set_inputs(0.0, {})
+    r2.update_scene("output_1", RES, 0, _transition_scene(200.0, tr2))
+    w2 = [l for l in r2.debug_layouts("output_1", 0.5)[0] if l.color.r == 255][0].width
+    assert abs(w2 - 150.0) < 1e-4
+
+
+def test_bounce_transition():
+    r = setup(_transition_scene(100.0), 0)
+    r.debug_set_inputs(0.0, {})
+    r.update_scene("output_1", RES, 0, _transition_scene(200.0, s.Transition(1.0, s.InterpolationKind.Bounce)))
+    w = [l for l in r.debug_layouts("output_1", 0.5)[0] if l.color.r == 255][0].width
+    assert abs(w - (100 + 100 * (7.5625 * (0.5 - 1.5 / 2.75) ** 2 + 0.75))) < 1e-3
+
+
+def test_tiles_transition_moves_tiles():
+    """tiles_transitions.rs flavour: adding an input re-flows the tiles; ids keep tiles matched."""
+    def scene(n, tr=None):
+        kids = [s.InputStreamComponent(input_id=f"input_{i}", id=f"c{i}") for i in range(1, n + 1)]
+        return s.TilesComponent(id="tiles", children=kids, background_color=BG, transition=tr)
+    r = host_renderer()
+    for i in (1, 2):
+        r.register_input(f"input_{i}")
+    r.update_scene("output_1", RES, 0, scene(1))
+    r.debug_set_inputs(0.0, {"input_1": RES, "input_2": RES})
+    r.update_scene("output_1", RES, 0, scene(2, s.Transition(duration=1.0)))
+    mid = [l for l in r.debug_layouts("output_1", 0.5)[0] if l.type == 0]
+    # tile c1 travels from (0,0,640,360) to (0,90,320,180); c2 is new and its slot was not occupied -> hidden until the end?
+    # (start has a tile at a different position, so the new tile is not shown during the transition)
+    c1 = [l for l in mid if l.child_index == 0][0]
+    assert rect(c1) == (0, 45, 480, 270)
+    assert len(mid) == 1
+    end = [l for l in r.debug_layouts("output_1", 1.0)[0] if l.type == 0]
+    assert [rect(l) for l in end] == [(0, 90, 320, 180), (320, 90, 320, 180)]
+
+
+def test_duplicate_component_ids_are_rejected():
+    r = host_renderer()
+    V = s.ViewComponent
+    with pytest.raises(s.UpdateSceneError) as e:
+        r.update_scene("output_1", RES, 0, V(id="a", children=[V(id="a")]))
+    assert e.value.status == 4 and "More than one component" in str(e.value)
+
+
+def test_unsupported_component_is_reported():
+    class Shader:
+        component_type = F.COMPONENT_SHADER
+        id = None
+    r = host_renderer()
+    with pytest.raises(s.UpdateSceneError) as e:
+        r.update_scene("output_1", RES, 0, s.ViewComponent(children=[Shader()]))
+    assert e.value.status == 5
+
+
+def test_max_layouts_and_masks_constants():
+    assert F.MAX_MASKS == 20
+    assert s.RendererOptions().max_layouts_count == 100
