@@ -132,6 +132,25 @@ def rgba_to_nv12(rgba):
     return y, uv
 
 
+def rgba_to_yuv420_scaled(rgba, w, h):
+    rgba = _u8(rgba)
+    sh, sw = rgba.shape[:2]
+    y = np.empty((h, w), np.uint8)
+    u = np.empty((h // 2, w // 2), np.uint8)
+    v = np.empty((h // 2, w // 2), np.uint8)
+    lib().orc_rgba_to_yuv420_scaled(_p(rgba), sw, sh, w, h, _p(y), _p(u), _p(v))
+    return y, u, v
+
+
+def rgba_to_nv12_scaled(rgba, w, h):
+    rgba = _u8(rgba)
+    sh, sw = rgba.shape[:2]
+    y = np.empty((h, w), np.uint8)
+    uv = np.empty((h // 2, w // 2, 2), np.uint8)
+    lib().orc_rgba_to_nv12_scaled(_p(rgba), sw, sh, w, h, _p(y), _p(uv))
+    return y, uv
+
+
 def rgb_to_yuv_bytes(r, g, b):
     out = (C.c_uint8 * 3)()
     lib().orc_rgb_to_yuv_bytes(r, g, b, out)

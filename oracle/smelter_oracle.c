@@ -231,40 +231,52 @@ static inline float to_v(const float c[3]) {
     return fmaf(v + 0.5f, 0.87843137254f, K16);
 }
 
-static void rgba_to_y_plane(const uint8_t *rgba, int w, int h, uint8_t *y) {
+/* The converters draw a full-screen quad into planes of the OUTPUT size and sample the root texture
+ * with the linear sampler, so a root whose size differs from the output is rescaled here
+ * (render_loop.rs:68-73, output_texture.rs:49-58). */
+static void rgba_to_y_plane(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y) {
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < h; py++)
         for (int px = 0; px < w; px++) {
             float c[3];
-            sample_rgb_raw(rgba, w, h, ((float)px + 0.5f) / (float)w, ((float)py + 0.5f) / (float)h, c);
+            sample_rgb_raw(rgba, sw, sh, ((float)px + 0.5f) / (float)w, ((float)py + 0.5f) / (float)h, c);
             y[(size_t)py * w + px] = orc_unorm8(to_y(c));
         }
 }
 
-void orc_rgba_to_yuv420(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v) {
+void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *u,
+                               uint8_t *v) {
     int cw = w / 2, ch = h / 2;
-    rgba_to_y_plane(rgba, w, h, y);
+    rgba_to_y_plane(rgba, sw, sh, w, h, y);
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < ch; py++)
         for (int px = 0; px < cw; px++) {
             float c[3];
-            sample_rgb_raw(rgba, w, h, ((float)px + 0.5f) / (float)cw, ((float)py + 0.5f) / (float)ch, c);
+            sample_rgb_raw(rgba, sw, sh, ((float)px + 0.5f) / (float)cw, ((float)py + 0.5f) / (float)ch, c);
             u[(size_t)py * cw + px] = orc_unorm8(to_u(c));
             v[(size_t)py * cw + px] = orc_unorm8(to_v(c));
         }
 }
 
-void orc_rgba_to_nv12(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *uv) {
+void orc_rgba_to_nv12_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *uv) {
     int cw = w / 2, ch = h / 2;
-    rgba_to_y_plane(rgba, w, h, y);
+    rgba_to_y_plane(rgba, sw, sh, w, h, y);
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < ch; py++)
         for (int px = 0; px < cw; px++) {
             float c[3];
-            sample_rgb_raw(rgba, w, h, ((float)px + 0.5f) / (float)cw, ((float)py + 0.5f) / (float)ch, c);
+            sample_rgb_raw(rgba, sw, sh, ((float)px + 0.5f) / (float)cw, ((float)py + 0.5f) / (float)ch, c);
             uv[((size_t)py * cw + px) * 2 + 0] = orc_unorm8(to_u(c));
             uv[((size_t)py * cw + px) * 2 + 1] = orc_unorm8(to_v(c));
         }
+}
+
+void orc_rgba_to_yuv420(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v) {
+    orc_rgba_to_yuv420_scaled(rgba, w, h, w, h, y, u, v);
+}
+
+void orc_rgba_to_nv12(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *uv) {
+    orc_rgba_to_nv12_scaled(rgba, w, h, w, h, y, uv);
 }
 
 void orc_rgb_to_yuv_bytes(uint8_t r, uint8_t g, uint8_t b, uint8_t out[3]) {

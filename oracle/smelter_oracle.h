@@ -80,6 +80,10 @@ void orc_argb_to_rgba(const uint8_t *argb, int w, int h, uint8_t *rgba);
 /* --- K10/K11: output conversion (rgba_to_yuv.wgsl:26-54, rgba_to_nv12.wgsl:25-52) -------- */
 void orc_rgba_to_yuv420(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v);
 void orc_rgba_to_nv12(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *uv);
+/* same converters when the root texture (sw x sh) is not the output size (w x h) */
+void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *u,
+                               uint8_t *v);
+void orc_rgba_to_nv12_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *uv);
 /* RGBColor::to_yuv (scene/types.rs:28-42) stored through an R8Unorm target; black-frame fill
  * of render_loop.rs:127-139 */
 void orc_rgb_to_yuv_bytes(uint8_t r, uint8_t g, uint8_t b, uint8_t out_yuv[3]);

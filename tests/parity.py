@@ -1,0 +1,128 @@
+"""Shared parity harness: run a scene through the product (C ABI -> sm_100a kernels) and through the
+CPU oracle on the same inputs, return both outputs.  Test infrastructure (imports oracle/)."""
+import numpy as np
+
+import smelter_b200 as s
+from oracle import oracle as orc
+
+OUTPUT_ID = "output_1"
+
+
+def leaf_inputs(comp):
+    """DFS order of InputStream leaves == node children order (scene/layout.rs:95-103)."""
+    if isinstance(comp, s.InputStreamComponent):
+        return [comp.input_id]
+    if isinstance(comp, s.RescalerComponent):
+        return leaf_inputs(comp.child) if comp.child is not None else []
+    out = []
+    for c in getattr(comp, "children", []):
+        out += leaf_inputs(c)
+    return out
+
+
+def to_oracle_layout(l):
+    masks = [(tuple(l.masks[i].radius), l.masks[i].top, l.masks[i].left, l.masks[i].width, l.masks[i].height)
+             for i in range(l.masks_len)]
+    return orc.make_layout(l.type, l.top, l.left, l.width, l.height, l.rotation_degrees, tuple(l.border_radius),
+                           (l.color.r, l.color.g, l.color.b, l.color.a),
+                           (l.border_color.r, l.border_color.g, l.border_color.b, l.border_color.a),
+                           l.border_width, l.blur_radius, l.child_index,
+                           (l.crop_top, l.crop_left, l.crop_width, l.crop_height), masks)
+
+
+def node_texture(frame: s.Frame):
+    """K1/K2/K4 through the oracle."""
+    d = frame.data
+    w, h = frame.resolution.width, frame.resolution.height
+    if d.kind == "PlanarYuv420":
+        return orc.yuv420_to_rgba(*d.planes, w, h)
+    if d.kind == "PlanarYuvJ420":
+        return orc.yuv420_to_rgba(*d.planes, w, h, full_range=True)
+    if d.kind == "Nv12":
+        return orc.nv12_to_rgba(d.planes[0], d.planes[1], w, h)
+    if d.kind == "Bgra":
+        return orc.bgra_to_rgba(d.planes[0], w, h)
+    if d.kind == "Argb":
+        return orc.argb_to_rgba(d.planes[0], w, h)
+    if d.kind == "Rgba8":
+        return np.ascontiguousarray(d.planes[0], np.uint8).reshape(h, w, 4)
+    raise ValueError(d.kind)
+
+
+def oracle_output(renderer, scene, frames, resolution, out_format, mode, pts, live_inputs=None):
+    """Expected output planes from the oracle, fed with the layouts the product flattened."""
+    live = frames if live_inputs is None else {k: v for k, v in frames.items() if k in live_inputs}
+    if isinstance(scene, s.InputStreamComponent):
+        fr = live.get(scene.input_id)
+        if fr is None:
+            return black(resolution, out_format)
+        rgba = node_texture(fr)
+    else:
+        layouts, (rw, rh) = renderer.debug_layouts(OUTPUT_ID, pts)
+        if rw == 0 or rh == 0:
+            return black(resolution, out_format)
+        nodes = [node_texture(live[i]) if i in live else None for i in leaf_inputs(scene)]
+        layouts = [to_oracle_layout(l) for l in layouts]
+        rgba = orc.render_layout_node(rw, rh, layouts, nodes, mode=mode, max_layouts=renderer.opts.max_layouts_count)
+    W, H = resolution.width, resolution.height
+    if out_format == s.OutputFrameFormat.RgbaWgpuTexture:
+        assert rgba.shape[:2] == (H, W)
+        return (rgba,)
+    if out_format == s.OutputFrameFormat.Nv12WgpuTexture:
+        return orc.rgba_to_nv12_scaled(rgba, W, H)
+    return orc.rgba_to_yuv420_scaled(rgba, W, H)
+
+
+def black(resolution, out_format):
+    W, H = resolution.width, resolution.height
+    y, u, v = orc.rgb_to_yuv_bytes(0, 0, 0)
+    if out_format == s.OutputFrameFormat.RgbaWgpuTexture:
+        return (np.zeros((H, W, 4), np.uint8),)
+    if out_format == s.OutputFrameFormat.Nv12WgpuTexture:
+        uv = np.empty((H // 2, W // 2, 2), np.uint8)
+        uv[..., 0], uv[..., 1] = u, v
+        return (np.full((H, W), y, np.uint8), uv)
+    return (np.full((H, W), y, np.uint8), np.full((H // 2, W // 2), u, np.uint8), np.full((H // 2, W // 2), v, np.uint8))
+
+
+def product_planes(frame: s.Frame):
+    return tuple(np.asarray(p) for p in frame.data.planes)
+
+
+def run_case(scene, frames, resolution=s.Resolution(640, 360), out_format=s.OutputFrameFormat.PlanarYuv420Bytes,
+             mode=s.RenderingMode.GpuOptimized, pts=0.0, renderer=None, updates=None, max_layouts=100):
+    """frames: {input_id: Frame}.  Returns (product planes, oracle planes, renderer)."""
+    r = renderer or s.Renderer(s.RendererOptions(rendering_mode=mode, max_layouts_count=max_layouts))
+    if renderer is None:
+        for iid in frames:
+            r.register_input(iid)
+        r.update_scene(OUTPUT_ID, resolution, out_format, scene)
+    fs = s.FrameSet(frames=dict(frames), pts=pts)
+    out = r.render(fs)
+    got = product_planes(out.frames[OUTPUT_ID])
+    timeout = r.opts.stream_fallback_timeout
+    live = {k for k, f in frames.items() if not (max(pts - timeout, 0.0) > f.pts)}
+    exp = oracle_output(r, scene, frames, resolution, out_format, mode, pts, live_inputs=live)
+    return got, exp, r
+
+
+def assert_identical(got, exp, what=""):
+    assert len(got) == len(exp)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        g = np.asarray(g).reshape(np.asarray(e).shape)
+        if not np.array_equal(g, e):
+            d = np.abs(g.astype(int) - np.asarray(e).astype(int))
+            idx = np.unravel_index(np.argmax(d), d.shape)
+            raise AssertionError(f"{what} plane {i}: {np.count_nonzero(d)} / {d.size} bytes differ, max |d|={d.max()} "
+                                 f"at {idx}: got {g[idx]} expected {np.asarray(e)[idx]}")
+
+
+def yuv_frame(planes, w, h, pts=0.0):
+    y, u, v = planes
+    return s.Frame(s.FrameData.PlanarYuv420(s.YuvPlanes(y, u, v)), s.Resolution(w, h), pts)
+
+
+def nv12_frame(planes, w, h, pts=0.0):
+    y, u, v = planes
+    uv = np.stack([u, v], axis=-1)
+    return s.Frame(s.FrameData.Nv12(s.NvPlanes(y, uv)), s.Resolution(w, h), pts)

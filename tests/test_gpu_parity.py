@@ -1,0 +1,318 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, BIT-EXACT on every
+output byte, on scenes re-typed from the reference's render tests
+(integration-tests/src/render_tests/{simple,tiles,view,rescaler,transition}.rs) with the reference's
+procedural inputs (harness/input.rs).  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+
+import smelter_b200 as s
+from tests import harness
+from tests.parity import OUTPUT_ID, assert_identical, nv12_frame, run_case, yuv_frame
+
+pytestmark = pytest.mark.gpu
+
+RES = s.Resolution(640, 360)
+BG = s.RGBAColor(0x33, 0x33, 0x33, 255)
+V = s.ViewComponent
+YUV = s.OutputFrameFormat.PlanarYuv420Bytes
+NV12 = s.OutputFrameFormat.Nv12WgpuTexture
+RGBA = s.OutputFrameFormat.RgbaWgpuTexture
+
+
+def inputs(n, w=640, h=360):
+    return {f"input_{i}": yuv_frame(harness.test_input(i, w, h), w, h) for i in range(1, n + 1)}
+
+
+def streams(n):
+    return [s.InputStreamComponent(input_id=f"input_{i}") for i in range(1, n + 1)]
+
+
+def check(scene, frames, **kw):
+    got, exp, r = run_case(scene, frames, **kw)
+    assert_identical(got, exp, type(scene).__name__)
+    return r
+
+
+def test_library_is_the_cuda_path():
+    r = s.Renderer()
+    assert r.cuda_stream() is not None
+    st = r.stats()
+    assert st["kernel_launches"] == 0
+
+
+def test_simple_input_pass_through():
+    """simple.rs:18-30"""
+    r = check(V(children=streams(1)), inputs(1))
+    assert r.stats()["last_render_kernel_launches"] >= 1
+
+
+@pytest.mark.parametrize("fmt", [YUV, NV12, RGBA])
+def test_tiles_02_inputs_all_output_formats(fmt):
+    """tiles.rs:85-95 == BASELINE config 1 (2:1 Lanczos3, 13 taps/axis)"""
+    check(s.TilesComponent(children=streams(2), background_color=BG), inputs(2), out_format=fmt)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 15])
+def test_tiles_n_inputs(n):
+    """tiles.rs:73-143"""
+    check(s.TilesComponent(children=streams(n), background_color=BG), inputs(n))
+
+
+def test_tiles_portrait_inputs_with_margin_and_padding():
+    """tiles.rs portrait + margin/padding cases: non-integer tile geometry -> fractional Lanczos phases"""
+    fr = {f"input_{i}": yuv_frame(harness.test_input(i, 360, 640), 360, 640) for i in range(1, 4)}
+    check(s.TilesComponent(children=streams(3), background_color=BG, tile_aspect_ratio=(1, 2), margin=7.0,
+                           padding=3.0, horizontal_align=s.HorizontalAlign.Left,
+                           vertical_align=s.VerticalAlign.Top), fr)
+
+
+def test_nv12_input_and_output():
+    fr = {f"input_{i}": nv12_frame(harness.smooth_yuv420(i, 640, 360), 640, 360) for i in range(1, 5)}
+    check(s.TilesComponent(children=streams(4), background_color=BG), fr, out_format=NV12)
+
+
+def test_full_range_j420_input():
+    y, u, v = harness.random_yuv420(7, 320, 180)
+    fr = {"input_1": s.Frame(s.FrameData.PlanarYuvJ420(s.YuvPlanes(y, u, v)), s.Resolution(320, 180))}
+    check(V(children=streams(1), background_color=BG), fr, resolution=s.Resolution(320, 180))
+
+
+def test_random_noise_input_2to1():
+    """white-noise planes exercise every rounding boundary of K1 / Lanczos / K10"""
+    fr = {f"input_{i}": yuv_frame(harness.random_yuv420(100 + i, 640, 360), 640, 360) for i in range(1, 5)}
+    check(s.TilesComponent(children=streams(4), background_color=BG), fr)
+
+
+def test_root_input_stream_same_size_and_rescaled():
+    """pass-through root (BASELINE `single_video_pass_through`): K1 -> K10 only; a root whose size differs
+    from the output is stretched by the converter's sampler (render_loop.rs:68-73)"""
+    fr = inputs(1)
+    check(s.InputStreamComponent(input_id="input_1"), fr)
+    check(s.InputStreamComponent(input_id="input_1"), fr, resolution=s.Resolution(320, 200))
+    check(s.InputStreamComponent(input_id="input_1"), fr, resolution=s.Resolution(854, 480), out_format=NV12)
+
+
+def test_missing_frame_gives_black_and_culls_layer():
+    """render_loop.rs:24-32,127-139"""
+    r = s.Renderer()
+    r.register_input("input_1")
+    r.update_scene(OUTPUT_ID, RES, YUV, s.InputStreamComponent(input_id="input_1"))
+    out = r.render(s.FrameSet(pts=0.0)).frames[OUTPUT_ID]
+    y, u, v = out.data.planes
+    assert np.all(y == 16) and np.all(u == 128) and np.all(v == 128)
+    # missing input inside Tiles: slot reserved, nothing drawn there
+    fr = inputs(1)
+    r2 = s.Renderer()
+    for i in (1, 2):
+        r2.register_input(f"input_{i}")
+    scene = s.TilesComponent(children=streams(2), background_color=BG)
+    r2.update_scene(OUTPUT_ID, RES, YUV, scene)
+    got, exp, _ = run_case(scene, fr, renderer=r2)
+    assert_identical(got, exp, "tiles with a missing input")
+
+
+def test_stale_frame_is_dropped():
+    fr = {"input_1": yuv_frame(harness.test_input(1), 640, 360, pts=1.0)}
+    scene = s.TilesComponent(children=streams(1), background_color=BG)
+    got, exp, _ = run_case(scene, fr, pts=4.5)  # 4.5 - 3.0 > 1.0 -> stale
+    assert_identical(got, exp, "stale")
+    assert len(np.unique(got[0])) == 1  # only the background
+
+
+def test_view_background_borders_radius_shadow():
+    """view.rs border_radius / border_width / box_shadow cases"""
+    sh = [s.BoxShadow(offset_x=12.0, offset_y=18.0, blur_radius=20.0, color=s.RGBAColor(0, 0, 0, 200)),
+          s.BoxShadow(offset_x=-15.0, offset_y=-10.0, blur_radius=6.0, color=s.RGBAColor(0, 255, 0, 255))]
+    child = V(position=s.Position.Absolute(width=300.0, height=180.0, left=150.0, top=80.0),
+              background_color=s.RGBAColor(255, 0, 0, 255), border_radius=s.BorderRadius(50.0, 10.0, 30.0, 0.0),
+              border_width=12.0, border_color=s.RGBAColor(255, 255, 255, 180), box_shadow=sh)
+    check(V(children=[child], background_color=BG), {})
+
+
+def test_view_video_child_with_radius_border_and_overflow_mask():
+    """view.rs: rounded video with border inside a rounded, padded parent (nested masks, asymmetric radii)"""
+    inner = V(children=streams(1), position=s.Position.Static(width=320.0, height=180.0),
+              border_radius=s.BorderRadius(40.0, 8.0, 24.0, 60.0), border_width=6.0,
+              border_color=s.RGBAColor(255, 255, 0, 255))
+    outer = V(children=[inner], position=s.Position.Absolute(width=400.0, height=260.0, left=120.0, top=50.0),
+              border_radius=s.BorderRadius(80.0, 20.0, 50.0, 10.0), padding=s.Padding(10, 10, 10, 120),
+              background_color=s.RGBAColor(0, 0, 255, 128))
+    check(V(children=[outer], background_color=BG), inputs(1))
+
+
+def test_semi_transparent_overlay_and_zorder():
+    """view.rs:514-574 absolute children over siblings + alpha overlay (BASELINE config 3 ingredients)"""
+    kids = [s.RescalerComponent(child=streams(2)[0]), ]
+    over = V(position=s.Position.Absolute(width=400.0, height=120.0, left=60.0, bottom=30.0),
+             background_color=s.RGBAColor(20, 40, 200, 110), border_radius=s.BorderRadius.new_with_radius(30.0))
+    over2 = V(position=s.Position.Absolute(width=200.0, height=200.0, right=20.0, top=20.0),
+              children=[s.RescalerComponent(child=streams(2)[1])], border_width=4.0,
+              border_color=s.RGBAColor(255, 255, 255, 255))
+    check(V(children=kids + [over, over2], background_color=BG), inputs(2))
+
+
+@pytest.mark.parametrize("mode_fit", [s.RescaleMode.Fit, s.RescaleMode.Fill])
+def test_rescaler_modes_and_alignment(mode_fit):
+    """rescaler.rs fit/fill with alignment, border, radius, shadow"""
+    resc = s.RescalerComponent(child=streams(1)[0], mode=mode_fit, horizontal_align=s.HorizontalAlign.Right,
+                               vertical_align=s.VerticalAlign.Top, border_width=8.0,
+                               border_color=s.RGBAColor(255, 0, 255, 255),
+                               border_radius=s.BorderRadius.new_with_radius(36.0),
+                               box_shadow=[s.BoxShadow(8.0, 8.0, 12.0, s.RGBAColor(0, 0, 0, 255))],
+                               position=s.Position.Absolute(width=300.0, height=260.0, left=170.0, top=50.0))
+    check(V(children=[resc], background_color=BG), inputs(1))
+
+
+def test_rescaler_upscale_and_view_subtree():
+    """rescaler.rs:76-187: a View subtree rescaled (scale propagates through flatten_child), incl. an
+    upscaled video (kernel_scale = 1, 7 taps)"""
+    inner = V(position=s.Position.Static(width=320.0, height=180.0), background_color=s.RGBAColor(200, 30, 30, 255),
+              border_width=10.0, border_color=s.RGBAColor(250, 250, 250, 255), direction=s.ViewChildrenDirection.Row,
+              children=[V(children=streams(1), position=s.Position.Static(width=160.0)),
+                        V(background_color=s.RGBAColor(0, 200, 0, 255))])
+    fr = {"input_1": yuv_frame(harness.test_input(1, 160, 90), 160, 90)}
+    check(s.RescalerComponent(child=inner), fr)
+
+
+def test_scaling_filter_lanczos3_multiscale_grid():
+    """rescaler.rs:838-859 at a reduced size: multiscale grid, 3:1 (19 taps, no box pre-pass)"""
+    w, h = 1920, 1080
+    fr = {"input_1": yuv_frame(harness.multiscale_grid(w, h), w, h)}
+    check(s.RescalerComponent(child=streams(1)[0]), fr, resolution=s.Resolution(640, 360))
+
+
+def test_box_predecimation_above_4x():
+    """resampler.rs:56-58: 1920 -> 300 is 6.4:1 -> one 2x box level, then Lanczos on the reduced source;
+    the other axis (1080 -> 270 = 4:1) stays unreduced"""
+    w, h = 1920, 1080
+    fr = {"input_1": yuv_frame(harness.smooth_yuv420(3, w, h), w, h)}
+    resc = s.RescalerComponent(child=V(children=streams(1), position=s.Position.Static(width=1920.0, height=1080.0)),
+                               mode=s.RescaleMode.Fill,
+                               position=s.Position.Absolute(width=300.0, height=270.0, left=20.0, top=20.0))
+    # Fill keeps aspect; use a plain View with explicit stretch instead to get anisotropic ratios
+    stretch = V(children=[s.InputStreamComponent(input_id="input_1")], overflow=s.Overflow.Fit,
+                position=s.Position.Absolute(width=300.0, height=270.0, left=20.0, top=20.0))
+    check(V(children=[resc], background_color=BG), fr)
+    check(V(children=[stretch], background_color=BG), fr)
+
+
+@pytest.mark.parametrize("pts", [0.25, 0.5, 0.9])
+def test_transition_fractional_geometry(pts):
+    """transition.rs: mid-transition layouts have fractional position and size -> non-trivial resample
+    phases and K9 bilinear taps"""
+    def scene(w, left, tr=None):
+        return V(background_color=BG, children=[
+            s.RescalerComponent(id="r", child=streams(1)[0], transition=tr,
+                                position=s.Position.Absolute(width=w, height=w * 9 / 16, left=left, top=33.0))])
+    r = s.Renderer()
+    r.register_input("input_1")
+    r.update_scene(OUTPUT_ID, RES, YUV, scene(200.0, 10.0))
+    fr = inputs(1)
+    run_case(scene(200.0, 10.0), fr, renderer=r, pts=0.0)
+    sc2 = scene(517.0, 101.0, s.Transition(duration=1.0, interpolation_kind=s.InterpolationKind.CubicBezier(0.25, 0.1, 0.25, 1.0)))
+    r.update_scene(OUTPUT_ID, RES, YUV, sc2)
+    got, exp, _ = run_case(sc2, fr, renderer=r, pts=pts)
+    assert_identical(got, exp, f"transition pts={pts}")
+
+
+def test_rotated_absolute_child():
+    """apply_layouts.wgsl:95-157 rotation path (no reference snapshot uses it; oracle = NC-7)"""
+    child = V(position=s.Position.Absolute(width=260.0, height=120.0, left=190.0, top=110.0, rotation_degrees=27.0),
+              background_color=s.RGBAColor(30, 200, 120, 230), border_radius=s.BorderRadius.new_with_radius(25.0),
+              border_width=5.0, border_color=s.RGBAColor(255, 255, 255, 255))
+    vid = V(position=s.Position.Absolute(width=160.0, height=90.0, left=40.0, top=40.0, rotation_degrees=-12.5),
+            children=streams(1))
+    fr = {"input_1": yuv_frame(harness.test_input(4, 160, 90), 160, 90)}
+    check(V(children=[child, vid], background_color=BG), fr)
+
+
+def test_cpu_optimized_mode_bilinear():
+    """rescaler.rs:814-836 scaling_filter_bilinear + BASELINE config 2 semantics: gamma-space blend,
+    bilinear scaling inside K9, no resampler"""
+    fr = {f"input_{i}": nv12_frame(harness.smooth_yuv420(20 + i, 640, 360), 640, 360) for i in range(1, 5)}
+    over = V(position=s.Position.Absolute(width=300.0, height=100.0, left=170.0, top=130.0),
+             background_color=s.RGBAColor(255, 255, 255, 90), border_radius=s.BorderRadius.new_with_radius(18.0))
+    scene = V(background_color=BG, children=[s.TilesComponent(children=streams(4), background_color=BG), over])
+    check(scene, fr, mode=s.RenderingMode.CpuOptimized, out_format=NV12)
+
+
+def test_bgra_argb_inputs_reference_kat():
+    """pixel_input_format_tests.rs:31-152 through the real CUDA path (RGBA texture output, exact)"""
+    data = np.arange(1, 65, dtype=np.uint8)
+    for kind, perm in (("Bgra", (2, 1, 0, 3)), ("Argb", (1, 2, 3, 0))):
+        fd = getattr(s.FrameData, kind)(data)
+        fr = {"input": s.Frame(fd, s.Resolution(8, 2))}
+        r = s.Renderer()
+        r.register_input("input")
+        r.update_scene(OUTPUT_ID, s.Resolution(8, 2), RGBA, V(children=[s.InputStreamComponent(input_id="input")]))
+        out = r.render(s.FrameSet(frames=fr, pts=0.0)).frames[OUTPUT_ID].data.planes[0]
+        exp = data.reshape(16, 4)[:, perm]
+        assert np.array_equal(out.reshape(16, 4), exp)
+
+
+def test_yuv_uniform_color_reference_kat():
+    """yuv_tests.rs:83-132 through the CUDA path"""
+    from oracle import oracle as orc
+    scene = V(background_color=s.RGBAColor(50, 0, 0, 255))
+    r = s.Renderer()
+    r.update_scene(OUTPUT_ID, s.Resolution(8, 2), RGBA, scene)
+    rgba = r.render(s.FrameSet(pts=0.0)).frames[OUTPUT_ID].data.planes[0]
+    assert rgba.reshape(-1).tolist() == [50, 0, 0, 255] * 16
+    r.update_scene(OUTPUT_ID, s.Resolution(8, 2), YUV, scene)
+    y, u, v = r.render(s.FrameSet(pts=0.0)).frames[OUTPUT_ID].data.planes
+    back = orc.harness_yuv420_to_rgba(y, u, v, 8, 2)
+    assert back.reshape(-1).tolist() == [49, 0, 0, 255] * 16
+
+
+def test_odd_output_size_uses_general_converter():
+    fr = inputs(2)
+    check(s.TilesComponent(children=streams(2), background_color=BG), fr, resolution=s.Resolution(641, 359))
+
+
+def test_max_layouts_count_truncates():
+    """params.rs:176-182 / shader.rs:152: layouts beyond max_layouts_count are skipped"""
+    kids = [V(position=s.Position.Absolute(width=30.0, height=30.0, left=10.0 + 25 * i, top=20.0 + 9 * i),
+              background_color=s.RGBAColor(40 * i % 256, 255 - 30 * i % 256, 90, 255)) for i in range(12)]
+    check(V(children=kids, background_color=BG), {}, max_layouts=6)
+
+
+def test_two_outputs_share_an_input():
+    """render_loop.rs:232-236: outputs are independent; inputs are shared read-only state"""
+    fr = inputs(2)
+    r = s.Renderer()
+    for i in fr:
+        r.register_input(i)
+    sc1 = s.TilesComponent(children=streams(2), background_color=BG)
+    sc2 = V(children=[s.RescalerComponent(child=streams(2)[1])], background_color=BG)
+    r.update_scene("output_1", RES, YUV, sc1)
+    r.update_scene("output_2", s.Resolution(320, 180), NV12, sc2)
+    out = r.render(s.FrameSet(frames=fr, pts=0.0))
+    got1, exp1, _ = run_case(sc1, fr)
+    assert_identical([np.asarray(p) for p in out.frames["output_1"].data.planes], exp1, "output_1")
+    got2, exp2, _ = run_case(sc2, fr, resolution=s.Resolution(320, 180), out_format=NV12)
+    assert_identical([np.asarray(p) for p in out.frames["output_2"].data.planes], exp2, "output_2")
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full size (16 x 4K -> 4K): size-independent properties instead of the oracle:
+    (1) determinism, (2) tile independence: every tile region equals the same input rendered alone into a
+    960x540 output, (3) background bytes exact."""
+    w, h = 3840, 2160
+    base = [harness.smooth_yuv420(40 + i, w, h) for i in range(4)]
+    fr = {f"input_{i}": nv12_frame(base[(i - 1) % 4], w, h) for i in range(1, 17)}
+    r = s.Renderer()
+    for i in fr:
+        r.register_input(i)
+    r.update_scene(OUTPUT_ID, s.Resolution(w, h), NV12, s.TilesComponent(children=streams(16), background_color=BG))
+    a = r.render(s.FrameSet(frames=fr, pts=0.0)).frames[OUTPUT_ID].data.planes
+    b = r.render(s.FrameSet(frames=fr, pts=0.0)).frames[OUTPUT_ID].data.planes
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    r1 = s.Renderer()
+    r1.register_input("input_1")
+    for k in range(4):
+        r1.update_scene(OUTPUT_ID, s.Resolution(960, 540), NV12, V(children=[s.RescalerComponent(child=streams(1)[0])]))
+        one = r1.render(s.FrameSet(frames={"input_1": fr[f"input_{k + 1}"]}, pts=0.0)).frames[OUTPUT_ID].data.planes
+        for slot in (k, k + 4, k + 8, k + 12):
+            ty, tx = divmod(slot, 4)
+            assert np.array_equal(a[0][ty * 540:(ty + 1) * 540, tx * 960:(tx + 1) * 960], one[0])
+            assert np.array_equal(a[1][ty * 270:(ty + 1) * 270, tx * 480:(tx + 1) * 480], one[1])
