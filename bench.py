@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native compositor (contract: see DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input: one output frame of the
+workload (default: BASELINE config 3, 16 x 4K NV12 -> 4K NV12 mosaic with per-input Lanczos3 4:1
+downscale, rounded corners and an alpha overlay).  N > 1: one process per GPU (torchrun), every rank
+composites its own output stream (weak scaling, no data-path collective: outputs shard).
+
+`value`     frames/s with inputs resident in HBM, device-timed (CUDA events on the launching stream).
+`e2e`       frames/s through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timing).
+`roofline`  dominant kernel: algorithmic bytes per launch / its device time (events inside the library).
+`cpu_baseline` / `--impl reference`: the CPU oracle (restatement of the reference's wgpu path; the
+            reference itself is Rust + wgpu and cannot run here) timed on the host cores, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+BG = (0x33, 0x33, 0x33, 255)
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs / SURVEY 8d)
+# ------------------------------------------------------------------------------------------------
+def workload(name):
+    import smelter_b200 as s
+    V = s.ViewComponent
+    bg = s.RGBAColor(*BG)
+
+    def streams(n):
+        return [s.InputStreamComponent(input_id=f"input_{i}") for i in range(1, n + 1)]
+
+    def rounded_tiles(n, radius, shadow=False):
+        kids = []
+        for c in streams(n):
+            sh = [s.BoxShadow(6.0, 6.0, 16.0, s.RGBAColor(0, 0, 0, 160))] if shadow else []
+            kids.append(s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(radius), box_shadow=sh))
+        return kids
+
+    if name == "cfg3":   # 16 x 4K NV12 -> 4K NV12, Tiles 4x4 (scale exactly 4 -> 25-tap Lanczos3), GpuOptimized
+        W, H, n, iw, ih = 3840, 2160, 16, 3840, 2160
+        overlay = V(position=s.Position.Absolute(width=1600.0, height=360.0, left=1120.0, bottom=120.0),
+                    background_color=s.RGBAColor(16, 32, 160, 112), border_radius=s.BorderRadius.new_with_radius(48.0))
+        scene = V(background_color=bg, children=[s.TilesComponent(children=rounded_tiles(n, 32.0), background_color=bg),
+                                                 overlay])
+        mode = s.RenderingMode.GpuOptimized
+        desc = "16x(3840x2160 NV12)->3840x2160 NV12, Tiles 4x4, Lanczos3 4:1, rounded corners + alpha overlay, GpuOptimized"
+    elif name == "cfg3b":  # same with 1080p inputs (scale 2)
+        W, H, n, iw, ih = 3840, 2160, 16, 1920, 1080
+        overlay = V(position=s.Position.Absolute(width=1600.0, height=360.0, left=1120.0, bottom=120.0),
+                    background_color=s.RGBAColor(16, 32, 160, 112), border_radius=s.BorderRadius.new_with_radius(48.0))
+        scene = V(background_color=bg, children=[s.TilesComponent(children=rounded_tiles(n, 32.0), background_color=bg),
+                                                 overlay])
+        mode = s.RenderingMode.GpuOptimized
+        desc = "16x(1920x1080 NV12)->3840x2160 NV12, Tiles 4x4, Lanczos3 2:1, rounded corners + alpha overlay"
+    elif name == "cfg2":  # 4 x 1080p NV12 -> 1080p NV12, Tiles 2x2, CpuOptimized (gamma blend, bilinear)
+        W, H, n, iw, ih = 1920, 1080, 4, 1920, 1080
+        scene = s.TilesComponent(children=streams(n), background_color=bg)
+        mode = s.RenderingMode.CpuOptimized
+        desc = "4x(1920x1080 NV12)->1920x1080 NV12, Tiles 2x2, bilinear, CpuOptimized"
+    elif name == "cfg5":  # 32 x 4K -> 8K, box shadow + radius
+        W, H, n, iw, ih = 7680, 4320, 32, 3840, 2160
+        scene = s.TilesComponent(children=rounded_tiles(n, 40.0, shadow=True), background_color=bg, margin=24.0)
+        mode = s.RenderingMode.GpuOptimized
+        desc = "32x(3840x2160 NV12)->7680x4320 NV12, Tiles 6x6 grid, Lanczos3 + box-shadow + radius"
+    elif name == "passthrough":  # single_video_pass_through of the reference's benchmark suite
+        W, H, n, iw, ih = 3840, 2160, 1, 3840, 2160
+        scene = s.InputStreamComponent(input_id="input_1")
+        mode = s.RenderingMode.GpuOptimized
+        desc = "1x(3840x2160 NV12)->3840x2160 NV12 pass-through root"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    alg = n * (iw * ih * 3 // 2) + W * H * 3 // 2   # every needed input byte once + every output byte once
+    return dict(name=name, scene=scene, W=W, H=H, n=n, iw=iw, ih=ih, mode=mode, desc=desc, alg_bytes=alg)
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_planes_torch(torch, dev, w, h, seed):
+    """procedural NV12 frame on the device: smooth blobs + noise, legal range."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    def plane(pw, ph, lo, hi, ch):
+        coarse = torch.rand((ph // 32 + 2, pw // 32 + 2, ch), generator=g, device=dev)
+        up = coarse.repeat_interleave(32, 0).repeat_interleave(32, 1)[:ph, :pw]
+        x = up * 0.85 + 0.15 * torch.rand((ph, pw, ch), generator=g, device=dev)
+        return (lo + x * (hi - lo)).to(torch.uint8).contiguous()
+    return plane(w, h, 16, 235, 1), plane(w // 2, h // 2, 16, 240, 2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded sample (1 of n tiles of the workload)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(wl, repeats=1):
+    """Time the oracle on ONE input of the workload composited into ITS tile-sized output region with the
+    same per-tile layers (K1/K2 -> Lanczos -> K9 -> K11).  Returns (seconds per sample, description)."""
+    import smelter_b200 as s
+    from oracle import oracle as orc
+    from tests import harness
+    n, iw, ih = wl["n"], wl["iw"], wl["ih"]
+    cols = int(np.ceil(np.sqrt(n)))
+    tw, th = wl["W"] // cols, (wl["W"] // cols) * 9 // 16
+    if wl["name"] == "passthrough":
+        tw, th = wl["W"], wl["H"]
+    y, u, v = harness.smooth_yuv420(1, iw, ih)
+    uv = np.stack([u, v], axis=-1)
+    mode = orc.MODE_CPU_OPTIMIZED if wl["mode"] == s.RenderingMode.CpuOptimized else orc.MODE_GPU_OPTIMIZED
+    radius = 0.0 if wl["name"] in ("cfg2", "passthrough") else 32.0
+    layers = [orc.make_layout(orc.LAYOUT_COLOR, 0, 0, tw, th, color=BG),
+              orc.make_layout(orc.LAYOUT_TEXTURE, 0, 0, tw, th, child_index=0, crop=(0, 0, iw, ih),
+                              masks=[((radius,) * 4, 0, 0, tw, th)] if radius else [])]
+    if wl["name"] in ("cfg3", "cfg3b"):  # this tile's share of the alpha overlay
+        layers.append(orc.make_layout(orc.LAYOUT_COLOR, th * 0.3, 0, tw, th * 0.5, color=(16, 32, 160, 112)))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        node = orc.nv12_to_rgba(y, uv, iw, ih)
+        if wl["name"] == "passthrough":
+            img = node
+        else:
+            img = orc.render_layout_node(tw, th, layers, [node], mode=mode)
+        orc.rgba_to_nv12(img)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    desc = (f"1 of {n} tiles: one {iw}x{ih} NV12 input -> {tw}x{th} NV12 region with the tile's layers; "
+            f"frame time = {n} x sample")
+    return best, desc, orc.num_threads()
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU path cannot run here (Rust + wgpu, no rustc / Vulkan ICD in
+    the image), so this arm times the CPU oracle -- the restatement of that path -- on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    samples = []
+    desc, cores = "", 1
+    for i in range(args.warmup + args.steps):
+        dt, desc, cores = cpu_sample(wl)
+        if i >= args.warmup:
+            samples.append(dt)
+    per_frame = float(np.mean(samples)) * wl["n"]
+    fps = 1.0 / per_frame
+    line = {"impl": "reference", "metric": "composited output frames/sec", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_frame * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "detail": wl["desc"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--variants", type=int, default=4, help="distinct synthetic frames per input, cycled")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import smelter_b200 as s
+    from smelter_b200 import _ffi as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the compositor has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    r = s.Renderer(s.RendererOptions(rendering_mode=wl["mode"], cuda_device=local))
+    n, iw, ih, W, H = wl["n"], wl["iw"], wl["ih"], wl["W"], wl["H"]
+    ids = [f"input_{i}".encode() for i in range(1, n + 1)]
+    for b in ids:
+        r.register_input(b.decode())
+    r.update_scene("output_1", s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture, wl["scene"])
+
+    # ---- device-resident synthetic inputs: `variants` distinct frames per input, cycled -------------
+    nvar = max(1, args.variants)
+    dev_frames = [[synth_planes_torch(torch, dev, iw, ih, 0x5EED0000 + 1000 * v + i + 97 * rank) for i in range(n)]
+                  for v in range(nvar)]
+    out_y = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    out_uv = torch.empty((H // 2, W // 2, 2), dtype=torch.uint8, device=dev)
+
+    def in_array(planes_for_variant, mem_kind, ptr):
+        arr = (F.InputFrame * n)()
+        for i in range(n):
+            yv, uvv = planes_for_variant[i]
+            arr[i].input_id = ids[i]
+            arr[i].format = F.FRAME_NV12
+            arr[i].width, arr[i].height = iw, ih
+            arr[i].mem_kind = mem_kind
+            arr[i].planes[0], arr[i].planes[1] = ptr(yv), ptr(uvv)
+        return arr
+
+    dev_in = [in_array(dev_frames[v], F.MEM_DEVICE, lambda t: t.data_ptr()) for v in range(nvar)]
+    dev_out = (F.OutputFrame * 1)()
+    dev_out[0].output_id = b"output_1"
+    dev_out[0].mem_kind = F.MEM_DEVICE
+    dev_out[0].planes[0], dev_out[0].planes[1] = out_y.data_ptr(), out_uv.data_ptr()
+
+    stream = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
+    frame_ns = 33_333_333
+
+    def step_dev(k):
+        for a in dev_in[k % nvar]:
+            a.pts_ns = k * frame_ns
+        r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, 1, wait=False)
+
+    # ---- value: device-resident, device-timed ---------------------------------------------------------
+    for k in range(args.warmup):
+        step_dev(k)
+    r.wait()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = r.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(args.steps):
+        step_dev(args.warmup + k)
+    r.wait()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = r.stats()["kernel_launches"] - launches0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop()
+    ms_per_step = ms / args.steps
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- roofline: per-kernel device time from the library's own events -----------------------------
+    r.set_profiling(True)
+    for k in range(args.steps):
+        step_dev(k)
+        r.wait()
+    kt = r.kernel_times()
+    r.set_profiling(False)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    per_kernel = {}
+    for name, (tot, cnt) in kt.items():
+        if cnt:
+            per_launch_ms = tot / cnt
+            launches_per_frame = cnt / args.steps
+            per_kernel[name] = {"ms_per_launch": per_launch_ms, "launches_per_frame": launches_per_frame,
+                                "ms_per_frame": tot / args.steps}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_frame"]) if per_kernel else None
+    gpu_ms_frame = sum(v["ms_per_frame"] for v in per_kernel.values())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath) and dom:
+        traffic = json.load(open(tpath)).get(wl["name"], {}).get(dom)
+    roofline = None
+    if dom:
+        # one launch of the dominant kernel processes one whole output frame's worth of its stage
+        ach = wl["alg_bytes"] / (per_kernel[dom]["ms_per_frame"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": wl["alg_bytes"] // max(1, round(per_kernel[dom]["launches_per_frame"])),
+                    "kernel_share_of_gpu_time": per_kernel[dom]["ms_per_frame"] / gpu_ms_frame,
+                    "whole_frame": {"achieved": wl["alg_bytes"] / (ms_per_step * 1e-3) / 1e9,
+                                    "frac": wl["alg_bytes"] / (ms_per_step * 1e-3) / 1e9 / peak},
+                    "kernels": per_kernel}
+
+    # ---- e2e: through the C ABI with pinned HOST buffers --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hv = min(nvar, 2)
+        host_frames = [[(dev_frames[v][i][0].cpu().pin_memory(), dev_frames[v][i][1].cpu().pin_memory())
+                        for i in range(n)] for v in range(hv)]
+        host_in = [in_array(host_frames[v], F.MEM_HOST, lambda t: t.data_ptr()) for v in range(hv)]
+        hy = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+        huv = torch.empty((H // 2, W // 2, 2), dtype=torch.uint8).pin_memory()
+        host_out = (F.OutputFrame * 1)()
+        host_out[0].output_id = b"output_1"
+        host_out[0].mem_kind = F.MEM_HOST
+        host_out[0].planes[0], host_out[0].planes[1] = hy.data_ptr(), huv.data_ptr()
+        ke = max(5, min(args.steps, 30))
+        st0 = r.stats()
+        for k in range(3):
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, 1, wait=True)
+        barrier()
+        st0 = r.stats()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ee0.record(stream)
+        for k in range(ke):
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, 1, wait=True)
+            _ = int(hy[0, 0])  # the step's result is read on the host
+        ee1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        st1 = r.stats()
+        e2e_s = max(wall, ee0.elapsed_time(ee1) * 1e-3)
+        if dist is not None:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * ke / e2e_s, "unit": "frames/s", "steps": ke,
+               "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // ke,
+               "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // ke}
+
+    # ---- cpu baseline (rank 0, N = 1 only) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, desc, cores = cpu_sample(wl, repeats=2)
+        cpu = {"value": 1.0 / (dt * wl["n"]), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {"metric": "4K composited frames/sec (16-input grid) per GPU" if wl["name"] == "cfg3" else "composited output frames/sec",
+                "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 math on u8 planes (f16 resampler scratch)", "data": "synthetic",
+                "config": {"workload": wl["name"], "detail": wl["desc"], "outputs_per_gpu": 1,
+                           "l2_policy": f"inputs larger than L2: {nvar} distinct frame sets of "
+                                        f"{wl['alg_bytes'] / 1e6:.0f} MB cycled (> 126 MB L2)",
+                           "algorithmic_bytes_per_frame": wl["alg_bytes"], "wall_s_timed_region": t_wall},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

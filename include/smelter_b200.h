@@ -184,6 +184,24 @@ typedef struct {
     uint64_t last_render_kernel_launches;
 } smr_stats;
 
+/* per-kernel-class device time, measured with cudaEvents on the launching stream when profiling is on
+ * (the reference has no GPU timestamps: `timestamp_writes: None`, e.g. rgba_to_yuv.rs:104) */
+typedef enum {
+    SMR_KERNEL_CONVERT = 0,        /* K1/K2/K4 materialised node texture */
+    SMR_KERNEL_WEIGHTS = 1,        /* Lanczos weight tables for new mappings */
+    SMR_KERNEL_RESAMPLE_BOX = 2,   /* K7 */
+    SMR_KERNEL_RESAMPLE_FIRST = 3, /* K8 first pass -> f16 */
+    SMR_KERNEL_RESAMPLE_LAST = 4,  /* K8 last pass -> sRGB8 */
+    SMR_KERNEL_COMPOSITE = 5,      /* K9 (+K10/K11 fused) */
+    SMR_KERNEL_OUTPUT = 6,         /* K10/K11 stand-alone */
+    SMR_KERNEL_FILL = 7,           /* K6 */
+    SMR_KERNEL_CLASSES = 8
+} smr_kernel_class;
+typedef struct {
+    double total_ms[SMR_KERNEL_CLASSES];
+    uint64_t launches[SMR_KERNEL_CLASSES];
+} smr_kernel_times;
+
 /* ------------------------------------------ entry points ------------------------------------ */
 /* Renderer::new(RendererOptions)                                    state.rs:96-100,196-211 */
 smr_status smr_create(const smr_options *opts, smr_renderer **out);
@@ -230,6 +248,8 @@ smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pt
 smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs);
 
 smr_status smr_get_stats(smr_renderer *r, smr_stats *out);
+smr_status smr_set_profiling(smr_renderer *r, int32_t enabled);   /* also resets the accumulated times */
+smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out);
 void *smr_cuda_stream(smr_renderer *r);          /* cudaStream_t the handle launches on */
 const char *smr_last_error(smr_renderer *r);     /* ErrorStack::into_string analogue; valid until next call */
 const char *smr_version(void);

@@ -105,10 +105,18 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("last_render_kernel_launches", C.c_uint64)]
 
 
+KERNEL_CLASSES = ["convert", "weights", "resample_box", "resample_first", "resample_last", "composite", "output",
+                  "fill"]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("total_ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
 EXPORTS = [
     "smr_create", "smr_destroy", "smr_register_input", "smr_unregister_input", "smr_update_scene",
     "smr_unregister_output", "smr_render", "smr_render_begin", "smr_render_end", "smr_output_plane_sizes",
-    "smr_component_default", "smr_debug_layouts", "smr_debug_set_inputs", "smr_get_stats", "smr_cuda_stream", "smr_last_error",
+    "smr_component_default", "smr_debug_layouts", "smr_debug_set_inputs", "smr_get_stats", "smr_set_profiling", "smr_get_kernel_times", "smr_cuda_stream", "smr_last_error",
     "smr_version",
 ]
 
@@ -143,6 +151,8 @@ def lib():
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.smr_debug_set_inputs.argtypes = [vp, C.c_uint64, C.POINTER(InputFrame), C.c_uint32]
     L.smr_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.smr_set_profiling.argtypes = [vp, C.c_int32]
+    L.smr_get_kernel_times.argtypes = [vp, C.POINTER(KernelTimes)]
     L.smr_cuda_stream.argtypes = [vp]
     L.smr_cuda_stream.restype = vp
     L.smr_last_error.argtypes = [vp]

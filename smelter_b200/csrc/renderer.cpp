@@ -237,6 +237,16 @@ class Renderer {
     std::map<WeightKey, WeightEntry> weights_;
     bool in_flight_ = false;
     bool host_only_ = false;
+    // optional per-kernel-class device timing (cudaEvents on the launching stream)
+    void prof_mark(int kernel_class);
+    bool profiling_ = false;
+    std::vector<cudaEvent_t> prof_events_;
+    size_t prof_next_event_ = 0;
+    std::vector<std::pair<cudaEvent_t, int>> prof_marks_;
+    smr_kernel_times prof_ = {};
+  public:
+    smr_status set_profiling(int enabled);
+    void kernel_times(smr_kernel_times *out) { std::lock_guard<std::mutex> g(mu_); *out = prof_; }
 };
 
 Renderer::~Renderer() {
@@ -843,14 +853,19 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
 
     // ---- launches -----------------------------------------------------------------------------
     auto launched = [&](int n) -> bool { if (n < 0) return false; launches += (uint64_t)n; return true; };
+    prof_mark(-1);
     for (auto &cj : convert_jobs_) {
         const dev::Tex &src = tex_table_[cj.first];
         if (!launched(dev::launch_convert_to_rgba(src, fb + cj.second, src.width * 4, stream_))) goto fail;
+        prof_mark(SMR_KERNEL_CONVERT);
     }
     if (!launched(dev::launch_weights((const dev::WeightJob *)(pd + wj_off), weight_jobs_.data(), (int)weight_jobs_.size(), stream_))) goto fail;
-    for (int s = 0; s < 3; s++)
+    if (!weight_jobs_.empty()) prof_mark(SMR_KERNEL_WEIGHTS);
+    for (int s = 0; s < 3; s++) {
         if (!launched(dev::launch_resample((const dev::ResampleJob *)(pd + stage_off[s]), stage_jobs_[s].data(),
                                            (int)stage_jobs_[s].size(), stream_))) goto fail;
+        if (!stage_jobs_[s].empty()) prof_mark(SMR_KERNEL_RESAMPLE_BOX + s);
+    }
     for (PendingComposite &pc : composites_) {
         pc.job.layers = (const dev::LayerDev *)(pd + pc.layers_off);
         pc.job.masks = (const dev::MaskDev *)(pd + pc.masks_off);
@@ -860,12 +875,17 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             pc.job.out1 = nullptr;
         }
         if (!launched(dev::launch_composite(pc.job, stream_))) goto fail;
+        prof_mark(SMR_KERNEL_COMPOSITE);
     }
-    for (dev::OutputJob &oj : output_jobs_)
+    for (dev::OutputJob &oj : output_jobs_) {
         if (!launched(dev::launch_output(oj, stream_))) goto fail;
-    for (Fill &f : fills_)
+        prof_mark(SMR_KERNEL_OUTPUT);
+    }
+    for (Fill &f : fills_) {
         if (!launched(dev::launch_fill_yuv(f.p[0], f.p[1], f.p[2], f.pitch[0], f.pitch[1], f.pitch[2], f.w, f.h, f.fmt,
                                            f.yuv[0], f.yuv[1], f.yuv[2], stream_))) goto fail;
+        prof_mark(SMR_KERNEL_FILL);
+    }
     for (PendingCopy &c : d2h_)
         CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, stream_));
     stats_.kernel_launches += launches;
@@ -907,6 +927,37 @@ smr_status Renderer::render_end() {
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     in_flight_ = false;
     CUDA_OK(cudaStreamSynchronize(stream_));
+    // fold this tick's event pairs into the per-kernel-class totals
+    for (size_t i = 1; i < prof_marks_.size(); i++) {
+        int k = prof_marks_[i].second;
+        if (k < 0) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, prof_marks_[i - 1].first, prof_marks_[i].first) == cudaSuccess) {
+            prof_.total_ms[k] += ms;
+            prof_.launches[k] += 1;
+        }
+    }
+    prof_marks_.clear();
+    return SMR_OK;
+}
+
+void Renderer::prof_mark(int kernel_class) {
+    if (!profiling_) return;
+    if (kernel_class == -1) { prof_marks_.clear(); prof_next_event_ = 0; }
+    if (prof_next_event_ >= prof_events_.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        prof_events_.push_back(e);
+    }
+    cudaEvent_t e = prof_events_[prof_next_event_++];
+    cudaEventRecord(e, stream_);
+    prof_marks_.push_back({e, kernel_class});
+}
+
+smr_status Renderer::set_profiling(int enabled) {
+    std::lock_guard<std::mutex> g(mu_);
+    profiling_ = enabled != 0;
+    memset(&prof_, 0, sizeof(prof_));
     return SMR_OK;
 }
 
@@ -1014,6 +1065,12 @@ smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, 
 smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap,
                              uint32_t *n, uint32_t *rw, uint32_t *rh) { SMR_GUARD(r->impl.debug_layouts(output_id, pts, out, cap, n, rw, rh)) }
 smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in) { SMR_GUARD(r->impl.debug_set_inputs(pts, in, n_in)) }
+smr_status smr_set_profiling(smr_renderer *r, int32_t enabled) { SMR_GUARD(r->impl.set_profiling(enabled)) }
+smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out) {
+    if (!r || !out) return SMR_ERR_INVALID_ARGUMENT;
+    r->impl.kernel_times(out);
+    return SMR_OK;
+}
 smr_status smr_get_stats(smr_renderer *r, smr_stats *out) {
     if (!r || !out) return SMR_ERR_INVALID_ARGUMENT;
     r->impl.stats(out);

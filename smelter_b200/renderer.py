@@ -534,5 +534,14 @@ class Renderer:
         self._check(self._lib.smr_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in F.Stats._fields_}
 
+    def set_profiling(self, enabled: bool):
+        self._check(self._lib.smr_set_profiling(self._h, int(enabled)))
+
+    def kernel_times(self):
+        """{kernel class: (total device ms, launches)} since set_profiling(True)."""
+        t = F.KernelTimes()
+        self._check(self._lib.smr_get_kernel_times(self._h, C.byref(t)))
+        return {name: (t.total_ms[i], int(t.launches[i])) for i, name in enumerate(F.KERNEL_CLASSES)}
+
     def cuda_stream(self):
         return self._lib.smr_cuda_stream(self._h)
