@@ -195,7 +195,8 @@ typedef enum {
     SMR_KERNEL_COMPOSITE = 5,      /* K9 (+K10/K11 fused) */
     SMR_KERNEL_OUTPUT = 6,         /* K10/K11 stand-alone */
     SMR_KERNEL_FILL = 7,           /* K6 */
-    SMR_KERNEL_CLASSES = 8
+    SMR_KERNEL_RESAMPLE_FUSED = 8, /* K1/K2 + both K8 passes in one kernel */
+    SMR_KERNEL_CLASSES = 9
 } smr_kernel_class;
 typedef struct {
     double total_ms[SMR_KERNEL_CLASSES];

@@ -742,3 +742,31 @@ void orc_render_layout_node(int W, int H, const orc_layout *layouts_in, int n, c
     for (int i = 0; i < n; i++) free(owned[i]);
     free(owned); free(tex); free(layouts);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* self-check used by tests: for even plane sizes the K1/K2 chroma taps of NC-6 are exactly     */
+/* (x/2-1, x/2; f=.75) for even x and ((x-1)/2, (x+1)/2; f=.25) for odd x (clamped), the luma   */
+/* tap and the K10 chroma tap (f=.5 between 2c and 2c+1) likewise.  Returns the mismatch count. */
+/* ------------------------------------------------------------------------------------------ */
+long orc_check_even_size_phases(int max_dim) {
+    long bad = 0;
+    for (int w = 2; w <= max_dim; w += 2) {
+        int cw = w / 2;
+        for (int x = 0; x < w; x++) {
+            float t = ((float)x + 0.5f) / (float)w;
+            lin_tap c = linear_tap(t, cw);
+            int e0 = (x & 1) ? (x - 1) / 2 : x / 2 - 1, e1 = e0 + 1;
+            float ef = (x & 1) ? 0.25f : 0.75f;
+            if (e0 < 0) e0 = 0;
+            if (e1 > cw - 1) e1 = cw - 1;
+            if (c.i0 != e0 || c.i1 != e1 || c.f != ef) bad++;
+            lin_tap l = linear_tap(t, w); /* luma: must select texel x with weight exactly 1 */
+            if (!((l.f == 0.0f && l.i0 == x) || (l.f == 1.0f && l.i1 == x))) bad++;
+        }
+        for (int c = 0; c < cw; c++) { /* K10: chroma target texel c samples the full-res texture */
+            lin_tap k = linear_tap(((float)c + 0.5f) / (float)cw, w);
+            if (k.i0 != 2 * c || k.i1 != 2 * c + 1 || k.f != 0.5f) bad++;
+        }
+    }
+    return bad;
+}

@@ -106,11 +106,11 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ["convert", "weights", "resample_box", "resample_first", "resample_last", "composite", "output",
-                  "fill"]
+                  "fill", "resample_fused"]
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("total_ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+    _fields_ = [("total_ms", C.c_double * 9), ("launches", C.c_uint64 * 9)]
 
 
 EXPORTS = [

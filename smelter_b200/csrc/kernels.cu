@@ -155,6 +155,28 @@ __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int 
         case TEX_YUV420:
         case TEX_NV12: {
             int cw = s.width / 2, ch = s.height / 2;
+            if (((s.width | s.height) & 1) == 0) {
+                // Even sizes: the NC-6 taps are exactly texel (x,y) for luma and the .25/.75 pair for chroma
+                // (proved for every even size <= 8192 by oracle test test_even_size_sampler_phases_exhaustive).
+                int x0 = (x & 1) ? (x >> 1) : max((x >> 1) - 1, 0), x1 = (x & 1) ? min((x >> 1) + 1, cw - 1) : (x >> 1);
+                int y0 = (y & 1) ? (y >> 1) : max((y >> 1) - 1, 0), y1 = (y & 1) ? min((y >> 1) + 1, ch - 1) : (y >> 1);
+                float fx = (x & 1) ? 0.25f : 0.75f, fy = (y & 1) ? 0.25f : 0.75f;
+                float yy = T.u8n[__ldg(s.p0 + (size_t)y * s.pitch0 + x)];
+                float uu, vv;
+                if (s.kind == TEX_YUV420) {
+                    const uint8_t *u0 = s.p1 + (size_t)y0 * s.pitch1, *u1 = s.p1 + (size_t)y1 * s.pitch1;
+                    const uint8_t *v0 = s.p2 + (size_t)y0 * s.pitch2, *v1 = s.p2 + (size_t)y1 * s.pitch2;
+                    uu = bilerp(T.u8n[__ldg(u0 + x0)], T.u8n[__ldg(u0 + x1)], T.u8n[__ldg(u1 + x0)], T.u8n[__ldg(u1 + x1)], fx, fy);
+                    vv = bilerp(T.u8n[__ldg(v0 + x0)], T.u8n[__ldg(v0 + x1)], T.u8n[__ldg(v1 + x0)], T.u8n[__ldg(v1 + x1)], fx, fy);
+                } else {
+                    const uchar2 *r0 = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)y0 * s.pitch1);
+                    const uchar2 *r1 = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)y1 * s.pitch1);
+                    uchar2 a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
+                    uu = bilerp(T.u8n[a.x], T.u8n[b.x], T.u8n[c.x], T.u8n[d.x], fx, fy);
+                    vv = bilerp(T.u8n[a.y], T.u8n[b.y], T.u8n[c.y], T.u8n[d.y], fx, fy);
+                }
+                return yuv_to_rgba8(yy, uu, vv, s.full_range);
+            }
             float tx = ((float)x + 0.5f) / (float)s.width, ty = ((float)y + 0.5f) / (float)s.height;
             LinTap ax = linear_tap(tx, s.width), ay = linear_tap(ty, s.height);
             LinTap cx = linear_tap(tx, cw), cy = linear_tap(ty, ch);
@@ -324,6 +346,139 @@ int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1/K2 + K8 + K8 fused: the common resample (YUV input, horizontal pass first, then vertical).
+//
+// One block owns a strip of FS_TW output columns and a run of output rows and streams DOWN the source:
+//   phase A  each warp takes whole source rows: converts the strip's source pixels ONCE (K1/K2 -> RGBA8
+//            quantisation -> sRGB decode), runs the horizontal Lanczos pass out of a per-warp shared-memory
+//            row and stores the f16-quantised result into a ring of intermediate rows in shared memory;
+//   phase B  each warp produces one output row: vertical Lanczos pass out of the ring, sRGB8 encode,
+//            coalesced uchar4 store.
+// Neither the RGBA8 node texture (4 B/px of the INPUT resolution) nor the Rgba16Float intermediate ever
+// reaches HBM; a source row is converted once per strip.  Bit-identical to running K1, resample.wgsl pass 1
+// (-> f16) and pass 2 (-> sRGB8) separately: every quantisation point is reproduced.
+// ------------------------------------------------------------------------------------------------
+#define FS_TW 32         // output columns per block (one lane each)
+#define FS_WARPS 8
+#define FS_RING 64       // intermediate rows resident in shared memory (power of two)
+#define FS_SPAN 160      // max source pixels a strip's horizontal taps touch
+#define FS_MAXTAPS 32
+
+struct FusedSmem {
+    Tables T;
+    float hw[FS_TW * FS_MAXTAPS];           // horizontal weights of the strip's columns [lane][tap]
+    float ring[FS_RING][3][FS_TW];          // f16-quantised intermediate rows (kept as f32 values)
+    float srow[FS_WARPS][3][FS_SPAN];       // per-warp converted + decoded source row
+};
+
+// K1/K2 for one pixel of an even-sized YUV texture, returning decoded linear rgb (alpha is 1)
+__device__ __forceinline__ void yuv_px_linear(const Tables &T, const Tex &s, int x, int y, float &r, float &g, float &b) {
+    uchar4 p = node_texel(T, s, x, y);
+    r = T.dec[p.x]; g = T.dec[p.y]; b = T.dec[p.z];
+}
+
+__global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused(const FusedJob *jobs) {
+    extern __shared__ __align__(16) unsigned char fs_raw[];
+    FusedSmem &S = *reinterpret_cast<FusedSmem *>(fs_raw);
+    load_tables(S.T);
+    const FusedJob &J = jobs[blockIdx.z];
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int ox0 = blockIdx.x * FS_TW;
+    if (ox0 >= J.dst_w) return;
+    const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
+    if (oy_begin >= J.dst_h) return;
+    const Tex &src = J.src;
+    const int W = src.width, H = src.height;
+    const int th = J.taps_h, tv = J.taps_v;
+
+    // horizontal tables of this strip
+    const int ox = min(ox0 + lane, J.dst_w - 1);
+    const int first_h = __ldg(J.first_h + ox);
+    const float inv_h = __ldg(J.inv_h + ox);
+    for (int t = warp; t < th; t += FS_WARPS) S.hw[lane * th + t] = __ldg(J.w_h + (size_t)ox * th + t);
+    const int xa = __shfl_sync(0xffffffffu, first_h, 0);  // first_h is non-decreasing in ox
+    const int o_last = min(ox0 + FS_TW - 1, J.dst_w - 1);
+    const int span = (__ldg(J.first_h + o_last) + th - 1) - xa + 1;  // <= FS_SPAN (host checked)
+    const int off = first_h - xa;
+    __syncthreads();
+
+    int produced_hi = -0x40000000;  // highest source row already in the ring
+    for (int o0 = oy_begin; o0 < oy_end; o0 += FS_WARPS) {
+        const int o_l = min(o0 + FS_WARPS - 1, oy_end - 1);
+        const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
+        const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
+        const int start = max(produced_hi + 1, need_lo);
+        // ---- phase A: produce intermediate rows [start, need_hi] ---------------------------------
+        for (int r = start + warp; r <= need_hi; r += FS_WARPS) {
+            float *sr = S.srow[warp][0], *sg = S.srow[warp][1], *sb = S.srow[warp][2];
+            for (int i = lane; i < span; i += 32) {
+                int x = min(max(xa + i, 0), W - 1);
+                float rr, gg, bb;
+                yuv_px_linear(S.T, src, x, r, rr, gg, bb);
+                sr[i] = rr; sg[i] = gg; sb[i] = bb;
+            }
+            __syncwarp();
+            float ar = 0.f, ag = 0.f, ab = 0.f;
+            const float *w = &S.hw[lane * th];
+            for (int t = 0; t < th; t++) {
+                float wt = w[t];
+                ar = fmaf(sr[off + t], wt, ar);
+                ag = fmaf(sg[off + t], wt, ag);
+                ab = fmaf(sb[off + t], wt, ab);
+            }
+            float *dst = &S.ring[r & (FS_RING - 1)][0][0];
+            dst[lane] = __half2float(__float2half_rn(ar * inv_h));               // NC-5
+            dst[FS_TW + lane] = __half2float(__float2half_rn(ag * inv_h));
+            dst[2 * FS_TW + lane] = __half2float(__float2half_rn(ab * inv_h));
+            __syncwarp();
+        }
+        produced_hi = max(produced_hi, need_hi);
+        __syncthreads();
+        // ---- phase B: one output row per warp ---------------------------------------------------------
+        const int oy = o0 + warp;
+        if (oy < oy_end) {
+            const int fv = __ldg(J.first_v + oy);
+            const float *wv = J.w_v + (size_t)oy * tv;
+            float ar = 0.f, ag = 0.f, ab = 0.f;
+            for (int t = 0; t < tv; t++) {
+                float wt = __ldg(wv + t);
+                if (wt == 0.0f) continue;
+                int row = min(max(fv + t, 0), H - 1);
+                const float *p = &S.ring[row & (FS_RING - 1)][0][0];
+                ar = fmaf(p[lane], wt, ar);
+                ag = fmaf(p[FS_TW + lane], wt, ag);
+                ab = fmaf(p[2 * FS_TW + lane], wt, ab);
+            }
+            float inv_v = __ldg(J.inv_v + oy);
+            if (ox0 + lane < J.dst_w) {
+                uchar4 o = make_uchar4((unsigned char)srgb_encode(S.T, ar * inv_v), (unsigned char)srgb_encode(S.T, ag * inv_v),
+                                       (unsigned char)srgb_encode(S.T, ab * inv_v), 255);
+                reinterpret_cast<uchar4 *>(J.dst + (size_t)oy * J.dst_pitch)[ox0 + lane] = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n, Stream s) {
+    if (n <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_resample_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        attr_set = true;
+    }
+    int mx = 1, my = 1;
+    for (int i = 0; i < n; i++) {
+        int sx = (jobs_host[i].dst_w + FS_TW - 1) / FS_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
+        mx = sx > mx ? sx : mx;
+        my = sy > my ? sy : my;
+    }
+    dim3 b(FS_TW, FS_WARPS), g(mx, my, n);
+    k_resample_fused<<<g, b, sizeof(FusedSmem), (cudaStream_t)s>>>(jobs_dev);
+    return check_launch("k_resample_fused") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9 (+K10/K11): composite
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float smoothstep_f(float e0, float e1, float x) {
@@ -358,14 +513,22 @@ __device__ __forceinline__ bool quad_covers(const LayerDev &L, int px, int py) {
 }
 
 // textureSample of a child through NodeTextureState::view()
-__device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, int mode, float tx, float ty) {
+__device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, int mode, float tx, float ty,
+                                              bool &exact, uchar4 &texel) {
+    exact = false;
     if (tex == nullptr || tex->kind == TEX_NONE) return make_float4(0.f, 0.f, 0.f, 0.f);  // default_empty_view
     const Tex &S = *tex;
     LinTap ax = linear_tap(tx, S.width), ay = linear_tap(ty, S.height);
     const float *lut = mode == 0 ? T.dec : T.u8n;
+    // a weight of exactly 1 on the second tap is the same single-texel hit as a weight of 0
+    if (ax.f == 1.0f) { ax.i0 = ax.i1; ax.f = 0.0f; }
+    if (ay.f == 1.0f) { ay.i0 = ay.i1; ay.f = 0.0f; }
     uchar4 p00 = node_texel(T, S, ax.i0, ay.i0);
-    if (ax.f == 0.0f && ay.f == 0.0f)  // exact texel hit: the other three weights are zero
+    if (ax.f == 0.0f && ay.f == 0.0f) {  // exact texel hit: the other three weights are zero
+        exact = true;
+        texel = p00;
         return make_float4(lut[p00.x], lut[p00.y], lut[p00.z], T.u8n[p00.w]);
+    }
     uchar4 p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
     uchar4 p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
     uchar4 p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
@@ -378,7 +541,11 @@ __device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, i
 }
 
 // vs_main + fs_main of apply_layouts.wgsl for one covered pixel
-__device__ __forceinline__ float4 shade(const Tables &T, const CompositeJob &J, const LayerDev &L, int px, int py) {
+// `pass` is set when the fragment is an unmodified opaque texel: blending it through the sRGB target
+// reproduces the texel's bytes exactly (encode(decode(b)) == b), so the caller copies `texel`.
+__device__ __forceinline__ float4 shade(const Tables &T, const CompositeJob &J, const LayerDev &L, int px, int py,
+                                        bool &pass, uchar4 &texel) {
+    pass = false;
     float pcx = (float)px + 0.5f, pcy = (float)py + 0.5f;
     float lx, ly, u, v;
     if (!L.rotated) {
@@ -405,10 +572,12 @@ __device__ __forceinline__ float4 shade(const Tables &T, const CompositeJob &J, 
     if (L.type == 0) {
         float tx = u * L.crop_sx + L.crop_ox;
         float ty = v * L.crop_sy + L.crop_oy;
-        float4 sample = sample_node(T, L.tex >= 0 ? &J.textures[L.tex] : nullptr, J.mode, tx, ty);
+        bool exact;
+        float4 sample = sample_node(T, L.tex >= 0 ? &J.textures[L.tex] : nullptr, J.mode, tx, ty, exact, texel);
         float bw = L.border_width;
         if (bw < 1.0f) {
             float ca = smoothstep_f(-0.5f, 0.5f, edge);
+            pass = exact && ca == 1.0f && mask_alpha == 1.0f && texel.w == 255;
             src = make_float4((sample.x * ca) * mask_alpha, (sample.y * ca) * mask_alpha,
                               (sample.z * ca) * mask_alpha, (sample.w * ca) * mask_alpha);
         } else if (mask_alpha < 0.01f) {
@@ -457,6 +626,19 @@ __device__ __forceinline__ uchar4 blend(const Tables &T, int mode, uchar4 dst, f
     if (s.x == 0.0f && s.y == 0.0f && s.z == 0.0f && s.w == 0.0f) return dst;  // encode(decode(b)) == b
     float ia = 1.0f - s.w;
     uchar4 o;
+    if (ia == 0.0f) {  // opaque source: fma(dst, 0, s) == s, the destination is never read
+        if (mode == 0) {
+            o.x = (unsigned char)srgb_encode(T, s.x);
+            o.y = (unsigned char)srgb_encode(T, s.y);
+            o.z = (unsigned char)srgb_encode(T, s.z);
+        } else {
+            o.x = (unsigned char)unorm8(s.x);
+            o.y = (unsigned char)unorm8(s.y);
+            o.z = (unsigned char)unorm8(s.z);
+        }
+        o.w = 255;
+        return o;
+    }
     if (mode == 0) {
         o.x = (unsigned char)srgb_encode(T, fmaf(T.dec[dst.x], ia, s.x));
         o.y = (unsigned char)srgb_encode(T, fmaf(T.dec[dst.y], ia, s.y));
@@ -489,11 +671,13 @@ __device__ __forceinline__ float to_v(float r, float g, float b) {
 #define CB_X 32          // threads per block, x
 #define CB_Y 8
 #define MAX_TILE_LAYERS 1024
+#define SM_LAYERS 40     // layers of a tile kept in shared memory (the rest are read from global)
 
 __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
     __shared__ Tables T;
     __shared__ unsigned short s_list[MAX_TILE_LAYERS];
     __shared__ int s_count;
+    __shared__ LayerDev s_layers[SM_LAYERS];
     load_tables(T);
     const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H);
     const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H, J.height);
@@ -507,6 +691,17 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
         s_count = c;
     }
     __syncthreads();
+    {
+        const int nsm = min(s_count, SM_LAYERS);
+        const int words = (int)(sizeof(LayerDev) / 4);
+        const int tid = threadIdx.y * CB_X + threadIdx.x;
+        for (int i = tid; i < nsm * words; i += CB_X * CB_Y) {
+            int l = i / words, w = i - l * words;
+            reinterpret_cast<unsigned int *>(&s_layers[l])[w] =
+                __ldg(reinterpret_cast<const unsigned int *>(&J.layers[s_list[l]]) + w);
+        }
+    }
+    __syncthreads();
 
     const int x0 = tile_x0 + threadIdx.x * CT_W, y0 = tile_y0 + threadIdx.y * CT_H;
     uchar4 px[CT_H][CT_W];
@@ -517,15 +712,19 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
 
     const int n = s_count;
     for (int li = 0; li < n; li++) {
-        const LayerDev &L = J.layers[s_list[li]];
+        const LayerDev &L = li < SM_LAYERS ? s_layers[li] : J.layers[s_list[li]];
         if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
 #pragma unroll
         for (int j = 0; j < CT_H; j++)
 #pragma unroll
             for (int i = 0; i < CT_W; i++) {
                 int X = x0 + i, Y = y0 + j;
-                if (X < J.width && Y < J.height && quad_covers(L, X, Y))
-                    px[j][i] = blend(T, J.mode, px[j][i], shade(T, J, L, X, Y));
+                if (X < J.width && Y < J.height && quad_covers(L, X, Y)) {
+                    bool pass;
+                    uchar4 texel;
+                    float4 src = shade(T, J, L, X, Y, pass, texel);
+                    px[j][i] = pass ? texel : blend(T, J.mode, px[j][i], src);
+                }
             }
     }
 

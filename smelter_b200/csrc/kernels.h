@@ -82,6 +82,22 @@ struct ResampleJob {
     int32_t box_fx, box_fy; // box pass when box_fx*box_fy > 1 (then weights unused)
 };
 
+// K1/K2 + both Lanczos passes fused (YUV source, horizontal pass first): see k_resample_fused
+struct FusedJob {
+    Tex src;                // TEX_YUV420 / TEX_NV12, even width and height
+    int32_t dst_w, dst_h;
+    uint8_t *dst;           // sRGB8 RGBA8
+    int32_t dst_pitch;
+    int32_t taps_h, taps_v;
+    const float *w_h, *inv_h;
+    const int32_t *first_h;
+    const float *w_v, *inv_v;
+    const int32_t *first_v;
+    int32_t seg_rows;       // output rows per block (multiple of 8)
+};
+// limits the host checks before choosing the fused kernel (mirrors FS_* in kernels.cu)
+constexpr int kFusedStripCols = 32, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 160, kFusedMaxTaps = 32;
+
 struct WeightJob {          // resample.wgsl:42-86 evaluated once per output coordinate
     float scale, offset;
     int32_t n_out, taps;
@@ -107,6 +123,7 @@ typedef void *Stream;  // cudaStream_t
 int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s);
 int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n_jobs, Stream s);
 int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n_jobs, Stream s);
+int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n_jobs, Stream s);
 int launch_composite(const CompositeJob &job, Stream s);
 int launch_output(const OutputJob &job, Stream s);
 int launch_fill_yuv(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,

@@ -198,6 +198,7 @@ class Renderer {
     smr_status plan_output(Output &o, smr_output_frame &of, uint64_t pts);
     smr_status get_weights(const KernelPass &p, WeightEntry &out);
     int materialised_input(Input &in);
+    int try_fused_resample(Input &in, const struct AxisMapping &hm, const struct AxisMapping &vm, int dw, int dh);
     void prepare_layer(const RenderLayout &l, int W, int H, int tex_index, int tex_w, int tex_h, dev::LayerDev &d, bool &skip);
     void shader_color(const RGBA &c, float out[4]) const;
 
@@ -218,6 +219,8 @@ class Renderer {
     std::vector<dev::ResampleJob> stage_jobs_[3];
     std::vector<std::pair<size_t, size_t>> stage_frame_off_[3];  // (src offset or SIZE_MAX, dst offset)
     std::vector<int> stage_src_tex_[3];       // texture-table index of the source, or -1 when src is a frame-arena f16
+    std::vector<dev::FusedJob> fused_jobs_;
+    std::vector<std::pair<int, size_t>> fused_src_dst_;   // (raw tex index, frame offset of dst)
     std::vector<dev::WeightJob> weight_jobs_;
     std::vector<std::pair<int, size_t>> convert_jobs_;  // (raw tex index, frame offset of RGBA8)
     std::vector<PendingComposite> composites_;
@@ -445,6 +448,42 @@ int Renderer::materialised_input(Input &in) {
     return in.node_tex;
 }
 
+// The common case -- a YUV input scaled on both axes, horizontal pass first, no box pre-pass -- runs as ONE
+// kernel (k_resample_fused).  Returns the texture-table index of the result, -1 when not eligible
+// (the generic multi-pass path is used), -2 on error.
+int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMapping &vm, int dw, int dh) {
+    const dev::Tex &t = in.tex;
+    if (t.kind != dev::TEX_YUV420 && t.kind != dev::TEX_NV12) return -1;
+    if ((t.width | t.height) & 1) return -1;
+    if (hm.predecimate_levels() != 0 || vm.predecimate_levels() != 0) return -1;
+    KernelPass passes[2];
+    if (plan_passes(hm, vm, passes) != 2 || passes[0].mapping.axis != 0) return -1;
+    float sh = hm.scale(), sv = vm.scale();
+    if (!(sh > 0.0f) || !(sv > 0.0f) || !(sh <= 4.001f) || !(sv <= 4.001f)) return -1;
+    int th = resample_taps(sh), tv = resample_taps(sv);
+    if (th > dev::kFusedMaxTaps || tv > dev::kFusedMaxTaps) return -1;
+    if ((int)std::ceil((dev::kFusedStripCols - 1) * sh) + th + 2 > dev::kFusedSpan) return -1;
+    if ((int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 2 > dev::kFusedRing) return -1;
+    WeightEntry wh, wv;
+    if (get_weights(passes[0], wh) != SMR_OK || get_weights(passes[1], wv) != SMR_OK) return -2;
+    size_t dst_off = frame_alloc((size_t)dw * dh * 4);
+    dev::FusedJob j{};
+    j.dst_w = dw; j.dst_h = dh; j.dst_pitch = dw * 4;
+    j.taps_h = wh.taps; j.taps_v = wv.taps;
+    j.w_h = wh.weights; j.inv_h = wh.inv; j.first_h = wh.first;
+    j.w_v = wv.weights; j.inv_v = wv.inv; j.first_v = wv.first;
+    int seg = ((dh + 3) / 4 + 7) & ~7;
+    j.seg_rows = std::max(seg, 64);
+    fused_jobs_.push_back(j);
+    fused_src_dst_.push_back({in.raw_tex, dst_off});
+    dev::Tex out;
+    out.kind = dev::TEX_RGBA8; out.width = dw; out.height = dh; out.pitch0 = dw * 4;
+    int idx = (int)tex_table_.size();
+    tex_table_.push_back(out);
+    tex_frame_off_.push_back(dst_off);
+    return idx;
+}
+
 void Renderer::shader_color(const RGBA &c, float out[4]) const {  // wgpu/utils.rs:51-71 + params.rs:353-361
     double a = (double)c.a / 255.0;
     if (opts_.rendering_mode == SMR_MODE_GPU_OPTIMIZED) {
@@ -629,6 +668,32 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
             set_error("RGBA output of a pass-through root must match the input resolution");
             return SMR_ERR_UNSUPPORTED;
         }
+        const bool same = in.res.width == o.res.width && in.res.height == o.res.height;
+        if (same && (o.format == SMR_OUT_RGBA8 || ((of.width % 2 == 0) && (of.height % 2 == 0)))) {
+            // Same size: K1 -> K10 runs as ONE composite launch with a single full-frame texture layer; an
+            // unmodified opaque texel passes through the sRGB target byte-exactly, so the bytes K10 sees
+            // are the node texture's.
+            RenderLayout l;
+            l.kind = RenderLayout::ChildNode;
+            l.width = (float)of.width; l.height = (float)of.height;
+            l.crop = {0.0f, 0.0f, (float)of.width, (float)of.height};
+            dev::LayerDev d;
+            bool skip;
+            prepare_layer(l, (int)of.width, (int)of.height, in.raw_tex, (int)of.width, (int)of.height, d, skip);
+            PendingComposite pc;
+            memset(&pc.job, 0, sizeof(pc.job));
+            pc.job.width = (int)of.width; pc.job.height = (int)of.height; pc.job.mode = mode;
+            pc.job.n_layers = skip ? 0 : 1;
+            pc.layers_off = param_alloc(sizeof(dev::LayerDev));
+            pc.masks_off = param_alloc(sizeof(dev::MaskDev));
+            if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
+            memcpy(param_host_.data() + pc.layers_off, &d, sizeof(d));
+            pc.job.out_format = o.format;
+            pc.job.out0 = dst[0]; pc.job.out1 = dst[1]; pc.job.out2 = dst[2];
+            pc.job.out_pitch0 = pitch[0]; pc.job.out_pitch1 = pitch[1]; pc.job.out_pitch2 = pitch[2];
+            composites_.push_back(pc);
+            return SMR_OK;
+        }
         push_output_job(in.raw_tex, 0);
         return SMR_OK;
     }
@@ -669,6 +734,10 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
                         auto hit = resample_cache_.find(key);
                         if (hit != resample_cache_.end()) {
                             tex_index = hit->second;  // same input/crop/size already resampled this tick
+                        } else if (int fused_tex = try_fused_resample(*in, hm, vm, dw, dh); fused_tex != -1) {
+                            if (fused_tex < -1) return SMR_ERR_CUDA;
+                            tex_index = fused_tex;
+                            resample_cache_[key] = tex_index;
                         } else {
                             int src_tex = materialised_input(*in);
                             int levels[2] = {hm.predecimate_levels(), vm.predecimate_levels()};
@@ -796,6 +865,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     tick_++;
     tex_table_.clear(); tex_frame_off_.clear();
     for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
+    fused_jobs_.clear(); fused_src_dst_.clear();
     weight_jobs_.clear(); convert_jobs_.clear(); composites_.clear(); output_jobs_.clear(); output_src_tex_.clear();
     fills_.clear(); d2h_.clear(); resample_cache_.clear();
     param_used_ = 0; frame_used_ = 0;
@@ -833,18 +903,24 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             j.dst = fb + stage_frame_off_[s][i].second;
         }
     for (size_t i = 0; i < output_jobs_.size(); i++) output_jobs_[i].src = tex_table_[output_src_tex_[i]];
+    for (size_t i = 0; i < fused_jobs_.size(); i++) {
+        fused_jobs_[i].src = tex_table_[fused_src_dst_[i].first];
+        fused_jobs_[i].dst = fb + fused_src_dst_[i].second;
+    }
 
     // ---- pack the parameter arena and ship it in one copy -------------------------------------
     size_t tex_off = param_alloc(sizeof(dev::Tex) * std::max<size_t>(tex_table_.size(), 1));
     size_t stage_off[3], wj_off;
     for (int s = 0; s < 3; s++) stage_off[s] = param_alloc(sizeof(dev::ResampleJob) * std::max<size_t>(stage_jobs_[s].size(), 1));
     wj_off = param_alloc(sizeof(dev::WeightJob) * std::max<size_t>(weight_jobs_.size(), 1));
+    size_t fj_off = param_alloc(sizeof(dev::FusedJob) * std::max<size_t>(fused_jobs_.size(), 1));
     if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
     if (!tex_table_.empty()) memcpy(param_host_.data() + tex_off, tex_table_.data(), sizeof(dev::Tex) * tex_table_.size());
     for (int s = 0; s < 3; s++)
         if (!stage_jobs_[s].empty())
             memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
+    if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
     CUDA_OK(param_pinned_.ensure(param_used_));
     CUDA_OK(param_dev_.ensure(param_used_));
     memcpy(param_pinned_.p, param_host_.data(), param_used_);
@@ -861,6 +937,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     }
     if (!launched(dev::launch_weights((const dev::WeightJob *)(pd + wj_off), weight_jobs_.data(), (int)weight_jobs_.size(), stream_))) goto fail;
     if (!weight_jobs_.empty()) prof_mark(SMR_KERNEL_WEIGHTS);
+    if (!launched(dev::launch_resample_fused((const dev::FusedJob *)(pd + fj_off), fused_jobs_.data(), (int)fused_jobs_.size(), stream_))) goto fail;
+    if (!fused_jobs_.empty()) prof_mark(SMR_KERNEL_RESAMPLE_FUSED);
     for (int s = 0; s < 3; s++) {
         if (!launched(dev::launch_resample((const dev::ResampleJob *)(pd + stage_off[s]), stage_jobs_[s].data(),
                                            (int)stage_jobs_[s].size(), stream_))) goto fail;

@@ -173,3 +173,12 @@ def test_chroma_upsample_phase_is_quarter():
     # b channel follows u: pixels 6,7 (chroma texel 3) get .75 weight, 5 and 8 get .25
     b = rgba[0, :, 2].astype(int)
     assert b[6] == b[7] and b[5] == b[8] and b[4] == b[9] and b[6] > b[5] > b[4]
+
+
+def test_even_size_sampler_phases_exhaustive():
+    """The CUDA fast paths hard-code the NC-6 taps for even plane sizes; prove the generic formula the
+    oracle evaluates gives exactly those taps for EVERY even size up to 8192 and every coordinate."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_check_even_size_phases.restype = C.c_long
+    assert L.orc_check_even_size_phases(8192) == 0
