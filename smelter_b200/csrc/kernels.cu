@@ -380,8 +380,9 @@ __device__ __forceinline__ void yuv_px_linear(const Tables &T, const Tex &s, int
 __global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused(const FusedJob *jobs) {
     extern __shared__ __align__(16) unsigned char fs_raw[];
     FusedSmem &S = *reinterpret_cast<FusedSmem *>(fs_raw);
-    load_tables(S.T);
     const FusedJob &J = jobs[blockIdx.z];
+    if (J.variant != 0) return;  // handled by k_resample_fused_int
+    load_tables(S.T);
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int ox0 = blockIdx.x * FS_TW;
     if (ox0 >= J.dst_w) return;
@@ -460,6 +461,199 @@ __global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused(const FusedJ
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same fused resample specialised for an INTEGER horizontal ratio S (2:1, 3:1, 4:1 with a zero crop
+// offset -- every grid / mosaic of the BASELINE configs).  Then first(o) = S*o + const and every output column
+// has the same TAPS = 6S+1 weights (exact small-integer arithmetic in resample.wgsl:45-50), which allows:
+//   * weights in registers, no per-tap weight fetch;
+//   * register blocking: a lane produces 4 adjacent output columns from one (3S+TAPS)-long window, so a
+//     shared-memory value feeds up to 4 FMAs (the plain kernel is shared-memory-bandwidth bound at 1 FMA/load);
+//   * a warp converts and filters 4 source rows per step (4 rows x 8 column groups x 4 columns);
+//   * K1/K2 on chroma-aligned pixel PAIRS (the .25/.75 chroma taps of the two pixels share 3 chroma texels);
+//   * conflict-free shared memory: value i of a row sits at i + 4*(i/16) and row stride = 1 (mod 32).
+// Accumulation order per output is tap 0..TAPS-1 exactly as in the shader, so results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+#define FI_ROWS 4                        // source rows per warp step
+#define FI_ROWSTRIDE 193                 // floats; == 1 (mod 32); >= padded span (150 + 9*4)
+#define FI_MAXSPAN 176                   // (FS_TW-1)*4 + 25 + alignment, before padding
+
+template <int S>
+struct FusedIntSmem {
+    Tables T;
+    float ring[FS_RING][3][FS_TW];
+    float srow[FS_WARPS][3][FI_ROWS][FI_ROWSTRIDE];
+};
+
+__device__ __forceinline__ int fi_pos(int i) { return i + ((i >> 4) << 2); }
+
+// K1/K2 of the chroma-aligned pixel pair (x, x+1), x even, 2 <= x, x + 3 <= W - 1 (no clamping needed)
+template <bool NV12>
+__device__ __forceinline__ void yuv_pair(const Tables &T, const Tex &s, const uint8_t *yrow, const uint8_t *c0a,
+                                         const uint8_t *c1a, const uint8_t *c0b, const uint8_t *c1b, int x, float fy,
+                                         uchar4 &pe, uchar4 &po) {
+    const int cx = x >> 1;
+    const uchar2 yy = __ldg(reinterpret_cast<const uchar2 *>(yrow + x));
+    float ua0, ub0, ud0, ua1, ub1, ud1, va0, vb0, vd0, va1, vb1, vd1;
+    if (NV12) {
+        const uchar2 *r0 = reinterpret_cast<const uchar2 *>(c0a) + cx, *r1 = reinterpret_cast<const uchar2 *>(c1a) + cx;
+        uchar2 a0 = __ldg(r0 - 1), b0 = __ldg(r0), d0 = __ldg(r0 + 1), a1 = __ldg(r1 - 1), b1 = __ldg(r1), d1 = __ldg(r1 + 1);
+        ua0 = T.u8n[a0.x]; ub0 = T.u8n[b0.x]; ud0 = T.u8n[d0.x]; ua1 = T.u8n[a1.x]; ub1 = T.u8n[b1.x]; ud1 = T.u8n[d1.x];
+        va0 = T.u8n[a0.y]; vb0 = T.u8n[b0.y]; vd0 = T.u8n[d0.y]; va1 = T.u8n[a1.y]; vb1 = T.u8n[b1.y]; vd1 = T.u8n[d1.y];
+    } else {
+        ua0 = T.u8n[__ldg(c0a + cx - 1)]; ub0 = T.u8n[__ldg(c0a + cx)]; ud0 = T.u8n[__ldg(c0a + cx + 1)];
+        ua1 = T.u8n[__ldg(c1a + cx - 1)]; ub1 = T.u8n[__ldg(c1a + cx)]; ud1 = T.u8n[__ldg(c1a + cx + 1)];
+        va0 = T.u8n[__ldg(c0b + cx - 1)]; vb0 = T.u8n[__ldg(c0b + cx)]; vd0 = T.u8n[__ldg(c0b + cx + 1)];
+        va1 = T.u8n[__ldg(c1b + cx - 1)]; vb1 = T.u8n[__ldg(c1b + cx)]; vd1 = T.u8n[__ldg(c1b + cx + 1)];
+    }
+    const float ify = 1.0f - fy;
+    // even pixel: taps (cx-1, cx), fx = .75 ; odd pixel: taps (cx, cx+1), fx = .25   (bilerp of NC-6)
+    float ue = fmaf(fmaf(ub1, 0.75f, ua1 * 0.25f), fy, fmaf(ub0, 0.75f, ua0 * 0.25f) * ify);
+    float uo = fmaf(fmaf(ud1, 0.25f, ub1 * 0.75f), fy, fmaf(ud0, 0.25f, ub0 * 0.75f) * ify);
+    float ve = fmaf(fmaf(vb1, 0.75f, va1 * 0.25f), fy, fmaf(vb0, 0.75f, va0 * 0.25f) * ify);
+    float vo = fmaf(fmaf(vd1, 0.25f, vb1 * 0.75f), fy, fmaf(vd0, 0.25f, vb0 * 0.75f) * ify);
+    pe = yuv_to_rgba8(T.u8n[yy.x], ue, ve, s.full_range);
+    po = yuv_to_rgba8(T.u8n[yy.y], uo, vo, s.full_range);
+}
+
+template <int S, bool NV12>
+__global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused_int(const FusedJob *jobs) {
+    constexpr int TAPS = 6 * S + 1;
+    constexpr int WIN = 3 * S + TAPS;  // window feeding 4 adjacent output columns
+    extern __shared__ __align__(16) unsigned char fs_raw[];
+    FusedIntSmem<S> &M = *reinterpret_cast<FusedIntSmem<S> *>(fs_raw);
+    const FusedJob &J = jobs[blockIdx.z];
+    if (J.variant != S || (J.src.kind == TEX_NV12) != NV12) return;
+    load_tables(M.T);
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int ox0 = blockIdx.x * FS_TW;
+    if (ox0 >= J.dst_w) return;
+    const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
+    if (oy_begin >= J.dst_h) return;
+    const Tex &src = J.src;
+    const int W = src.width, H = src.height, cwid = W >> 1, chei = H >> 1;
+    const int tv = J.taps_v;
+
+    float w[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) w[t] = __ldg(J.w_h + t);  // identical for every column
+    const float inv_h = __ldg(J.inv_h);
+    const int xa = __ldg(J.first_h + ox0);      // first(o) = S*o + const
+    const int xa_e = xa & ~1;                   // chroma-aligned start (xa may be negative: & ~1 floors)
+    const int d0 = xa - xa_e;
+    const int span = (FS_TW - 1) * S + TAPS + d0;
+    const int npairs = (span + 1) >> 1;
+    const int rr = lane >> 3, cg = lane & 7;
+
+    int produced_hi = -0x40000000;
+    for (int o0 = oy_begin; o0 < oy_end; o0 += FS_WARPS) {
+        const int o_l = min(o0 + FS_WARPS - 1, oy_end - 1);
+        const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
+        const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
+        const int start = max(produced_hi + 1, need_lo);
+        // ---- phase A: chunks of FI_ROWS source rows per warp ---------------------------------------
+        for (int r0 = start + warp * FI_ROWS; r0 <= need_hi; r0 += FS_WARPS * FI_ROWS) {
+            // A1: convert (K1/K2 -> u8 -> sRGB decode) the strip's pixels of rows r0..r0+3
+#pragma unroll 1
+            for (int k = 0; k < FI_ROWS; k++) {
+                const int r = r0 + k;
+                if (r > need_hi) break;
+                const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
+                const int cy0 = (r & 1) ? (r >> 1) : max((r >> 1) - 1, 0), cy1 = (r & 1) ? min((r >> 1) + 1, chei - 1) : (r >> 1);
+                const float fy = (r & 1) ? 0.25f : 0.75f;
+                const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
+                const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
+                const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
+                float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
+                for (int p = lane; p < npairs; p += 32) {
+                    const int x = xa_e + 2 * p;
+                    uchar4 pe, po;
+                    if (x >= 2 && x + 3 <= W - 1) {
+                        yuv_pair<NV12>(M.T, src, yrow, c0a, c1a, c0b, c1b, x, fy, pe, po);
+                    } else {  // image border: resample.wgsl clamps the tap index
+                        pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
+                        po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
+                    }
+                    const int q = fi_pos(2 * p);
+                    sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
+                    sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                }
+            }
+            __syncwarp();
+            // A2: horizontal Lanczos, lane = (row rr, column group cg) -> 4 adjacent output columns
+            const int r = r0 + rr;
+            if (r <= need_hi) {
+                const int i0 = 4 * S * cg + d0;   // window start of column ox0 + 4*cg, relative to xa_e
+                float *ringrow = &M.ring[r & (FS_RING - 1)][0][0];
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float *sp = M.srow[warp][ch][rr];
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < WIN; j++) {
+                        const float v = sp[fi_pos(i0 + j)];
+                        if (j < TAPS) a0 = fmaf(v, w[j], a0);
+                        if (j >= S && j - S < TAPS) a1 = fmaf(v, w[j - S], a1);
+                        if (j >= 2 * S && j - 2 * S < TAPS) a2 = fmaf(v, w[j - 2 * S], a2);
+                        if (j >= 3 * S) a3 = fmaf(v, w[j - 3 * S], a3);
+                    }
+                    float *dst = ringrow + ch * FS_TW + 4 * cg;
+                    dst[0] = __half2float(__float2half_rn(a0 * inv_h));  // NC-5
+                    dst[1] = __half2float(__float2half_rn(a1 * inv_h));
+                    dst[2] = __half2float(__float2half_rn(a2 * inv_h));
+                    dst[3] = __half2float(__float2half_rn(a3 * inv_h));
+                }
+            }
+            __syncwarp();
+        }
+        produced_hi = max(produced_hi, need_hi);
+        __syncthreads();
+        // ---- phase B: vertical pass, one output row per warp (any ratio) -------------------------------
+        const int oy = o0 + warp;
+        if (oy < oy_end) {
+            const int fv = __ldg(J.first_v + oy);
+            const float *wv = J.w_v + (size_t)oy * tv;
+            float ar = 0.f, ag = 0.f, ab = 0.f;
+            if (fv >= 0 && fv + tv - 1 <= H - 1) {
+                for (int t = 0; t < tv; t++) {
+                    const float wt = __ldg(wv + t);
+                    const float *p = &M.ring[(fv + t) & (FS_RING - 1)][0][0];
+                    ar = fmaf(p[lane], wt, ar);
+                    ag = fmaf(p[FS_TW + lane], wt, ag);
+                    ab = fmaf(p[2 * FS_TW + lane], wt, ab);
+                }
+            } else {
+                for (int t = 0; t < tv; t++) {
+                    const float wt = __ldg(wv + t);
+                    const int row = min(max(fv + t, 0), H - 1);
+                    const float *p = &M.ring[row & (FS_RING - 1)][0][0];
+                    ar = fmaf(p[lane], wt, ar);
+                    ag = fmaf(p[FS_TW + lane], wt, ag);
+                    ab = fmaf(p[2 * FS_TW + lane], wt, ab);
+                }
+            }
+            const float inv_v = __ldg(J.inv_v + oy);
+            if (ox0 + lane < J.dst_w) {
+                uchar4 o = make_uchar4((unsigned char)srgb_encode(M.T, ar * inv_v), (unsigned char)srgb_encode(M.T, ag * inv_v),
+                                       (unsigned char)srgb_encode(M.T, ab * inv_v), 255);
+                reinterpret_cast<uchar4 *>(J.dst + (size_t)oy * J.dst_pitch)[ox0 + lane] = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int S, bool NV12>
+static bool launch_fused_int(const FusedJob *jobs_dev, dim3 g, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_resample_fused_int<S, NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(FusedIntSmem<S>));
+        attr_set = true;
+    }
+    k_resample_fused_int<S, NV12><<<g, dim3(FS_TW, FS_WARPS), sizeof(FusedIntSmem<S>), s>>>(jobs_dev);
+    return check_launch("k_resample_fused_int");
+}
+
 int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n, Stream s) {
     if (n <= 0) return 0;
     static bool attr_set = false;
@@ -468,14 +662,31 @@ int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, i
         attr_set = true;
     }
     int mx = 1, my = 1;
+    bool have[5][2] = {};
     for (int i = 0; i < n; i++) {
         int sx = (jobs_host[i].dst_w + FS_TW - 1) / FS_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
         mx = sx > mx ? sx : mx;
         my = sy > my ? sy : my;
+        int v = jobs_host[i].variant;
+        have[(v >= 2 && v <= 4) ? v : 0][jobs_host[i].src.kind == TEX_NV12 ? 1 : 0] = true;
     }
-    dim3 b(FS_TW, FS_WARPS), g(mx, my, n);
-    k_resample_fused<<<g, b, sizeof(FusedSmem), (cudaStream_t)s>>>(jobs_dev);
-    return check_launch("k_resample_fused") ? 1 : -1;
+    dim3 g(mx, my, n);
+    cudaStream_t st = (cudaStream_t)s;
+    int launches = 0;
+    // one launch per kernel variant present in the tick; blocks of jobs of another variant exit at once
+    if (have[0][0] || have[0][1]) {
+        k_resample_fused<<<g, dim3(FS_TW, FS_WARPS), sizeof(FusedSmem), st>>>(jobs_dev);
+        if (!check_launch("k_resample_fused")) return -1;
+        launches++;
+    }
+#define SMR_LAUNCH_INT(SV)                                                                   \
+    if (have[SV][0]) { if (!launch_fused_int<SV, false>(jobs_dev, g, st)) return -1; launches++; } \
+    if (have[SV][1]) { if (!launch_fused_int<SV, true>(jobs_dev, g, st)) return -1; launches++; }
+    SMR_LAUNCH_INT(2)
+    SMR_LAUNCH_INT(3)
+    SMR_LAUNCH_INT(4)
+#undef SMR_LAUNCH_INT
+    return launches;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -666,6 +877,16 @@ __device__ __forceinline__ float to_v(float r, float g, float b) {
     return fmaf(v + 0.5f, 0.87843137254f, K16);
 }
 
+// general per-pixel path: full fragment shader + fixed-function blend.  Kept out of line: the fast paths of
+// k_composite cover almost every pixel and the instruction cache matters more than the call.
+__device__ __noinline__ uchar4 shade_blend(const Tables &T, const CompositeJob &J, const LayerDev &L, int X, int Y,
+                                           uchar4 dst) {
+    bool pass;
+    uchar4 texel;
+    float4 src = shade(T, J, L, X, Y, pass, texel);
+    return pass ? texel : blend(T, J.mode, dst, src);
+}
+
 #define CT_W 4           // pixels per thread, x
 #define CT_H 2           // pixels per thread, y
 #define CB_X 32          // threads per block, x
@@ -714,18 +935,44 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
     for (int li = 0; li < n; li++) {
         const LayerDev &L = li < SM_LAYERS ? s_layers[li] : J.layers[s_list[li]];
         if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
+        const bool all_in = x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1;
+        if (all_in && (L.fast & FAST_CONST)) {  // opaque colour interior: the layer leaves constant bytes
+            const uchar4 cb = *reinterpret_cast<const uchar4 *>(&L.const_bytes);
 #pragma unroll
-        for (int j = 0; j < CT_H; j++)
+            for (int j = 0; j < CT_H; j++)
 #pragma unroll
-            for (int i = 0; i < CT_W; i++) {
-                int X = x0 + i, Y = y0 + j;
-                if (X < J.width && Y < J.height && quad_covers(L, X, Y)) {
-                    bool pass;
-                    uchar4 texel;
-                    float4 src = shade(T, J, L, X, Y, pass, texel);
-                    px[j][i] = pass ? texel : blend(T, J.mode, px[j][i], src);
+                for (int i = 0; i < CT_W; i++) px[j][i] = cb;
+            continue;
+        }
+        if (all_in && (L.fast & FAST_IDENT)) {  // 1:1 texture interior: exact texel per pixel
+            const Tex &S = J.textures[L.tex];
+#pragma unroll
+            for (int j = 0; j < CT_H; j++)
+#pragma unroll
+                for (int i = 0; i < CT_W; i++) {
+                    uchar4 t = node_texel(T, S, x0 + i + L.tx_off, y0 + j + L.ty_off);
+                    if (t.w == 255) px[j][i] = t;  // encode(decode(b)) == b
+                    else {
+                        const float *lut = J.mode == 0 ? T.dec : T.u8n;
+                        px[j][i] = blend(T, J.mode, px[j][i], make_float4(lut[t.x], lut[t.y], lut[t.z], T.u8n[t.w]));
+                    }
                 }
+            continue;
+        }
+        for (int k = 0; k < CT_W * CT_H; k++) {  // general path, deliberately not unrolled (code size)
+            const int i = k & (CT_W - 1), j = k / CT_W;
+            const int X = x0 + i, Y = y0 + j;
+            if (X < J.width && Y < J.height && quad_covers(L, X, Y)) {
+                uchar4 cur = j == 0 ? (i == 0 ? px[0][0] : i == 1 ? px[0][1] : i == 2 ? px[0][2] : px[0][3])
+                                    : (i == 0 ? px[1][0] : i == 1 ? px[1][1] : i == 2 ? px[1][2] : px[1][3]);
+                uchar4 res = shade_blend(T, J, L, X, Y, cur);
+#pragma unroll
+                for (int jj = 0; jj < CT_H; jj++)
+#pragma unroll
+                    for (int ii = 0; ii < CT_W; ii++)
+                        if (jj == j && ii == i) px[jj][ii] = res;
             }
+        }
     }
 
     if (x0 >= J.width || y0 >= J.height) return;

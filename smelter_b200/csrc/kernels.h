@@ -50,8 +50,14 @@ struct LayerDev {
     int32_t tex;                     // index into the texture table; -1 = empty 1x1 texture
     float crop_sx, crop_ox, crop_sy, crop_oy;  // crop_w/dim, crop_left/dim, crop_h/dim, crop_top/dim
     int32_t mask_begin, mask_count;
-    int32_t opaque_fast;             // host hint: no masks/radius/border/rotation -> cheap interior test
+    // host-proved fast region: for pixels in [ix0,ix1)x[iy0,iy1) the rounded-rect / border / mask factors are
+    // all exactly 1 (>= 2 px inside every edge and radius), so the fragment is the bare colour or sample
+    int32_t ix0, ix1, iy0, iy1;
+    int32_t fast;                    // FAST_* bits
+    int32_t tx_off, ty_off;          // FAST_IDENT: texel = (px + tx_off, py + ty_off)
+    uint32_t const_bytes;            // FAST_CONST: bytes an opaque colour leaves in the target (RGBA little endian)
 };
+enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2 };
 
 struct CompositeJob {
     int32_t width, height;           // render target (root node texture) size
@@ -94,6 +100,7 @@ struct FusedJob {
     const float *w_v, *inv_v;
     const int32_t *first_v;
     int32_t seg_rows;       // output rows per block (multiple of 8)
+    int32_t variant;        // 0: generic kernel; 2,3,4: integer horizontal ratio (k_resample_fused_int<S>)
 };
 // limits the host checks before choosing the fused kernel (mirrors FS_* in kernels.cu)
 constexpr int kFusedStripCols = 32, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 160, kFusedMaxTaps = 32;

@@ -474,6 +474,8 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     j.w_v = wv.weights; j.inv_v = wv.inv; j.first_v = wv.first;
     int seg = ((dh + 3) / 4 + 7) & ~7;
     j.seg_rows = std::max(seg, 64);
+    j.variant = 0;
+    if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) j.variant = (int)sh;
     fused_jobs_.push_back(j);
     fused_src_dst_.push_back({in.raw_tex, dst_off});
     dev::Tex out;
@@ -496,6 +498,23 @@ void Renderer::shader_color(const RGBA &c, float out[4]) const {  // wgpu/utils.
         out[2] = (float)(a * (double)c.b / 255.0);
     }
     out[3] = (float)a;
+}
+
+static float g_thr_host[255];
+static bool g_thr_init = false;
+static uint8_t unorm8_host(float x) { return (uint8_t)std::rint(std::fmin(std::fmax(x, 0.0f), 1.0f) * 255.0f); }
+static uint8_t srgb_encode_host(float lin) {  // numeric contract NC-4, same thresholds as the device table
+    if (!g_thr_init) {
+        for (int k = 0; k < 255; k++) g_thr_host[k] = (float)eotf_f64(((double)k + 0.5) / 255.0);
+        g_thr_init = true;
+    }
+    float x = std::fmin(std::fmax(lin, 0.0f), 1.0f);
+    int lo = 0, hi = 255;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (x >= g_thr_host[mid]) lo = mid + 1; else hi = mid;
+    }
+    return (uint8_t)lo;
 }
 
 static inline long long snap256(float v) { return (long long)std::rint(v * 256.0f); }
@@ -559,6 +578,52 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
     if (l.kind == RenderLayout::ChildNode) {
         d.crop_sx = l.crop.width / (float)tex_w; d.crop_ox = l.crop.left / (float)tex_w;
         d.crop_sy = l.crop.height / (float)tex_h; d.crop_oy = l.crop.top / (float)tex_h;
+    }
+    // ---- fast interior (see LayerDev): only where every alpha factor of fs_main is provably exactly 1 ----
+    d.ix0 = d.ix1 = d.iy0 = d.iy1 = 0;
+    if (!d.rotated && l.kind != RenderLayout::BoxShadow) {
+        const float m = 2.0f;
+        float rmax = std::fmax(std::fmax(l.border_radius.top_left, l.border_radius.top_right),
+                               std::fmax(l.border_radius.bottom_left, l.border_radius.bottom_right));
+        float shrink = (l.border_width >= 1.0f ? l.border_width + 1.0f : 0.0f) + std::fmax(rmax, 0.0f) + m;
+        float lo_x = l.left + shrink, hi_x = l.left + l.width - shrink;
+        float lo_y = l.top + shrink, hi_y = l.top + l.height - shrink;
+        size_t nm = std::min<size_t>(l.masks.size(), SMR_MAX_MASKS);
+        for (size_t i = 0; i < nm; i++) {
+            const Mask &k = l.masks[i];
+            float mr = std::fmax(std::fmax(k.radius.top_left, k.radius.top_right),
+                                 std::fmax(k.radius.bottom_left, k.radius.bottom_right));
+            float ms = std::fmax(mr, 0.0f) + m;
+            lo_x = std::fmax(lo_x, k.left + ms); hi_x = std::fmin(hi_x, k.left + k.width - ms);
+            lo_y = std::fmax(lo_y, k.top + ms); hi_y = std::fmin(hi_y, k.top + k.height - ms);
+        }
+        if (lo_x == lo_x && hi_x == hi_x && lo_y == lo_y && hi_y == hi_y && lo_x < hi_x && lo_y < hi_y) {
+            // pixel X is inside iff lo <= X + .5 <= hi
+            d.ix0 = std::max((int)std::ceil(lo_x - 0.5f), d.px0); d.ix1 = std::min((int)std::floor(hi_x - 0.5f) + 1, d.px1);
+            d.iy0 = std::max((int)std::ceil(lo_y - 0.5f), d.py0); d.iy1 = std::min((int)std::floor(hi_y - 0.5f) + 1, d.py1);
+            if (d.ix0 >= d.ix1 || d.iy0 >= d.iy1) d.ix0 = d.ix1 = d.iy0 = d.iy1 = 0;
+        }
+        if (d.ix0 < d.ix1) {
+            if (l.kind == RenderLayout::Color && l.color.a == 255) {
+                // opaque colour: fma(dst, 0, src) == src, so the target bytes are a constant of the layer
+                d.fast |= dev::FAST_CONST;
+                uint8_t b[4];
+                for (int c = 0; c < 3; c++)
+                    b[c] = opts_.rendering_mode == SMR_MODE_GPU_OPTIMIZED ? srgb_encode_host(d.color[c]) : unorm8_host(d.color[c]);
+                b[3] = 255;
+                memcpy(&d.const_bytes, b, 4);
+            }
+            auto integral = [](float v) { return v == std::rint(v) && std::fabs(v) <= 4096.0f; };
+            if (l.kind == RenderLayout::ChildNode && tex_index >= 0 && tex_w <= 4096 && tex_h <= 4096 &&
+                l.width == (float)tex_w && l.crop.width == (float)tex_w && l.height == (float)tex_h &&
+                l.crop.height == (float)tex_h && integral(l.left) && integral(l.top) && l.crop.left == 0.0f &&
+                l.crop.top == 0.0f) {
+                // 1:1 mapping on whole texels: the NC-6 tap is texel (px - left, py - top) with weight exactly 1
+                // (|coordinate error| < 1e-3 << 1/512, the 8-bit weight rounds to 0 or 1)
+                d.fast |= dev::FAST_IDENT;
+                d.tx_off = -(int)l.left; d.ty_off = -(int)l.top;
+            }
+        }
     }
     skip = false;
 }

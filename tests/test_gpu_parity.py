@@ -316,3 +316,29 @@ def test_full_size_config3_properties():
             ty, tx = divmod(slot, 4)
             assert np.array_equal(a[0][ty * 540:(ty + 1) * 540, tx * 960:(tx + 1) * 960], one[0])
             assert np.array_equal(a[1][ty * 270:(ty + 1) * 270, tx * 480:(tx + 1) * 480], one[1])
+
+
+@pytest.mark.parametrize("kind", ["nv12", "yuv420"])
+def test_integer_ratio_4to1_fused_kernel(kind):
+    """BASELINE config 3 geometry at 1/3 size: 1280x720 -> 320x180 tiles (exactly 4:1, 25 taps) through the
+    register-blocked fused kernel, NV12 and planar, including the clamped border strips"""
+    mk = nv12_frame if kind == "nv12" else yuv_frame
+    fr = {f"input_{i}": mk(harness.random_yuv420(300 + i, 1280, 720) if i % 2 else harness.smooth_yuv420(300 + i, 1280, 720),
+                           1280, 720) for i in range(1, 5)}
+    kids = [s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(12.0)) for c in streams(4)]
+    over = V(position=s.Position.Absolute(width=300.0, height=80.0, left=170.0, bottom=20.0),
+             background_color=s.RGBAColor(16, 32, 160, 112), border_radius=s.BorderRadius.new_with_radius(16.0))
+    scene = V(background_color=BG, children=[s.TilesComponent(children=kids, background_color=BG), over])
+    check(scene, fr, out_format=NV12)
+
+
+def test_wide_identity_mapping_4k_row():
+    """FAST_IDENT / FAST_CONST interior paths at 4K width (largest coordinates the shortcut is allowed for)"""
+    w, h = 3840, 64
+    fr = {"input_1": nv12_frame(harness.random_yuv420(9, w, h), w, h)}
+    scene = V(background_color=BG, children=[
+        V(children=streams(1), position=s.Position.Absolute(width=float(w), height=float(h), left=0.0, top=0.0)),
+        V(position=s.Position.Absolute(width=900.0, height=40.0, left=1500.0, top=10.0),
+          background_color=s.RGBAColor(200, 10, 10, 255), border_width=3.0, border_color=s.RGBAColor(255, 255, 255, 255),
+          border_radius=s.BorderRadius.new_with_radius(9.0))])
+    check(scene, fr, resolution=s.Resolution(w, h), out_format=NV12)
