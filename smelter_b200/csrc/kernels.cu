@@ -549,33 +549,69 @@ __global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused_int(const Fu
         const int o_l = min(o0 + FS_WARPS - 1, oy_end - 1);
         const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
         const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
-        const int start = max(produced_hi + 1, need_lo);
+        const int start = max(produced_hi + 1, need_lo) & ~1;  // even: chunks share chroma rows (re-making a row is harmless)
         // ---- phase A: chunks of FI_ROWS source rows per warp ---------------------------------------
         for (int r0 = start + warp * FI_ROWS; r0 <= need_hi; r0 += FS_WARPS * FI_ROWS) {
-            // A1: convert (K1/K2 -> u8 -> sRGB decode) the strip's pixels of rows r0..r0+3
-#pragma unroll 1
-            for (int k = 0; k < FI_ROWS; k++) {
-                const int r = r0 + k;
-                if (r > need_hi) break;
-                const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
-                const int cy0 = (r & 1) ? (r >> 1) : max((r >> 1) - 1, 0), cy1 = (r & 1) ? min((r >> 1) + 1, chei - 1) : (r >> 1);
-                const float fy = (r & 1) ? 0.25f : 0.75f;
-                const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
-                const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
-                const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
-                float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
+            // A1: convert (K1/K2 -> u8 -> sRGB decode) the strip's pixels of rows r0..r0+3 (r0 is even).
+            // A lane owns a chroma-aligned pixel-pair COLUMN for all 4 rows: the 4 chroma rows j-1..j+2 they
+            // touch are loaded and horizontally interpolated once (bilerp of NC-6 is h-then-v, so the
+            // horizontal terms are shared bit-exactly between the rows that use the same chroma row).
+            {
+                const int nrows = min(FI_ROWS, need_hi - r0 + 1);
+                const int j = r0 >> 1;
+                const uint8_t *ca[4], *cb[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int cy = min(max(j - 1 + i, 0), chei - 1);
+                    ca[i] = src.p1 + (size_t)cy * src.pitch1;
+                    cb[i] = NV12 ? nullptr : src.p2 + (size_t)cy * src.pitch2;
+                }
+                const uint8_t *yrow0 = src.p0 + (size_t)r0 * src.pitch0;
                 for (int p = lane; p < npairs; p += 32) {
                     const int x = xa_e + 2 * p;
-                    uchar4 pe, po;
-                    if (x >= 2 && x + 3 <= W - 1) {
-                        yuv_pair<NV12>(M.T, src, yrow, c0a, c1a, c0b, c1b, x, fy, pe, po);
-                    } else {  // image border: resample.wgsl clamps the tap index
-                        pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
-                        po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
-                    }
                     const int q = fi_pos(2 * p);
-                    sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
-                    sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                    if (x >= 2 && x + 3 <= W - 1) {
+                        const int cx = x >> 1;
+                        float hue[4], huo[4], hve[4], hvo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float ua, ub, ud, va, vb, vd;
+                            if (NV12) {
+                                const uchar2 *rp = reinterpret_cast<const uchar2 *>(ca[i]) + cx;
+                                const uchar2 a = __ldg(rp - 1), b2 = __ldg(rp), d = __ldg(rp + 1);
+                                ua = M.T.u8n[a.x]; ub = M.T.u8n[b2.x]; ud = M.T.u8n[d.x];
+                                va = M.T.u8n[a.y]; vb = M.T.u8n[b2.y]; vd = M.T.u8n[d.y];
+                            } else {
+                                ua = M.T.u8n[__ldg(ca[i] + cx - 1)]; ub = M.T.u8n[__ldg(ca[i] + cx)]; ud = M.T.u8n[__ldg(ca[i] + cx + 1)];
+                                va = M.T.u8n[__ldg(cb[i] + cx - 1)]; vb = M.T.u8n[__ldg(cb[i] + cx)]; vd = M.T.u8n[__ldg(cb[i] + cx + 1)];
+                            }
+                            hue[i] = fmaf(ub, 0.75f, ua * 0.25f); huo[i] = fmaf(ud, 0.25f, ub * 0.75f);
+                            hve[i] = fmaf(vb, 0.75f, va * 0.25f); hvo[i] = fmaf(vd, 0.25f, vb * 0.75f);
+                        }
+#pragma unroll
+                        for (int k = 0; k < FI_ROWS; k++) {
+                            if (k < nrows) {
+                                const int i0 = (k + 1) >> 1, i1 = i0 + 1;
+                                const float fy = (k & 1) ? 0.25f : 0.75f, ify = (k & 1) ? 0.75f : 0.25f;
+                                const uchar2 yy = __ldg(reinterpret_cast<const uchar2 *>(yrow0 + (size_t)k * src.pitch0 + x));
+                                const uchar4 pe = yuv_to_rgba8(M.T.u8n[yy.x], fmaf(hue[i1], fy, hue[i0] * ify),
+                                                               fmaf(hve[i1], fy, hve[i0] * ify), src.full_range);
+                                const uchar4 po = yuv_to_rgba8(M.T.u8n[yy.y], fmaf(huo[i1], fy, huo[i0] * ify),
+                                                               fmaf(hvo[i1], fy, hvo[i0] * ify), src.full_range);
+                                float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
+                                sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
+                                sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                            }
+                        }
+                    } else {  // image border: resample.wgsl clamps the tap index
+                        for (int k = 0; k < nrows; k++) {
+                            const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r0 + k);
+                            const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r0 + k);
+                            float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
+                            sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
+                            sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                        }
+                    }
                 }
             }
             __syncwarp();
