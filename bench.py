@@ -76,6 +76,12 @@ def workload(name):
         scene = s.TilesComponent(children=rounded_tiles(n, 40.0, shadow=True), background_color=bg, margin=24.0)
         mode = s.RenderingMode.GpuOptimized
         desc = "32x(3840x2160 NV12)->7680x4320 NV12, Tiles 6x6 grid, Lanczos3 + box-shadow + radius"
+    elif name == "cfg4":  # 64 outputs x 1080p (4 of 8 pooled inputs each), 8 per GPU, shared inputs broadcast over NVLink
+        W, H, n, iw, ih = 1920, 1080, 8, 1920, 1080
+        scene = None   # per-rank scenes are built in main(): output k uses inputs (k + j) % 8, j < 4
+        mode = s.RenderingMode.GpuOptimized
+        desc = ("8 outputs/GPU of 4x(1920x1080 NV12)->1920x1080 NV12 Tiles 2x2 Lanczos3 2:1, inputs from a pool of 8 "
+                "replicated to every GPU by ncclBroadcast each tick")
     elif name == "passthrough":  # single_video_pass_through of the reference's benchmark suite
         W, H, n, iw, ih = 3840, 2160, 1, 3840, 2160
         scene = s.InputStreamComponent(input_id="input_1")
@@ -83,8 +89,12 @@ def workload(name):
         desc = "1x(3840x2160 NV12)->3840x2160 NV12 pass-through root"
     else:
         raise SystemExit(f"unknown workload {name}")
-    alg = n * (iw * ih * 3 // 2) + W * H * 3 // 2   # every needed input byte once + every output byte once
-    return dict(name=name, scene=scene, W=W, H=H, n=n, iw=iw, ih=ih, mode=mode, desc=desc, alg_bytes=alg)
+    n_out = 8 if name == "cfg4" else 1
+    # every needed input byte once (shared inputs count once per GPU per tick) + every output byte once
+    alg = n * (iw * ih * 3 // 2) + n_out * (W * H * 3 // 2)
+    tiles = 4 if name == "cfg4" else n   # texture layers per output frame (the CPU baseline times one of them)
+    return dict(name=name, scene=scene, W=W, H=H, n=n, iw=iw, ih=ih, mode=mode, desc=desc, alg_bytes=alg, n_out=n_out,
+                tiles=tiles)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -147,7 +157,7 @@ def cpu_sample(wl, repeats=1):
     import smelter_b200 as s
     from oracle import oracle as orc
     from tests import harness
-    n, iw, ih = wl["n"], wl["iw"], wl["ih"]
+    n, iw, ih = wl["tiles"], wl["iw"], wl["ih"]
     cols = int(np.ceil(np.sqrt(n)))
     tw, th = wl["W"] // cols, (wl["W"] // cols) * 9 // 16
     if wl["name"] == "passthrough":
@@ -189,7 +199,7 @@ def run_reference(args, wl):
         dt, desc, cores = cpu_sample(wl)
         if i >= args.warmup:
             samples.append(dt)
-    per_frame = float(np.mean(samples)) * wl["n"]
+    per_frame = float(np.mean(samples)) * wl["tiles"]
     fps = 1.0 / per_frame
     line = {"impl": "reference", "metric": "composited output frames/sec", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_frame * 1e3,
@@ -245,14 +255,30 @@ def main():
     ids = [f"input_{i}".encode() for i in range(1, n + 1)]
     for b in ids:
         r.register_input(b.decode())
-    r.update_scene("output_1", s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture, wl["scene"])
+    n_out = wl["n_out"]
+    out_ids = [f"output_{k + 1}".encode() for k in range(n_out)]
+    if wl["name"] == "cfg4":
+        for k in range(n_out):
+            g = rank * n_out + k   # global output index
+            kids = [s.InputStreamComponent(input_id=f"input_{(g + j) % n + 1}") for j in range(4)]
+            r.update_scene(out_ids[k].decode(), s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture,
+                           s.TilesComponent(children=kids, background_color=s.RGBAColor(*BG)))
+    else:
+        r.update_scene("output_1", s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture, wl["scene"])
+    # shared-input replication (only cfg4 has inputs referenced from several GPUs)
+    roots = None
+    if wl["name"] == "cfg4" and world > 1:
+        uid = [r.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        r.comm_init(uid[0], rank, world)
+        roots = [i % world for i in range(n)]   # input i is ingested on GPU i % N
 
     # ---- device-resident synthetic inputs: `variants` distinct frames per input, cycled -------------
     nvar = max(1, args.variants)
     dev_frames = [[synth_planes_torch(torch, dev, iw, ih, 0x5EED0000 + 1000 * v + i + 97 * rank) for i in range(n)]
                   for v in range(nvar)]
-    out_y = torch.empty((H, W), dtype=torch.uint8, device=dev)
-    out_uv = torch.empty((H // 2, W // 2, 2), dtype=torch.uint8, device=dev)
+    out_y = [torch.empty((H, W), dtype=torch.uint8, device=dev) for _ in range(n_out)]
+    out_uv = [torch.empty((H // 2, W // 2, 2), dtype=torch.uint8, device=dev) for _ in range(n_out)]
 
     def in_array(planes_for_variant, mem_kind, ptr):
         arr = (F.InputFrame * n)()
@@ -266,10 +292,11 @@ def main():
         return arr
 
     dev_in = [in_array(dev_frames[v], F.MEM_DEVICE, lambda t: t.data_ptr()) for v in range(nvar)]
-    dev_out = (F.OutputFrame * 1)()
-    dev_out[0].output_id = b"output_1"
-    dev_out[0].mem_kind = F.MEM_DEVICE
-    dev_out[0].planes[0], dev_out[0].planes[1] = out_y.data_ptr(), out_uv.data_ptr()
+    dev_out = (F.OutputFrame * n_out)()
+    for k in range(n_out):
+        dev_out[k].output_id = out_ids[k]
+        dev_out[k].mem_kind = F.MEM_DEVICE
+        dev_out[k].planes[0], dev_out[k].planes[1] = out_y[k].data_ptr(), out_uv[k].data_ptr()
 
     stream = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
     frame_ns = 33_333_333
@@ -277,7 +304,9 @@ def main():
     def step_dev(k):
         for a in dev_in[k % nvar]:
             a.pts_ns = k * frame_ns
-        r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, 1, wait=False)
+        if roots is not None:   # the tick's exchange step: one NCCL group on the render stream
+            r.comm_broadcast_inputs(dev_in[k % nvar], n, roots)
+        r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, n_out, wait=False)
 
     # ---- value: device-resident, device-timed ---------------------------------------------------------
     for k in range(args.warmup):
@@ -305,7 +334,7 @@ def main():
         ms = float(t.item())
     clk = clocks.stop()
     ms_per_step = ms / args.steps
-    value = world * args.steps / (ms * 1e-3)
+    value = world * n_out * args.steps / (ms * 1e-3)
 
     # ---- roofline: per-kernel device time from the library's own events -----------------------------
     r.set_profiling(True)
@@ -351,23 +380,25 @@ def main():
         host_frames = [[(dev_frames[v][i][0].cpu().pin_memory(), dev_frames[v][i][1].cpu().pin_memory())
                         for i in range(n)] for v in range(hv)]
         host_in = [in_array(host_frames[v], F.MEM_HOST, lambda t: t.data_ptr()) for v in range(hv)]
-        hy = torch.empty((H, W), dtype=torch.uint8).pin_memory()
-        huv = torch.empty((H // 2, W // 2, 2), dtype=torch.uint8).pin_memory()
-        host_out = (F.OutputFrame * 1)()
-        host_out[0].output_id = b"output_1"
-        host_out[0].mem_kind = F.MEM_HOST
-        host_out[0].planes[0], host_out[0].planes[1] = hy.data_ptr(), huv.data_ptr()
+        hys = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
+        huvs = [torch.empty((H // 2, W // 2, 2), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
+        hy = hys[0]
+        host_out = (F.OutputFrame * n_out)()
+        for k in range(n_out):
+            host_out[k].output_id = out_ids[k]
+            host_out[k].mem_kind = F.MEM_HOST
+            host_out[k].planes[0], host_out[k].planes[1] = hys[k].data_ptr(), huvs[k].data_ptr()
         ke = max(5, min(args.steps, 30))
         st0 = r.stats()
         for k in range(3):
-            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, 1, wait=True)
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, n_out, wait=True)
         barrier()
         st0 = r.stats()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ee0.record(stream)
         for k in range(ke):
-            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, 1, wait=True)
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out, n_out, wait=True)
             _ = int(hy[0, 0])  # the step's result is read on the host
         ee1.record(stream)
         torch.cuda.synchronize()
@@ -379,7 +410,7 @@ def main():
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        e2e = {"value": world * ke / e2e_s, "unit": "frames/s", "steps": ke,
+        e2e = {"value": world * n_out * ke / e2e_s, "unit": "frames/s", "steps": ke,
                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // ke,
                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // ke}
 
@@ -387,19 +418,22 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         dt, desc, cores = cpu_sample(wl, repeats=2)
-        cpu = {"value": 1.0 / (dt * wl["n"]), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+        cpu = {"value": 1.0 / (dt * wl["tiles"]), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:
         line = {"metric": "4K composited frames/sec (16-input grid) per GPU" if wl["name"] == "cfg3" else "composited output frames/sec",
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 math on u8 planes (f16 resampler scratch)", "data": "synthetic",
-                "config": {"workload": wl["name"], "detail": wl["desc"], "outputs_per_gpu": 1,
+                "config": {"workload": wl["name"], "detail": wl["desc"], "outputs_per_gpu": n_out,
+                           "nvlink_broadcast_bytes_per_tick": (n * iw * ih * 3 // 2) * (world - 1) if roots is not None else 0,
                            "l2_policy": f"inputs larger than L2: {nvar} distinct frame sets of "
                                         f"{wl['alg_bytes'] / 1e6:.0f} MB cycled (> 126 MB L2)",
                            "algorithmic_bytes_per_frame": wl["alg_bytes"], "wall_s_timed_region": t_wall},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
+    if roots is not None:
+        r.comm_destroy()
     if dist is not None:
         dist.destroy_process_group()
 

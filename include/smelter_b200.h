@@ -248,6 +248,18 @@ smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pt
  * lets the host logic be tested on a box without a GPU. */
 smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs);
 
+/* ---- multi-GPU (new: the reference is single-device, render_loop.rs:232-236 loops outputs serially) -------
+ * Outputs shard across GPUs (one handle per GPU, no data-path collective).  The single exchange step is
+ * replicating an input frame to every GPU that hosts an output referencing it: ncclBroadcast over NVLink,
+ * all shared inputs of a tick in one ncclGroup, enqueued on the handle's stream (the next smr_render on that
+ * handle is ordered after it).  The unique id travels over whatever transport the host already has. */
+smr_status smr_comm_get_unique_id(uint8_t id[128]);
+smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* frames[i]: device-resident planes, identical geometry on every rank; root_ranks[i] holds the data */
+smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n,
+                                     const int32_t *root_ranks);
+smr_status smr_comm_destroy(smr_renderer *r);
+
 smr_status smr_get_stats(smr_renderer *r, smr_stats *out);
 smr_status smr_set_profiling(smr_renderer *r, int32_t enabled);   /* also resets the accumulated times */
 smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out);

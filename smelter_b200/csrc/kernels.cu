@@ -485,6 +485,7 @@ struct FusedIntSmem {
 };
 
 __device__ __forceinline__ int fi_pos(int i) { return i + ((i >> 4) << 2); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // K1/K2 of the chroma-aligned pixel pair (x, x+1), x even, 2 <= x, x + 3 <= W - 1 (no clamping needed)
 template <bool NV12>
@@ -550,6 +551,20 @@ __global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused_int(const Fu
         const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
         const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
         const int start = max(produced_hi + 1, need_lo) & ~1;  // even: chunks share chroma rows (re-making a row is harmless)
+        {   // pull the NEXT group's source rows towards L2 while this group computes (they come from DRAM otherwise)
+            const int tid = warp * 32 + lane;
+            const int nr = need_hi + 1 + (tid >> 2), part = tid & 3;  // 64 luma rows x (2 luma + 2 chroma 128-B lines)
+            if (nr < H) {
+                const int xb = min(max(xa_e, 0), W - 1);
+                if (part < 2) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + xb + part * 128);
+                else if ((nr & 1) == 0) {
+                    const int cyn = min(nr >> 1, chei - 1);
+                    if (NV12) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + xb + (part - 2) * 128);
+                    else if (part == 2) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + (xb >> 1));
+                    else prefetch_l2(src.p2 + (size_t)cyn * src.pitch2 + (xb >> 1));
+                }
+            }
+        }
         // ---- phase A: chunks of FI_ROWS source rows per warp ---------------------------------------
         for (int r0 = start + warp * FI_ROWS; r0 <= need_hi; r0 += FS_WARPS * FI_ROWS) {
             // A1: convert (K1/K2 -> u8 -> sRGB decode) the strip's pixels of rows r0..r0+3 (r0 is even).

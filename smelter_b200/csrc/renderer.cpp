@@ -11,6 +11,7 @@
 // [first passes] -> [last passes] -> one composite(+YUV writeback) launch per output.  All transient
 // textures live in a frame arena in HBM that is recycled every tick.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -131,6 +132,39 @@ struct PinnedBuf {
     }
 };
 
+struct NcclId { char b[128]; };
+typedef int (*nccl_init_fn)(void **, int, NcclId, int);
+static struct {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    nccl_init_fn CommInitRank = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+static bool nccl_load(std::string &err) {
+    if (g_nccl.lib) return true;
+    // RTLD_NOLOAD first: reuse the NCCL already in the process (e.g. the one torch.distributed loaded)
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(NcclId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclBroadcast");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Broadcast || !g_nccl.GroupStart ||
+        !g_nccl.GroupEnd) { err = "libnccl lacks required symbols"; return false; }
+    g_nccl.lib = h;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 class Renderer {
   public:
@@ -247,7 +281,13 @@ class Renderer {
     size_t prof_next_event_ = 0;
     std::vector<std::pair<cudaEvent_t, int>> prof_marks_;
     smr_kernel_times prof_ = {};
+    // NCCL communicator for shared-input replication; libnccl is dlopen'ed on first use
+    void *nccl_comm_ = nullptr;
+    int comm_rank_ = 0, comm_size_ = 1;
   public:
+    smr_status comm_init(const uint8_t *id, int rank, int nranks);
+    smr_status comm_broadcast(const smr_input_frame *frames, uint32_t n, const int32_t *roots);
+    smr_status comm_destroy();
     smr_status set_profiling(int enabled);
     void kernel_times(smr_kernel_times *out) { std::lock_guard<std::mutex> g(mu_); *out = prof_; }
 };
@@ -256,6 +296,7 @@ Renderer::~Renderer() {
     if (stream_) {
         cudaSetDevice(opts_.cuda_device);
         cudaStreamSynchronize(stream_);
+        if (nccl_comm_) { g_nccl.CommDestroy(nccl_comm_); nccl_comm_ = nullptr; }
         for (auto &kv : weights_) {
             cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
         }
@@ -1097,6 +1138,62 @@ void Renderer::prof_mark(int kernel_class) {
     prof_marks_.push_back({e, kernel_class});
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: outputs shard across GPUs with no data-path collective; the only exchange is replicating an
+// input frame to every GPU that hosts an output referencing it (ncclBroadcast over NVLink, grouped per tick,
+// enqueued on the render stream so the following smr_render is ordered after it).
+// ------------------------------------------------------------------------------------------------
+smr_status Renderer::comm_init(const uint8_t *id, int rank, int nranks) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (host_only_) { set_error("host-only handle has no device"); return SMR_ERR_CUDA; }
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return SMR_ERR_INVALID_ARGUMENT;
+    std::string err;
+    if (!nccl_load(err)) { set_error(err); return SMR_ERR_UNSUPPORTED; }
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    NcclId nid;
+    memcpy(nid.b, id, 128);
+    int rc = g_nccl.CommInitRank(&nccl_comm_, nranks, nid, rank);
+    if (rc != 0) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
+    comm_rank_ = rank; comm_size_ = nranks;
+    return SMR_OK;
+}
+
+smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, const int32_t *roots) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!nccl_comm_) { set_error("smr_comm_init was not called"); return SMR_ERR_INVALID_ARGUMENT; }
+    if (n && (!frames || !roots)) return SMR_ERR_INVALID_ARGUMENT;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    int rc = g_nccl.GroupStart();
+    for (uint32_t i = 0; i < n && rc == 0; i++) {
+        const smr_input_frame &f = frames[i];
+        if (f.mem_kind != SMR_MEM_DEVICE) { g_nccl.GroupEnd(); set_error("broadcast needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (roots[i] < 0 || roots[i] >= comm_size_) { g_nccl.GroupEnd(); return SMR_ERR_INVALID_ARGUMENT; }
+        for (int p = 0; p < 3 && rc == 0; p++) {
+            size_t row_bytes = 0, rows = 0;
+            if (!plane_layout(f.format, f.width, f.height, p, row_bytes, rows)) continue;
+            size_t pitch = f.pitch[p] ? f.pitch[p] : row_bytes;
+            size_t bytes = pitch * (rows - 1) + row_bytes;
+            rc = g_nccl.Broadcast(f.planes[p], (void *)f.planes[p], bytes, /*ncclUint8*/ 1, roots[i], nccl_comm_, stream_);
+        }
+    }
+    int rc2 = g_nccl.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) { set_error(std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
+    in_flight_ = true;
+    return SMR_OK;
+}
+
+smr_status Renderer::comm_destroy() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (nccl_comm_) {
+        cudaSetDevice(opts_.cuda_device);
+        cudaStreamSynchronize(stream_);
+        g_nccl.CommDestroy(nccl_comm_);
+        nccl_comm_ = nullptr;
+    }
+    return SMR_OK;
+}
+
 smr_status Renderer::set_profiling(int enabled) {
     std::lock_guard<std::mutex> g(mu_);
     profiling_ = enabled != 0;
@@ -1208,6 +1305,18 @@ smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, 
 smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap,
                              uint32_t *n, uint32_t *rw, uint32_t *rh) { SMR_GUARD(r->impl.debug_layouts(output_id, pts, out, cap, n, rw, rh)) }
 smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in) { SMR_GUARD(r->impl.debug_set_inputs(pts, in, n_in)) }
+smr_status smr_comm_get_unique_id(uint8_t id[128]) {
+    if (!id) return SMR_ERR_INVALID_ARGUMENT;
+    std::string err;
+    if (!smr::nccl_load(err)) { g_create_error = err; return SMR_ERR_UNSUPPORTED; }
+    smr::NcclId nid;
+    if (smr::g_nccl.GetUniqueId(&nid) != 0) { g_create_error = "ncclGetUniqueId failed"; return SMR_ERR_CUDA; }
+    memcpy(id, nid.b, 128);
+    return SMR_OK;
+}
+smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, int32_t nranks) { SMR_GUARD(r->impl.comm_init(id, rank, nranks)) }
+smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks) { SMR_GUARD(r->impl.comm_broadcast(frames, n, root_ranks)) }
+smr_status smr_comm_destroy(smr_renderer *r) { SMR_GUARD(r->impl.comm_destroy()) }
 smr_status smr_set_profiling(smr_renderer *r, int32_t enabled) { SMR_GUARD(r->impl.set_profiling(enabled)) }
 smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out) {
     if (!r || !out) return SMR_ERR_INVALID_ARGUMENT;

@@ -534,6 +534,26 @@ class Renderer:
         self._check(self._lib.smr_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in F.Stats._fields_}
 
+    # -- multi-GPU: shared-input replication over NCCL (include/smelter_b200.h smr_comm_*) ------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        st = F.lib().smr_comm_get_unique_id(C.byref(buf))
+        if st != F.SMR_OK:
+            raise RendererError(st, (F.lib().smr_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128)(*unique_id)
+        self._check(self._lib.smr_comm_init(self._h, C.byref(buf), rank, nranks))
+
+    def comm_broadcast_inputs(self, in_arr, n, roots):
+        arr = (C.c_int32 * max(1, n))(*roots)
+        self._check(self._lib.smr_comm_broadcast_inputs(self._h, in_arr, n, arr))
+
+    def comm_destroy(self):
+        self._check(self._lib.smr_comm_destroy(self._h))
+
     def set_profiling(self, enabled: bool):
         self._check(self._lib.smr_set_profiling(self._h, int(enabled)))
 
