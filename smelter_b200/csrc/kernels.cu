@@ -140,6 +140,19 @@ __device__ __forceinline__ uchar4 yuv_to_rgba8(float y, float u, float v, int fu
     return make_uchar4((unsigned char)unorm8(r), (unsigned char)unorm8(g), (unsigned char)unorm8(b), 255);
 }
 
+// same arithmetic, results as integers (no byte packing) for callers that index a table next
+__device__ __forceinline__ void yuv_to_rgb8i(float y, float u, float v, int full_range, int &r8, int &g8, int &b8) {
+    if (!full_range) {
+        y = clamp01((y - K16) * RCP_Y);
+        u = clamp01((u - K16) * RCP_C);
+        v = clamp01((v - K16) * RCP_C);
+    }
+    float um = u - 0.5f, vm = v - 0.5f;
+    r8 = unorm8(fmaf(1.5748f, vm, y));
+    g8 = unorm8(fmaf(-0.4681f, vm, fmaf(-0.1873f, um, y)));
+    b8 = unorm8(fmaf(1.8556f, um, y));
+}
+
 __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int x, int y) {
     switch (s.kind) {
         case TEX_RGBA8:
@@ -465,228 +478,198 @@ __global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused(const FusedJ
 // The same fused resample specialised for an INTEGER horizontal ratio S (2:1, 3:1, 4:1 with a zero crop
 // offset -- every grid / mosaic of the BASELINE configs).  Then first(o) = S*o + const and every output column
 // has the same TAPS = 6S+1 weights (exact small-integer arithmetic in resample.wgsl:45-50), which allows:
-//   * weights in registers, no per-tap weight fetch;
-//   * register blocking: a lane produces 4 adjacent output columns from one (3S+TAPS)-long window, so a
-//     shared-memory value feeds up to 4 FMAs (the plain kernel is shared-memory-bandwidth bound at 1 FMA/load);
-//   * a warp converts and filters 4 source rows per step (4 rows x 8 column groups x 4 columns);
-//   * K1/K2 on chroma-aligned pixel PAIRS (the .25/.75 chroma taps of the two pixels share 3 chroma texels);
-//   * conflict-free shared memory: value i of a row sits at i + 4*(i/16) and row stride = 1 (mod 32).
+//   * weights in CONSTANT memory: the FFMA reads them as c[bank][offset] operands, no register, no load;
+//   * register blocking: a lane produces 2 adjacent output columns from one (S+TAPS)-long window;
+//   * 64-column strips (less horizontal halo), one source row per warp step, so only ~4 KB of shared memory
+//     per warp and 3 blocks (24 warps) per SM;
+//   * K1/K2 on chroma-aligned pixel PAIRS (the .25/.75 taps of the two pixels share 3 chroma texels per row),
+//     raw bytes of the next pair prefetched into registers while the current one is converted;
+//   * conflict-free shared memory: value i of a row sits at i + i/(2S)  (lane stride 2S+1, odd);
+//   * the f16 intermediate is kept AS f16 (half2 per lane) in the ring.
 // Accumulation order per output is tap 0..TAPS-1 exactly as in the shader, so results are bit-identical.
 // ------------------------------------------------------------------------------------------------
-#define FI_ROWS 4                        // source rows per warp step
-#define FI_ROWSTRIDE 193                 // floats; == 1 (mod 32); >= padded span (150 + 9*4)
-#define FI_MAXSPAN 176                   // (FS_TW-1)*4 + 25 + alignment, before padding
+#define W64_TW 64
+#define W64_WARPS 8
+#define W64_RING 64
 
-template <int S>
-struct FusedIntSmem {
-    Tables T;
-    float ring[FS_RING][3][FS_TW];
-    float srow[FS_WARPS][3][FI_ROWS][FI_ROWSTRIDE];
-};
+__constant__ float c_wint[5][32];   // [S][tap]
+__constant__ float c_winv[5];       // 1 / weight_sum
 
-__device__ __forceinline__ int fi_pos(int i) { return i + ((i >> 4) << 2); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// K1/K2 of the chroma-aligned pixel pair (x, x+1), x even, 2 <= x, x + 3 <= W - 1 (no clamping needed)
-template <bool NV12>
-__device__ __forceinline__ void yuv_pair(const Tables &T, const Tex &s, const uint8_t *yrow, const uint8_t *c0a,
-                                         const uint8_t *c1a, const uint8_t *c0b, const uint8_t *c1b, int x, float fy,
-                                         uchar4 &pe, uchar4 &po) {
-    const int cx = x >> 1;
-    const uchar2 yy = __ldg(reinterpret_cast<const uchar2 *>(yrow + x));
-    float ua0, ub0, ud0, ua1, ub1, ud1, va0, vb0, vd0, va1, vb1, vd1;
-    if (NV12) {
-        const uchar2 *r0 = reinterpret_cast<const uchar2 *>(c0a) + cx, *r1 = reinterpret_cast<const uchar2 *>(c1a) + cx;
-        uchar2 a0 = __ldg(r0 - 1), b0 = __ldg(r0), d0 = __ldg(r0 + 1), a1 = __ldg(r1 - 1), b1 = __ldg(r1), d1 = __ldg(r1 + 1);
-        ua0 = T.u8n[a0.x]; ub0 = T.u8n[b0.x]; ud0 = T.u8n[d0.x]; ua1 = T.u8n[a1.x]; ub1 = T.u8n[b1.x]; ud1 = T.u8n[d1.x];
-        va0 = T.u8n[a0.y]; vb0 = T.u8n[b0.y]; vd0 = T.u8n[d0.y]; va1 = T.u8n[a1.y]; vb1 = T.u8n[b1.y]; vd1 = T.u8n[d1.y];
-    } else {
-        ua0 = T.u8n[__ldg(c0a + cx - 1)]; ub0 = T.u8n[__ldg(c0a + cx)]; ud0 = T.u8n[__ldg(c0a + cx + 1)];
-        ua1 = T.u8n[__ldg(c1a + cx - 1)]; ub1 = T.u8n[__ldg(c1a + cx)]; ud1 = T.u8n[__ldg(c1a + cx + 1)];
-        va0 = T.u8n[__ldg(c0b + cx - 1)]; vb0 = T.u8n[__ldg(c0b + cx)]; vd0 = T.u8n[__ldg(c0b + cx + 1)];
-        va1 = T.u8n[__ldg(c1b + cx - 1)]; vb1 = T.u8n[__ldg(c1b + cx)]; vd1 = T.u8n[__ldg(c1b + cx + 1)];
-    }
-    const float ify = 1.0f - fy;
-    // even pixel: taps (cx-1, cx), fx = .75 ; odd pixel: taps (cx, cx+1), fx = .25   (bilerp of NC-6)
-    float ue = fmaf(fmaf(ub1, 0.75f, ua1 * 0.25f), fy, fmaf(ub0, 0.75f, ua0 * 0.25f) * ify);
-    float uo = fmaf(fmaf(ud1, 0.25f, ub1 * 0.75f), fy, fmaf(ud0, 0.25f, ub0 * 0.75f) * ify);
-    float ve = fmaf(fmaf(vb1, 0.75f, va1 * 0.25f), fy, fmaf(vb0, 0.75f, va0 * 0.25f) * ify);
-    float vo = fmaf(fmaf(vd1, 0.25f, vb1 * 0.75f), fy, fmaf(vd0, 0.25f, vb0 * 0.75f) * ify);
-    pe = yuv_to_rgba8(T.u8n[yy.x], ue, ve, s.full_range);
-    po = yuv_to_rgba8(T.u8n[yy.y], uo, vo, s.full_range);
+void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s) {
+    cudaMemcpyToSymbolAsync(c_wint, weights_dev, sizeof(float) * taps, sizeof(float) * 32 * S, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+    cudaMemcpyToSymbolAsync(c_winv, inv_dev, sizeof(float), sizeof(float) * S, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
 }
 
+template <int S>
+struct W64 {
+    static constexpr int TAPS = 6 * S + 1;
+    static constexpr int SPAN = (W64_TW - 1) * S + TAPS + 1;          // + chroma alignment
+    static constexpr int ROWLEN = ((SPAN + SPAN / (2 * S) + 2) + 7) & ~7;
+    struct Smem {
+        Tables T;
+        __half2 ring[W64_RING][3][W64_TW / 2];
+        float srow[W64_WARPS][3][ROWLEN];
+    };
+    static __device__ __forceinline__ int pos(int i) { return i + i / (2 * S); }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int S, bool NV12>
-__global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused_int(const FusedJob *jobs) {
-    constexpr int TAPS = 6 * S + 1;
-    constexpr int WIN = 3 * S + TAPS;  // window feeding 4 adjacent output columns
+__global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const FusedJob *jobs) {
+    using K = W64<S>;
+    constexpr int TAPS = K::TAPS;
+    constexpr int WIN = S + TAPS;  // window feeding 2 adjacent output columns
     extern __shared__ __align__(16) unsigned char fs_raw[];
-    FusedIntSmem<S> &M = *reinterpret_cast<FusedIntSmem<S> *>(fs_raw);
+    typename K::Smem &M = *reinterpret_cast<typename K::Smem *>(fs_raw);
     const FusedJob &J = jobs[blockIdx.z];
     if (J.variant != S || (J.src.kind == TEX_NV12) != NV12) return;
-    load_tables(M.T);
-    const int lane = threadIdx.x, warp = threadIdx.y;
-    const int ox0 = blockIdx.x * FS_TW;
+    const int ox0 = blockIdx.x * W64_TW;
     if (ox0 >= J.dst_w) return;
     const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
     if (oy_begin >= J.dst_h) return;
+    load_tables(M.T);
+    const int lane = threadIdx.x, warp = threadIdx.y;
     const Tex &src = J.src;
-    const int W = src.width, H = src.height, cwid = W >> 1, chei = H >> 1;
+    const int W = src.width, H = src.height, chei = H >> 1;
     const int tv = J.taps_v;
-
-    float w[TAPS];
-#pragma unroll
-    for (int t = 0; t < TAPS; t++) w[t] = __ldg(J.w_h + t);  // identical for every column
-    const float inv_h = __ldg(J.inv_h);
+    const float inv_h = c_winv[S];
     const int xa = __ldg(J.first_h + ox0);      // first(o) = S*o + const
-    const int xa_e = xa & ~1;                   // chroma-aligned start (xa may be negative: & ~1 floors)
+    const int xa_e = xa & ~1;                   // chroma-aligned start
     const int d0 = xa - xa_e;
-    const int span = (FS_TW - 1) * S + TAPS + d0;
-    const int npairs = (span + 1) >> 1;
-    const int rr = lane >> 3, cg = lane & 7;
+    const int npairs = ((W64_TW - 1) * S + TAPS + d0 + 1) >> 1;
+    const int full_range = src.full_range;
 
     int produced_hi = -0x40000000;
-    for (int o0 = oy_begin; o0 < oy_end; o0 += FS_WARPS) {
-        const int o_l = min(o0 + FS_WARPS - 1, oy_end - 1);
+    for (int o0 = oy_begin; o0 < oy_end; o0 += W64_WARPS) {
+        const int o_l = min(o0 + W64_WARPS - 1, oy_end - 1);
         const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
         const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
-        const int start = max(produced_hi + 1, need_lo) & ~1;  // even: chunks share chroma rows (re-making a row is harmless)
-        {   // pull the NEXT group's source rows towards L2 while this group computes (they come from DRAM otherwise)
+        const int start = max(produced_hi + 1, need_lo);
+        {   // pull the NEXT group's source rows towards L2 while this group computes
             const int tid = warp * 32 + lane;
-            const int nr = need_hi + 1 + (tid >> 2), part = tid & 3;  // 64 luma rows x (2 luma + 2 chroma 128-B lines)
-            if (nr < H) {
+            const int nr = need_hi + 1 + (tid >> 3), part = tid & 7;  // 32 luma rows x (3 luma + 3 chroma lines)
+            if (nr < H && part < 6) {
                 const int xb = min(max(xa_e, 0), W - 1);
-                if (part < 2) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + xb + part * 128);
+                if (part < 3) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(xb + part * 128, W - 1));
                 else if ((nr & 1) == 0) {
                     const int cyn = min(nr >> 1, chei - 1);
-                    if (NV12) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + xb + (part - 2) * 128);
-                    else if (part == 2) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + (xb >> 1));
-                    else prefetch_l2(src.p2 + (size_t)cyn * src.pitch2 + (xb >> 1));
+                    if (NV12) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + min(xb + (part - 3) * 128, W - 2));
+                    else if (part < 5) prefetch_l2((part == 3 ? src.p1 : src.p2) + (size_t)cyn * (part == 3 ? src.pitch1 : src.pitch2) + (xb >> 1));
                 }
             }
         }
-        // ---- phase A: chunks of FI_ROWS source rows per warp ---------------------------------------
-        for (int r0 = start + warp * FI_ROWS; r0 <= need_hi; r0 += FS_WARPS * FI_ROWS) {
-            // A1: convert (K1/K2 -> u8 -> sRGB decode) the strip's pixels of rows r0..r0+3 (r0 is even).
-            // A lane owns a chroma-aligned pixel-pair COLUMN for all 4 rows: the 4 chroma rows j-1..j+2 they
-            // touch are loaded and horizontally interpolated once (bilerp of NC-6 is h-then-v, so the
-            // horizontal terms are shared bit-exactly between the rows that use the same chroma row).
+        // ---- phase A: one source row per warp step -----------------------------------------------------
+        for (int r = start + warp; r <= need_hi; r += W64_WARPS) {
+            float *sr = M.srow[warp][0], *sg = M.srow[warp][1], *sb = M.srow[warp][2];
+            // A1: K1/K2 -> u8 -> sRGB decode of the strip's pixels of row r
             {
-                const int nrows = min(FI_ROWS, need_hi - r0 + 1);
-                const int j = r0 >> 1;
-                const uint8_t *ca[4], *cb[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int cy = min(max(j - 1 + i, 0), chei - 1);
-                    ca[i] = src.p1 + (size_t)cy * src.pitch1;
-                    cb[i] = NV12 ? nullptr : src.p2 + (size_t)cy * src.pitch2;
-                }
-                const uint8_t *yrow0 = src.p0 + (size_t)r0 * src.pitch0;
-                for (int p = lane; p < npairs; p += 32) {
-                    const int x = xa_e + 2 * p;
-                    const int q = fi_pos(2 * p);
-                    if (x >= 2 && x + 3 <= W - 1) {
-                        const int cx = x >> 1;
-                        float hue[4], huo[4], hve[4], hvo[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            float ua, ub, ud, va, vb, vd;
-                            if (NV12) {
-                                const uchar2 *rp = reinterpret_cast<const uchar2 *>(ca[i]) + cx;
-                                const uchar2 a = __ldg(rp - 1), b2 = __ldg(rp), d = __ldg(rp + 1);
-                                ua = M.T.u8n[a.x]; ub = M.T.u8n[b2.x]; ud = M.T.u8n[d.x];
-                                va = M.T.u8n[a.y]; vb = M.T.u8n[b2.y]; vd = M.T.u8n[d.y];
-                            } else {
-                                ua = M.T.u8n[__ldg(ca[i] + cx - 1)]; ub = M.T.u8n[__ldg(ca[i] + cx)]; ud = M.T.u8n[__ldg(ca[i] + cx + 1)];
-                                va = M.T.u8n[__ldg(cb[i] + cx - 1)]; vb = M.T.u8n[__ldg(cb[i] + cx)]; vd = M.T.u8n[__ldg(cb[i] + cx + 1)];
-                            }
-                            hue[i] = fmaf(ub, 0.75f, ua * 0.25f); huo[i] = fmaf(ud, 0.25f, ub * 0.75f);
-                            hve[i] = fmaf(vb, 0.75f, va * 0.25f); hvo[i] = fmaf(vd, 0.25f, vb * 0.75f);
-                        }
-#pragma unroll
-                        for (int k = 0; k < FI_ROWS; k++) {
-                            if (k < nrows) {
-                                const int i0 = (k + 1) >> 1, i1 = i0 + 1;
-                                const float fy = (k & 1) ? 0.25f : 0.75f, ify = (k & 1) ? 0.75f : 0.25f;
-                                const uchar2 yy = __ldg(reinterpret_cast<const uchar2 *>(yrow0 + (size_t)k * src.pitch0 + x));
-                                const uchar4 pe = yuv_to_rgba8(M.T.u8n[yy.x], fmaf(hue[i1], fy, hue[i0] * ify),
-                                                               fmaf(hve[i1], fy, hve[i0] * ify), src.full_range);
-                                const uchar4 po = yuv_to_rgba8(M.T.u8n[yy.y], fmaf(huo[i1], fy, huo[i0] * ify),
-                                                               fmaf(hvo[i1], fy, hvo[i0] * ify), src.full_range);
-                                float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
-                                sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
-                                sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
-                            }
-                        }
-                    } else {  // image border: resample.wgsl clamps the tap index
-                        for (int k = 0; k < nrows; k++) {
-                            const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r0 + k);
-                            const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r0 + k);
-                            float *sr = M.srow[warp][0][k], *sg = M.srow[warp][1][k], *sb = M.srow[warp][2][k];
-                            sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
-                            sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
-                        }
+                const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
+                const int cy0 = (r & 1) ? (r >> 1) : max((r >> 1) - 1, 0), cy1 = (r & 1) ? min((r >> 1) + 1, chei - 1) : (r >> 1);
+                const float fy = (r & 1) ? 0.25f : 0.75f, ify = (r & 1) ? 0.75f : 0.25f;
+                const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
+                const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
+                const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
+                struct Raw { uchar2 y, a0, b0, d0, a1, b1, d1; };
+                auto interior = [&](int pp) { const int x = xa_e + 2 * pp; return x >= 2 && x + 3 <= W - 1; };
+                auto load_raw = [&](int pp, Raw &R) {
+                    const int x = xa_e + 2 * pp, cx = x >> 1;
+                    if (NV12) {
+                        const uchar2 *r0 = reinterpret_cast<const uchar2 *>(c0a) + cx, *r1 = reinterpret_cast<const uchar2 *>(c1a) + cx;
+                        R.a0 = __ldg(r0 - 1); R.b0 = __ldg(r0); R.d0 = __ldg(r0 + 1);
+                        R.a1 = __ldg(r1 - 1); R.b1 = __ldg(r1); R.d1 = __ldg(r1 + 1);
+                    } else {
+                        R.a0 = make_uchar2(__ldg(c0a + cx - 1), __ldg(c0b + cx - 1)); R.b0 = make_uchar2(__ldg(c0a + cx), __ldg(c0b + cx));
+                        R.d0 = make_uchar2(__ldg(c0a + cx + 1), __ldg(c0b + cx + 1));
+                        R.a1 = make_uchar2(__ldg(c1a + cx - 1), __ldg(c1b + cx - 1)); R.b1 = make_uchar2(__ldg(c1a + cx), __ldg(c1b + cx));
+                        R.d1 = make_uchar2(__ldg(c1a + cx + 1), __ldg(c1b + cx + 1));
                     }
+                    R.y = __ldg(reinterpret_cast<const uchar2 *>(yrow + x));
+                };
+                Raw cur;
+                if (lane < npairs && interior(lane)) load_raw(lane, cur);
+                for (int p = lane; p < npairs; p += 32) {
+                    const int q = K::pos(2 * p);
+                    Raw nxt;
+                    if (p + 32 < npairs && interior(p + 32)) load_raw(p + 32, nxt);
+                    if (interior(p)) {
+                        const float ua0 = M.T.u8n[cur.a0.x], ub0 = M.T.u8n[cur.b0.x], ud0 = M.T.u8n[cur.d0.x];
+                        const float ua1 = M.T.u8n[cur.a1.x], ub1 = M.T.u8n[cur.b1.x], ud1 = M.T.u8n[cur.d1.x];
+                        const float va0 = M.T.u8n[cur.a0.y], vb0 = M.T.u8n[cur.b0.y], vd0 = M.T.u8n[cur.d0.y];
+                        const float va1 = M.T.u8n[cur.a1.y], vb1 = M.T.u8n[cur.b1.y], vd1 = M.T.u8n[cur.d1.y];
+                        // even pixel: taps (cx-1, cx) fx=.75 ; odd pixel: taps (cx, cx+1) fx=.25   (bilerp of NC-6)
+                        const float ue = fmaf(fmaf(ub1, 0.75f, ua1 * 0.25f), fy, fmaf(ub0, 0.75f, ua0 * 0.25f) * ify);
+                        const float uo = fmaf(fmaf(ud1, 0.25f, ub1 * 0.75f), fy, fmaf(ud0, 0.25f, ub0 * 0.75f) * ify);
+                        const float ve = fmaf(fmaf(vb1, 0.75f, va1 * 0.25f), fy, fmaf(vb0, 0.75f, va0 * 0.25f) * ify);
+                        const float vo = fmaf(fmaf(vd1, 0.25f, vb1 * 0.75f), fy, fmaf(vd0, 0.25f, vb0 * 0.75f) * ify);
+                        int r8, g8, b8;
+                        yuv_to_rgb8i(M.T.u8n[cur.y.x], ue, ve, full_range, r8, g8, b8);
+                        sr[q] = M.T.dec[r8]; sg[q] = M.T.dec[g8]; sb[q] = M.T.dec[b8];
+                        yuv_to_rgb8i(M.T.u8n[cur.y.y], uo, vo, full_range, r8, g8, b8);
+                        sr[q + 1] = M.T.dec[r8]; sg[q + 1] = M.T.dec[g8]; sb[q + 1] = M.T.dec[b8];
+                    } else {  // image border: resample.wgsl clamps the tap index
+                        const int x = xa_e + 2 * p;
+                        const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
+                        const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
+                        sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
+                        sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                    }
+                    cur = nxt;
                 }
             }
             __syncwarp();
-            // A2: horizontal Lanczos, lane = (row rr, column group cg) -> 4 adjacent output columns
-            const int r = r0 + rr;
-            if (r <= need_hi) {
-                const int i0 = 4 * S * cg + d0;   // window start of column ox0 + 4*cg, relative to xa_e
-                float *ringrow = &M.ring[r & (FS_RING - 1)][0][0];
+            // A2: horizontal Lanczos, each lane 2 adjacent output columns, weights from the constant bank
+            {
+                const int i0 = 2 * S * lane + d0;
+                __half2 *ringrow = &M.ring[r & (W64_RING - 1)][0][0];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-                    const float *sp = M.srow[warp][ch][rr];
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    const float *sp = M.srow[warp][ch];
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int j = 0; j < WIN; j++) {
-                        const float v = sp[fi_pos(i0 + j)];
-                        if (j < TAPS) a0 = fmaf(v, w[j], a0);
-                        if (j >= S && j - S < TAPS) a1 = fmaf(v, w[j - S], a1);
-                        if (j >= 2 * S && j - 2 * S < TAPS) a2 = fmaf(v, w[j - 2 * S], a2);
-                        if (j >= 3 * S) a3 = fmaf(v, w[j - 3 * S], a3);
+                        const float v = sp[K::pos(i0 + j)];
+                        if (j < TAPS) a0 = fmaf(v, c_wint[S][j], a0);
+                        if (j >= S) a1 = fmaf(v, c_wint[S][j - S], a1);
                     }
-                    float *dst = ringrow + ch * FS_TW + 4 * cg;
-                    dst[0] = __half2float(__float2half_rn(a0 * inv_h));  // NC-5
-                    dst[1] = __half2float(__float2half_rn(a1 * inv_h));
-                    dst[2] = __half2float(__float2half_rn(a2 * inv_h));
-                    dst[3] = __half2float(__float2half_rn(a3 * inv_h));
+                    ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv_h, a1 * inv_h);  // NC-5
                 }
             }
             __syncwarp();
         }
         produced_hi = max(produced_hi, need_hi);
         __syncthreads();
-        // ---- phase B: vertical pass, one output row per warp (any ratio) -------------------------------
+        // ---- phase B: vertical pass, one output row per warp, 2 columns per lane (any ratio) ----------------
         const int oy = o0 + warp;
         if (oy < oy_end) {
             const int fv = __ldg(J.first_v + oy);
             const float *wv = J.w_v + (size_t)oy * tv;
-            float ar = 0.f, ag = 0.f, ab = 0.f;
-            if (fv >= 0 && fv + tv - 1 <= H - 1) {
-                for (int t = 0; t < tv; t++) {
-                    const float wt = __ldg(wv + t);
-                    const float *p = &M.ring[(fv + t) & (FS_RING - 1)][0][0];
-                    ar = fmaf(p[lane], wt, ar);
-                    ag = fmaf(p[FS_TW + lane], wt, ag);
-                    ab = fmaf(p[2 * FS_TW + lane], wt, ab);
-                }
-            } else {
-                for (int t = 0; t < tv; t++) {
-                    const float wt = __ldg(wv + t);
-                    const int row = min(max(fv + t, 0), H - 1);
-                    const float *p = &M.ring[row & (FS_RING - 1)][0][0];
-                    ar = fmaf(p[lane], wt, ar);
-                    ag = fmaf(p[FS_TW + lane], wt, ag);
-                    ab = fmaf(p[2 * FS_TW + lane], wt, ab);
-                }
+            float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+            const bool inside = fv >= 0 && fv + tv - 1 <= H - 1;
+            for (int t = 0; t < tv; t++) {
+                const float wt = __ldg(wv + t);
+                const int row = inside ? fv + t : min(max(fv + t, 0), H - 1);
+                const __half2 *p = &M.ring[row & (W64_RING - 1)][0][0];
+                const float2 vr = __half22float2(p[lane]), vg = __half22float2(p[W64_TW / 2 + lane]), vb = __half22float2(p[W64_TW + lane]);
+                r0 = fmaf(vr.x, wt, r0); r1 = fmaf(vr.y, wt, r1);
+                g0 = fmaf(vg.x, wt, g0); g1 = fmaf(vg.y, wt, g1);
+                b0 = fmaf(vb.x, wt, b0); b1 = fmaf(vb.y, wt, b1);
             }
             const float inv_v = __ldg(J.inv_v + oy);
-            if (ox0 + lane < J.dst_w) {
-                uchar4 o = make_uchar4((unsigned char)srgb_encode(M.T, ar * inv_v), (unsigned char)srgb_encode(M.T, ag * inv_v),
-                                       (unsigned char)srgb_encode(M.T, ab * inv_v), 255);
-                reinterpret_cast<uchar4 *>(J.dst + (size_t)oy * J.dst_pitch)[ox0 + lane] = o;
+            const int ox = ox0 + 2 * lane;
+            uchar4 oa = make_uchar4((unsigned char)srgb_encode(M.T, r0 * inv_v), (unsigned char)srgb_encode(M.T, g0 * inv_v),
+                                    (unsigned char)srgb_encode(M.T, b0 * inv_v), 255);
+            uchar4 ob = make_uchar4((unsigned char)srgb_encode(M.T, r1 * inv_v), (unsigned char)srgb_encode(M.T, g1 * inv_v),
+                                    (unsigned char)srgb_encode(M.T, b1 * inv_v), 255);
+            uchar4 *drow = reinterpret_cast<uchar4 *>(J.dst + (size_t)oy * J.dst_pitch);
+            if (ox + 1 < J.dst_w && (J.dst_pitch & 7) == 0) {
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned int *>(&oa);
+                pk.y = *reinterpret_cast<unsigned int *>(&ob);
+                *reinterpret_cast<uint2 *>(drow + ox) = pk;
+            } else {
+                if (ox < J.dst_w) drow[ox] = oa;
+                if (ox + 1 < J.dst_w) drow[ox + 1] = ob;
             }
         }
         __syncthreads();
@@ -698,10 +681,10 @@ static bool launch_fused_int(const FusedJob *jobs_dev, dim3 g, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_resample_fused_int<S, NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(FusedIntSmem<S>));
+                             (int)sizeof(typename W64<S>::Smem));
         attr_set = true;
     }
-    k_resample_fused_int<S, NV12><<<g, dim3(FS_TW, FS_WARPS), sizeof(FusedIntSmem<S>), s>>>(jobs_dev);
+    k_resample_fused_int<S, NV12><<<g, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev);
     return check_launch("k_resample_fused_int");
 }
 
@@ -712,16 +695,18 @@ int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, i
         cudaFuncSetAttribute(k_resample_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
         attr_set = true;
     }
-    int mx = 1, my = 1;
+    int mx = 1, my = 1, mx64 = 1;
     bool have[5][2] = {};
     for (int i = 0; i < n; i++) {
         int sx = (jobs_host[i].dst_w + FS_TW - 1) / FS_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
+        int sx64 = (jobs_host[i].dst_w + W64_TW - 1) / W64_TW;
         mx = sx > mx ? sx : mx;
+        mx64 = sx64 > mx64 ? sx64 : mx64;
         my = sy > my ? sy : my;
         int v = jobs_host[i].variant;
         have[(v >= 2 && v <= 4) ? v : 0][jobs_host[i].src.kind == TEX_NV12 ? 1 : 0] = true;
     }
-    dim3 g(mx, my, n);
+    dim3 g(mx, my, n), g64(mx64, my, n);
     cudaStream_t st = (cudaStream_t)s;
     int launches = 0;
     // one launch per kernel variant present in the tick; blocks of jobs of another variant exit at once
@@ -731,8 +716,8 @@ int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, i
         launches++;
     }
 #define SMR_LAUNCH_INT(SV)                                                                   \
-    if (have[SV][0]) { if (!launch_fused_int<SV, false>(jobs_dev, g, st)) return -1; launches++; } \
-    if (have[SV][1]) { if (!launch_fused_int<SV, true>(jobs_dev, g, st)) return -1; launches++; }
+    if (have[SV][0]) { if (!launch_fused_int<SV, false>(jobs_dev, g64, st)) return -1; launches++; } \
+    if (have[SV][1]) { if (!launch_fused_int<SV, true>(jobs_dev, g64, st)) return -1; launches++; }
     SMR_LAUNCH_INT(2)
     SMR_LAUNCH_INT(3)
     SMR_LAUNCH_INT(4)

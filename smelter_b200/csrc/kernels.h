@@ -131,6 +131,8 @@ int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s
 int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n_jobs, Stream s);
 int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n_jobs, Stream s);
 int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n_jobs, Stream s);
+// integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping
+void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s);
 int launch_composite(const CompositeJob &job, Stream s);
 int launch_output(const OutputJob &job, Stream s);
 int launch_fill_yuv(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,

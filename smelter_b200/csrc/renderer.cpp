@@ -253,6 +253,8 @@ class Renderer {
     std::vector<dev::ResampleJob> stage_jobs_[3];
     std::vector<std::pair<size_t, size_t>> stage_frame_off_[3];  // (src offset or SIZE_MAX, dst offset)
     std::vector<int> stage_src_tex_[3];       // texture-table index of the source, or -1 when src is a frame-arena f16
+    bool int_weights_set_[5] = {false, false, false, false, false};
+    std::vector<std::pair<int, WeightEntry>> pending_int_weights_;
     std::vector<dev::FusedJob> fused_jobs_;
     std::vector<std::pair<int, size_t>> fused_src_dst_;   // (raw tex index, frame offset of dst)
     std::vector<dev::WeightJob> weight_jobs_;
@@ -516,7 +518,13 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     int seg = ((dh + 3) / 4 + 7) & ~7;
     j.seg_rows = std::max(seg, 64);
     j.variant = 0;
-    if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) j.variant = (int)sh;
+    if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) {
+        j.variant = (int)sh;
+        if (!int_weights_set_[j.variant]) {   // enqueued after k_weights of this tick (same stream)
+            int_weights_set_[j.variant] = true;
+            pending_int_weights_.push_back({j.variant, wh});
+        }
+    }
     fused_jobs_.push_back(j);
     fused_src_dst_.push_back({in.raw_tex, dst_off});
     dev::Tex out;
@@ -1043,6 +1051,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     }
     if (!launched(dev::launch_weights((const dev::WeightJob *)(pd + wj_off), weight_jobs_.data(), (int)weight_jobs_.size(), stream_))) goto fail;
     if (!weight_jobs_.empty()) prof_mark(SMR_KERNEL_WEIGHTS);
+    for (auto &pw : pending_int_weights_) dev::set_int_weights(pw.first, pw.second.weights, pw.second.inv, pw.second.taps, stream_);
+    pending_int_weights_.clear();
     if (!launched(dev::launch_resample_fused((const dev::FusedJob *)(pd + fj_off), fused_jobs_.data(), (int)fused_jobs_.size(), stream_))) goto fail;
     if (!fused_jobs_.empty()) prof_mark(SMR_KERNEL_RESAMPLE_FUSED);
     for (int s = 0; s < 3; s++) {
