@@ -65,7 +65,7 @@ __device__ __forceinline__ void load_tables(Tables &t) {
     __syncthreads();
 }
 
-__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+__device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }  // [0,1], NaN -> 0 (== fmin(fmax(x,0),1))
 
 __device__ __forceinline__ int unorm8(float x) { return __float2int_rn(clamp01(x) * 255.0f); }  // NC-2
 
@@ -539,6 +539,8 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
     const int d0 = xa - xa_e;
     const int npairs = ((W64_TW - 1) * S + TAPS + d0 + 1) >> 1;
     const int full_range = src.full_range;
+    // pairs whose pixels and chroma taps need no clamping: x = xa_e + 2p >= 2 and x + 3 <= W - 1
+    const int p_in_lo = xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1, p_in_hi = (W - 4 - xa_e) >> 1;
 
     int produced_hi = -0x40000000;
     for (int o0 = oy_begin; o0 < oy_end; o0 += W64_WARPS) {
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                 const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
                 const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
                 struct Raw { uchar2 y, a0, b0, d0, a1, b1, d1; };
-                auto interior = [&](int pp) { const int x = xa_e + 2 * pp; return x >= 2 && x + 3 <= W - 1; };
+                auto interior = [&](int pp) { return pp >= p_in_lo && pp <= p_in_hi; };
                 auto load_raw = [&](int pp, Raw &R) {
                     const int x = xa_e + 2 * pp, cx = x >> 1;
                     if (NV12) {
@@ -915,8 +917,56 @@ __device__ __forceinline__ float to_v(float r, float g, float b) {
 
 // general per-pixel path: full fragment shader + fixed-function blend.  Kept out of line: the fast paths of
 // k_composite cover almost every pixel and the instruction cache matters more than the call.
+// true when the rounded-rect alpha of fs_main is provably exactly 1 at this pixel centre: at least `shr`
+// inside every edge and outside the four corner squares of side rmax+2 (there the SDF is the plain edge
+// distance, >= 2 > .5, so smoothstep(-.5,.5,.) == 1)
+__device__ __forceinline__ bool rect_alpha_one(float pcx, float pcy, float left, float top, float w, float h,
+                                               float rmax, float shr) {
+    const float hx = w * 0.5f, hy = h * 0.5f;
+    const float dx = fabsf(pcx - (left + hx)), dy = fabsf(pcy - (top + hy));
+    const bool inside = dx <= hx - shr && dy <= hy - shr;
+    const bool corner = dx > hx - rmax - 2.0f && dy > hy - rmax - 2.0f;
+    return inside && !corner;
+}
+
+// general per-pixel path: full fragment shader + fixed-function blend.  Kept out of line: the fast paths of
+// k_composite cover almost every pixel and the instruction cache matters more than the call.
 __device__ __noinline__ uchar4 shade_blend(const Tables &T, const CompositeJob &J, const LayerDev &L, int X, int Y,
                                            uchar4 dst) {
+    if (!L.rotated && L.type != 2) {
+        // per-pixel version of the host's interior classification (LayerDev::ix0..): straight edges of rounded
+        // layers and masks need no SDF -- only the corner squares do
+        const float pcx = (float)X + 0.5f, pcy = (float)Y + 0.5f;
+        const float rmax = fmaxf(fmaxf(L.border_radius[0], L.border_radius[1]), fmaxf(L.border_radius[2], L.border_radius[3]));
+        const float shr = 2.0f + (L.border_width >= 1.0f ? L.border_width + 1.0f : 0.0f);
+        bool one = rect_alpha_one(pcx, pcy, L.left, L.top, L.content_w, L.content_h, fmaxf(rmax, 0.0f), shr);
+        for (int i = 0; one && i < L.mask_count; i++) {
+            const MaskDev &m = J.masks[L.mask_begin + i];
+            const float mr = fmaxf(fmaxf(m.radius[0], m.radius[1]), fmaxf(m.radius[2], m.radius[3]));
+            one = rect_alpha_one(pcx, pcy, m.left, m.top, m.width, m.height, fmaxf(mr, 0.0f), 2.0f);
+        }
+        if (one) {
+            if (L.type == 1) {  // bare colour
+                if (L.fast & FAST_CONST) return *reinterpret_cast<const uchar4 *>(&L.const_bytes);
+                return blend(T, J.mode, dst, make_float4(L.color[0], L.color[1], L.color[2], L.color[3]));
+            }
+            bool exact;
+            uchar4 texel;
+            float4 sample;
+            if (L.fast & FAST_IDENT) {
+                texel = node_texel(T, J.textures[L.tex], X + L.tx_off, Y + L.ty_off);
+                exact = true;
+                const float *lut = J.mode == 0 ? T.dec : T.u8n;
+                sample = make_float4(lut[texel.x], lut[texel.y], lut[texel.z], T.u8n[texel.w]);
+            } else {
+                const float u = (pcx - L.left) / L.width, v = (pcy - L.top) / L.height;
+                sample = sample_node(T, L.tex >= 0 ? &J.textures[L.tex] : nullptr, J.mode, u * L.crop_sx + L.crop_ox,
+                                     v * L.crop_sy + L.crop_oy, exact, texel);
+            }
+            if (exact && texel.w == 255) return texel;  // encode(decode(b)) == b
+            return blend(T, J.mode, dst, sample);
+        }
+    }
     bool pass;
     uchar4 texel;
     float4 src = shade(T, J, L, X, Y, pass, texel);
