@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstring>
 
 #include "kernels.h"
 
@@ -207,6 +208,42 @@ __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int 
         default:
             return make_uchar4(0, 0, 0, 0);
     }
+}
+
+// K1/K2 for the aligned 2x2 pixel quad (x, y), x and y even, of an even-sized YUV texture.  The four pixels
+// share one 3x3 chroma neighbourhood: texels and horizontal interpolants are computed once (bilerp of NC-6 is
+// horizontal-then-vertical, so sharing the horizontal terms is bit-exact).  Requires 2 <= x <= W-4, 2 <= y <= H-4.
+__device__ __forceinline__ bool yuv_quad_ok(const Tex &s, int x, int y) {
+    return (s.kind == TEX_NV12 || s.kind == TEX_YUV420) && (((s.width | s.height | x | y) & 1) == 0) && x >= 2 &&
+           x + 3 <= s.width - 1 && y >= 2 && y + 3 <= s.height - 1;
+}
+__device__ __forceinline__ void yuv_quad(const Tables &T, const Tex &s, int x, int y, uchar4 &p00, uchar4 &p10,
+                                         uchar4 &p01, uchar4 &p11) {
+    const int cx = x >> 1, cy = y >> 1;
+    float hue[3], huo[3], hve[3], hvo[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float ua, ub, ud, va, vb, vd;
+        if (s.kind == TEX_NV12) {
+            const uchar2 *rp = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)(cy - 1 + i) * s.pitch1) + cx;
+            const uchar2 a = __ldg(rp - 1), b = __ldg(rp), d = __ldg(rp + 1);
+            ua = T.u8n[a.x]; ub = T.u8n[b.x]; ud = T.u8n[d.x];
+            va = T.u8n[a.y]; vb = T.u8n[b.y]; vd = T.u8n[d.y];
+        } else {
+            const uint8_t *ru = s.p1 + (size_t)(cy - 1 + i) * s.pitch1 + cx, *rv = s.p2 + (size_t)(cy - 1 + i) * s.pitch2 + cx;
+            ua = T.u8n[__ldg(ru - 1)]; ub = T.u8n[__ldg(ru)]; ud = T.u8n[__ldg(ru + 1)];
+            va = T.u8n[__ldg(rv - 1)]; vb = T.u8n[__ldg(rv)]; vd = T.u8n[__ldg(rv + 1)];
+        }
+        hue[i] = fmaf(ub, 0.75f, ua * 0.25f); huo[i] = fmaf(ud, 0.25f, ub * 0.75f);
+        hve[i] = fmaf(vb, 0.75f, va * 0.25f); hvo[i] = fmaf(vd, 0.25f, vb * 0.75f);
+    }
+    const uchar2 y0 = __ldg(reinterpret_cast<const uchar2 *>(s.p0 + (size_t)y * s.pitch0 + x));
+    const uchar2 y1 = __ldg(reinterpret_cast<const uchar2 *>(s.p0 + (size_t)(y + 1) * s.pitch0 + x));
+    // even row: chroma rows (cy-1, cy), fy = .75 ; odd row: (cy, cy+1), fy = .25
+    p00 = yuv_to_rgba8(T.u8n[y0.x], fmaf(hue[1], 0.75f, hue[0] * 0.25f), fmaf(hve[1], 0.75f, hve[0] * 0.25f), s.full_range);
+    p10 = yuv_to_rgba8(T.u8n[y0.y], fmaf(huo[1], 0.75f, huo[0] * 0.25f), fmaf(hvo[1], 0.75f, hvo[0] * 0.25f), s.full_range);
+    p01 = yuv_to_rgba8(T.u8n[y1.x], fmaf(hue[2], 0.25f, hue[1] * 0.75f), fmaf(hve[2], 0.25f, hve[1] * 0.75f), s.full_range);
+    p11 = yuv_to_rgba8(T.u8n[y1.y], fmaf(huo[2], 0.25f, huo[1] * 0.75f), fmaf(hvo[2], 0.25f, hvo[1] * 0.75f), s.full_range);
 }
 
 __global__ void __launch_bounds__(256) k_convert(Tex src, uint8_t *dst, int dst_pitch) {
@@ -778,9 +815,14 @@ __device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, i
         texel = p00;
         return make_float4(lut[p00.x], lut[p00.y], lut[p00.z], T.u8n[p00.w]);
     }
-    uchar4 p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
-    uchar4 p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
-    uchar4 p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
+    uchar4 p10, p01, p11;
+    if (ax.i1 == ax.i0 + 1 && ay.i1 == ay.i0 + 1 && yuv_quad_ok(S, ax.i0, ay.i0)) {
+        yuv_quad(T, S, ax.i0, ay.i0, p00, p10, p01, p11);  // the 4 taps are one chroma-aligned quad (e.g. exact 2:1)
+    } else {
+        p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
+        p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
+        p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
+    }
     float4 r;
     r.x = bilerp(lut[p00.x], lut[p10.x], lut[p01.x], lut[p11.x], ax.f, ay.f);
     r.y = bilerp(lut[p00.y], lut[p10.y], lut[p01.y], lut[p11.y], ax.f, ay.f);
@@ -977,40 +1019,73 @@ __device__ __noinline__ uchar4 shade_blend(const Tables &T, const CompositeJob &
 #define CT_H 2           // pixels per thread, y
 #define CB_X 32          // threads per block, x
 #define CB_Y 8
+#define CT_ITERS 1       // vertical steps per thread (1: a block covers 128 x 16 pixels; more starves 1080p frames of blocks)
 #define MAX_TILE_LAYERS 1024
 #define SM_LAYERS 40     // layers of a tile kept in shared memory (the rest are read from global)
 
-__global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
+// PARAM: the layer list travels in the kernel parameter block (constant bank): the per-tile culling and the
+// per-pixel loop read it with no global round trip and no shared-memory copy; used whenever it fits.
+#define PARAM_LAYERS 96
+struct CompositeParams {
+    CompositeJob job;
+    LayerDev layers[PARAM_LAYERS];
+};
+
+template <bool PARAM>
+__device__ __forceinline__ void composite_body(const CompositeJob &J, const LayerDev *__restrict__ LAYERS) {
     __shared__ Tables T;
     __shared__ unsigned short s_list[MAX_TILE_LAYERS];
     __shared__ int s_count;
-    __shared__ LayerDev s_layers[SM_LAYERS];
+    __shared__ LayerDev s_layers[PARAM ? 1 : SM_LAYERS];
     load_tables(T);
-    const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H);
-    const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H, J.height);
-    // per-tile layer culling, painter's order preserved
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        int c = 0;
-        for (int i = 0; i < J.n_layers && c < MAX_TILE_LAYERS; i++) {
-            const LayerDev &L = J.layers[i];
-            if (L.px0 < tile_x1 && L.px1 > tile_x0 && L.py0 < tile_y1 && L.py1 > tile_y0) s_list[c++] = (unsigned short)i;
+    const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H * CT_ITERS);
+    const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H * CT_ITERS, J.height);
+    // per-tile layer culling, painter's order preserved.  One layer per thread (a serial loop over the layer
+    // list costs one dependent global-load latency per layer while the whole block waits), ordered compaction
+    // with ballots.
+    {
+        __shared__ int s_wc[CB_Y];
+        const int tid = threadIdx.y * CB_X + threadIdx.x;
+        int base_count = 0;
+        for (int base = 0; base < J.n_layers; base += CB_X * CB_Y) {
+            const int i = base + tid;
+            bool hit = false;
+            if (i < J.n_layers) {
+                int4 bb;
+                if (PARAM) bb = make_int4(LAYERS[i].px0, LAYERS[i].px1, LAYERS[i].py0, LAYERS[i].py1);
+                else bb = __ldg(reinterpret_cast<const int4 *>(&LAYERS[i].px0));
+                hit = bb.x < tile_x1 && bb.y > tile_x0 && bb.z < tile_y1 && bb.w > tile_y0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (threadIdx.x == 0) s_wc[threadIdx.y] = __popc(m);
+            __syncthreads();
+            int before = base_count, total = base_count;
+            for (int w = 0; w < CB_Y; w++) {
+                if (w < (int)threadIdx.y) before += s_wc[w];
+                total += s_wc[w];
+            }
+            const int pos = before + __popc(m & ((1u << threadIdx.x) - 1u));
+            if (hit && pos < MAX_TILE_LAYERS) s_list[pos] = (unsigned short)i;
+            base_count = min(total, MAX_TILE_LAYERS);
+            __syncthreads();
         }
-        s_count = c;
+        if (tid == 0) s_count = base_count;
     }
     __syncthreads();
-    {
+    if (!PARAM) {
         const int nsm = min(s_count, SM_LAYERS);
         const int words = (int)(sizeof(LayerDev) / 4);
         const int tid = threadIdx.y * CB_X + threadIdx.x;
         for (int i = tid; i < nsm * words; i += CB_X * CB_Y) {
             int l = i / words, w = i - l * words;
             reinterpret_cast<unsigned int *>(&s_layers[l])[w] =
-                __ldg(reinterpret_cast<const unsigned int *>(&J.layers[s_list[l]]) + w);
+                __ldg(reinterpret_cast<const unsigned int *>(&LAYERS[s_list[l]]) + w);
         }
     }
     __syncthreads();
 
-    const int x0 = tile_x0 + threadIdx.x * CT_W, y0 = tile_y0 + threadIdx.y * CT_H;
+    for (int it = 0; it < CT_ITERS; it++) {
+    const int x0 = tile_x0 + threadIdx.x * CT_W, y0 = tile_y0 + (it * CB_Y + threadIdx.y) * CT_H;
     uchar4 px[CT_H][CT_W];
 #pragma unroll
     for (int j = 0; j < CT_H; j++)
@@ -1019,7 +1094,7 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
 
     const int n = s_count;
     for (int li = 0; li < n; li++) {
-        const LayerDev &L = li < SM_LAYERS ? s_layers[li] : J.layers[s_list[li]];
+        const LayerDev &L = PARAM ? LAYERS[s_list[li]] : (li < SM_LAYERS ? s_layers[li] : LAYERS[s_list[li]]);
         if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
         const bool all_in = x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1;
         if (all_in && (L.fast & FAST_CONST)) {  // opaque colour interior: the layer leaves constant bytes
@@ -1032,6 +1107,24 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
         }
         if (all_in && (L.fast & FAST_IDENT)) {  // 1:1 texture interior: exact texel per pixel
             const Tex &S = J.textures[L.tex];
+            const int sx = x0 + L.tx_off, sy = y0 + L.ty_off;
+            if (yuv_quad_ok(S, sx, sy) && yuv_quad_ok(S, sx + 2, sy)) {  // YUV source: two chroma-aligned quads
+                yuv_quad(T, S, sx, sy, px[0][0], px[0][1], px[1][0], px[1][1]);       // alpha is 255: bytes pass through
+                yuv_quad(T, S, sx + 2, sy, px[0][2], px[0][3], px[1][2], px[1][3]);
+                continue;
+            }
+            if (S.kind == TEX_RGBA8 && (sx & 3) == 0 && (S.pitch0 & 15) == 0 && ((size_t)S.p0 & 15) == 0) {
+                // RGBA8 source (e.g. a resampled child): one 16-byte load per row
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)sy * S.pitch0) + (sx >> 2));
+                const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)(sy + 1) * S.pitch0) + (sx >> 2));
+                if ((r0.x & r0.y & r0.z & r0.w & r1.x & r1.y & r1.z & r1.w) >= 0xff000000u) {  // all 8 alphas are 255
+                    *reinterpret_cast<unsigned int *>(&px[0][0]) = r0.x; *reinterpret_cast<unsigned int *>(&px[0][1]) = r0.y;
+                    *reinterpret_cast<unsigned int *>(&px[0][2]) = r0.z; *reinterpret_cast<unsigned int *>(&px[0][3]) = r0.w;
+                    *reinterpret_cast<unsigned int *>(&px[1][0]) = r1.x; *reinterpret_cast<unsigned int *>(&px[1][1]) = r1.y;
+                    *reinterpret_cast<unsigned int *>(&px[1][2]) = r1.z; *reinterpret_cast<unsigned int *>(&px[1][3]) = r1.w;
+                    continue;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < CT_H; j++)
 #pragma unroll
@@ -1061,7 +1154,7 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
         }
     }
 
-    if (x0 >= J.width || y0 >= J.height) return;
+    if (x0 >= J.width || y0 >= J.height) continue;
     if (J.out_format < 0 || J.out_format == 3) {  // RGBA8 node texture / RgbaWgpuTexture analogue
 #pragma unroll
         for (int j = 0; j < CT_H; j++) {
@@ -1079,7 +1172,7 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
                 for (int i = 0; i < CT_W && x0 + i < J.width; i++) row[x0 + i] = px[j][i];
             }
         }
-        return;
+        continue;
     }
     // fused K10/K11 (host guarantees even width/height): Y per pixel, chroma = 2x2 box of raw bytes
     unsigned char yv[CT_H][CT_W];
@@ -1122,10 +1215,23 @@ __global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) {
         } else
             for (int c = 0; c < 2 && cx + c < cw; c++) { ru[c] = uo[c]; rv[c] = vo[c]; }
     }
+    }  // it
+}
+
+__global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
+__global__ void __launch_bounds__(CB_X *CB_Y) k_composite_p(const __grid_constant__ CompositeParams P) {
+    composite_body<true>(P.job, P.layers);
 }
 
 int launch_composite(const CompositeJob &job, Stream s) {
-    dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H - 1) / (CB_Y * CT_H));
+    dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
+    if (job.n_layers <= PARAM_LAYERS && job.layers_host != nullptr) {
+        static CompositeParams P;   // launches are serialised by the handle's mutex; the driver copies at launch
+        P.job = job;
+        memcpy(P.layers, job.layers_host, sizeof(LayerDev) * (size_t)job.n_layers);
+        k_composite_p<<<g, b, 0, (cudaStream_t)s>>>(P);
+        return check_launch("k_composite_p") ? 1 : -1;
+    }
     k_composite<<<g, b, 0, (cudaStream_t)s>>>(job);
     return check_launch("k_composite") ? 1 : -1;
 }

@@ -35,7 +35,7 @@ struct MaskDev {
 
 // One flattened RenderLayout, prepared on the host for the composite kernel
 // (uniform blocks of layout/params.rs:199-317 + the vertex stage of apply_layouts.wgsl:174-243).
-struct LayerDev {
+struct alignas(16) LayerDev {
     int32_t type;       // 0 texture, 1 color, 2 box shadow
     int32_t rotated;
     float left, top, width, height;  // the quad (box shadow: grown by blur_radius)
@@ -63,7 +63,8 @@ struct CompositeJob {
     int32_t width, height;           // render target (root node texture) size
     int32_t mode;                    // 0 GpuOptimized (sRGB target, linear blend), 1 CpuOptimized
     int32_t n_layers;
-    const LayerDev *layers;
+    const LayerDev *layers;          // device copy
+    const LayerDev *layers_host;     // host copy: small lists are passed in the kernel parameter block instead
     const MaskDev *masks;
     const Tex *textures;
     // outputs: RGBA8 target and/or fused YUV planes (K10/K11)

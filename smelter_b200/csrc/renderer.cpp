@@ -1062,6 +1062,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     }
     for (PendingComposite &pc : composites_) {
         pc.job.layers = (const dev::LayerDev *)(pd + pc.layers_off);
+        pc.job.layers_host = (const dev::LayerDev *)(param_host_.data() + pc.layers_off);
         pc.job.masks = (const dev::MaskDev *)(pd + pc.masks_off);
         pc.job.textures = (const dev::Tex *)(pd + tex_off);
         if (pc.job.out_format == -1 && pc.job.out1 == (uint8_t *)(uintptr_t)1) {
