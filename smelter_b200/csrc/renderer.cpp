@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -191,7 +192,7 @@ class Renderer {
     struct Input {
         bool has_frame = false;
         dev::Tex tex;           // planes as they sit in HBM
-        DevBuf planes[3];       // owned copies of host frames
+        DevBuf planes[2][3];    // owned copies of host frames, double-buffered by tick parity
         Resolution res;
         int node_tex = -1;      // index in the tick's texture table of the materialised RGBA8 node texture
         int raw_tex = -1;       // index of the virtual (fused K1/K2) texture
@@ -269,12 +270,24 @@ class Renderer {
 
     std::vector<uint8_t> param_host_;  // built here, copied to pinned, then to device
     size_t param_used_ = 0;
-    PinnedBuf param_pinned_;
-    DevBuf param_dev_;
+    PinnedBuf param_pinned_[2];   // double-buffered by tick parity: tick n+1 is prepared and uploaded
+    DevBuf param_dev_[2];         // while tick n is still executing
     size_t frame_used_ = 0;
     DevBuf frame_dev_;
     std::map<WeightKey, WeightEntry> weights_;
-    bool in_flight_ = false;
+    // up to two ticks in flight: uploads of tick n+1 (copy stream) overlap the kernels of tick n
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, tick_done_[2] = {nullptr, nullptr};
+    std::deque<int> inflight_;
+    int slot_ = 0;
+    bool uploaded_ = false;
+    void drain() {
+        if (stream_) cudaStreamSynchronize(stream_);
+        if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+        fold_profile();
+        inflight_.clear();
+    }
+    void fold_profile();
     bool host_only_ = false;
     // optional per-kernel-class device timing (cudaEvents on the launching stream)
     void prof_mark(int kernel_class);
@@ -298,6 +311,8 @@ Renderer::~Renderer() {
     if (stream_) {
         cudaSetDevice(opts_.cuda_device);
         cudaStreamSynchronize(stream_);
+        if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+        for (int i = 0; i < 2; i++) { if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]); if (tick_done_[i]) cudaEventDestroy(tick_done_[i]); }
         if (nccl_comm_) { g_nccl.CommDestroy(nccl_comm_); nccl_comm_ = nullptr; }
         for (auto &kv : weights_) {
             cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
@@ -328,6 +343,11 @@ smr_status Renderer::init() {
     }
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_OK(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&tick_done_[i], cudaEventDisableTiming));
+    }
     float u8n[256], dec[256], thr[255];
     for (int b = 0; b < 256; b++) {
         u8n[b] = (float)b / 255.0f;
@@ -349,7 +369,7 @@ smr_status Renderer::register_input(const char *id) {
 smr_status Renderer::unregister_input(const char *id) {
     if (!id) return SMR_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(mu_);
-    if (in_flight_) { cudaSetDevice(opts_.cuda_device); cudaStreamSynchronize(stream_); in_flight_ = false; }
+    if (!host_only_) { cudaSetDevice(opts_.cuda_device); drain(); }
     inputs_.erase(id);
     return SMR_OK;
 }
@@ -357,7 +377,7 @@ smr_status Renderer::unregister_input(const char *id) {
 smr_status Renderer::unregister_output(const char *id) {
     if (!id) return SMR_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(mu_);
-    if (in_flight_) { cudaSetDevice(opts_.cuda_device); cudaStreamSynchronize(stream_); in_flight_ = false; }
+    if (!host_only_) { cudaSetDevice(opts_.cuda_device); drain(); }
     outputs_.erase(id);
     scene_.unregister_output(id);
     return SMR_OK;
@@ -454,11 +474,12 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
                 ptrs[p] = (const uint8_t *)f->planes[p];
                 pitches[p] = (int)spitch;
             } else {
-                CUDA_OK(I.planes[p].ensure(row_bytes * rows));
-                CUDA_OK(cudaMemcpy2DAsync(I.planes[p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
-                                          cudaMemcpyHostToDevice, stream_));
+                CUDA_OK(I.planes[slot_][p].ensure(row_bytes * rows));
+                CUDA_OK(cudaMemcpy2DAsync(I.planes[slot_][p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
+                                          cudaMemcpyHostToDevice, copy_stream_));
+                uploaded_ = true;
                 stats_.h2d_bytes += row_bytes * rows;
-                ptrs[p] = I.planes[p].p;
+                ptrs[p] = I.planes[slot_][p].p;
                 pitches[p] = (int)row_bytes;
             }
         }
@@ -750,6 +771,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
             pitch[p] = (int)user_pitch;
         } else {
             size_t dp = (row_bytes[p] + 15) & ~(size_t)15;  // 16-B rows: vector stores
+            if (dp * rows[p] > o.planes[p].cap && !inflight_.empty()) CUDA_OK(cudaStreamSynchronize(stream_));
             CUDA_OK(o.planes[p].ensure(dp * rows[p]));
             dst[p] = o.planes[p].p;
             pitch[p] = (int)dp;
@@ -975,8 +997,17 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     std::lock_guard<std::mutex> g(mu_);
     if (host_only_) { set_error("host-only handle (cuda_device = -1) cannot render: no CPU fallback"); return SMR_ERR_CUDA; }
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
-    if (in_flight_) { CUDA_OK(cudaStreamSynchronize(stream_)); in_flight_ = false; }
+    if (profiling_ && !inflight_.empty()) drain();   // per-kernel timing: one tick at a time
     tick_++;
+    slot_ = (int)(tick_ & 1);
+    // the slot's buffers (pinned params, input staging) belong to tick-2: wait for it (without retiring it)
+    for (int s : inflight_)
+        if (s == slot_) CUDA_OK(cudaEventSynchronize(tick_done_[s]));
+    while (inflight_.size() >= 2) {   // never more than two in flight: the oldest is retired here
+        CUDA_OK(cudaEventSynchronize(tick_done_[inflight_.front()]));
+        inflight_.pop_front();
+    }
+    uploaded_ = false;
     tex_table_.clear(); tex_frame_off_.clear();
     for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
     fused_jobs_.clear(); fused_src_dst_.clear();
@@ -1005,6 +1036,11 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     }
 
     // ---- resolve frame-arena addresses --------------------------------------------------------
+    if (uploaded_) {   // kernels of this tick start after its uploads; earlier ticks keep running meanwhile
+        CUDA_OK(cudaEventRecord(h2d_done_[slot_], copy_stream_));
+        CUDA_OK(cudaStreamWaitEvent(stream_, h2d_done_[slot_], 0));
+    }
+    if (frame_used_ + 512 > frame_dev_.cap && !inflight_.empty()) CUDA_OK(cudaStreamSynchronize(stream_));
     CUDA_OK(frame_dev_.ensure(frame_used_ + 512));
     uint8_t *fb = frame_dev_.p;
     for (size_t i = 0; i < tex_table_.size(); i++)
@@ -1035,11 +1071,11 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
     if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
-    CUDA_OK(param_pinned_.ensure(param_used_));
-    CUDA_OK(param_dev_.ensure(param_used_));
-    memcpy(param_pinned_.p, param_host_.data(), param_used_);
-    CUDA_OK(cudaMemcpyAsync(param_dev_.p, param_pinned_.p, param_used_, cudaMemcpyHostToDevice, stream_));
-    uint8_t *pd = param_dev_.p;
+    CUDA_OK(param_pinned_[slot_].ensure(param_used_));
+    CUDA_OK(param_dev_[slot_].ensure(param_used_));
+    memcpy(param_pinned_[slot_].p, param_host_.data(), param_used_);
+    CUDA_OK(cudaMemcpyAsync(param_dev_[slot_].p, param_pinned_[slot_].p, param_used_, cudaMemcpyHostToDevice, stream_));
+    uint8_t *pd = param_dev_[slot_].p;
 
     // ---- launches -----------------------------------------------------------------------------
     auto launched = [&](int n) -> bool { if (n < 0) return false; launches += (uint64_t)n; return true; };
@@ -1086,7 +1122,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     stats_.kernel_launches += launches;
     stats_.last_render_kernel_launches = launches;
     stats_.frames_rendered += n_out;
-    in_flight_ = true;
+    CUDA_OK(cudaEventRecord(tick_done_[slot_], stream_));
+    inflight_.push_back(slot_);
     return SMR_OK;
 fail:
     set_error(dev::last_launch_error());
@@ -1116,12 +1153,18 @@ smr_status Renderer::debug_set_inputs(uint64_t pts, const smr_input_frame *in, u
     return SMR_OK;
 }
 
-smr_status Renderer::render_end() {
+smr_status Renderer::render_end() {   // retires the OLDEST tick in flight
     std::lock_guard<std::mutex> g(mu_);
-    if (!in_flight_) return SMR_OK;
+    if (inflight_.empty()) return SMR_OK;
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
-    in_flight_ = false;
-    CUDA_OK(cudaStreamSynchronize(stream_));
+    int s = inflight_.front();
+    inflight_.pop_front();
+    CUDA_OK(cudaEventSynchronize(tick_done_[s]));
+    if (inflight_.empty()) fold_profile();
+    return SMR_OK;
+}
+
+void Renderer::fold_profile() {
     // fold this tick's event pairs into the per-kernel-class totals
     for (size_t i = 1; i < prof_marks_.size(); i++) {
         int k = prof_marks_[i].second;
@@ -1133,7 +1176,6 @@ smr_status Renderer::render_end() {
         }
     }
     prof_marks_.clear();
-    return SMR_OK;
 }
 
 void Renderer::prof_mark(int kernel_class) {
@@ -1190,7 +1232,6 @@ smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, c
     int rc2 = g_nccl.GroupEnd();
     if (rc == 0) rc = rc2;
     if (rc != 0) { set_error(std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
-    in_flight_ = true;
     return SMR_OK;
 }
 
@@ -1207,6 +1248,7 @@ smr_status Renderer::comm_destroy() {
 
 smr_status Renderer::set_profiling(int enabled) {
     std::lock_guard<std::mutex> g(mu_);
+    if (!host_only_) { cudaSetDevice(opts_.cuda_device); drain(); }
     profiling_ = enabled != 0;
     memset(&prof_, 0, sizeof(prof_));
     return SMR_OK;

@@ -342,3 +342,45 @@ def test_wide_identity_mapping_4k_row():
           background_color=s.RGBAColor(200, 10, 10, 255), border_width=3.0, border_color=s.RGBAColor(255, 255, 255, 255),
           border_radius=s.BorderRadius.new_with_radius(9.0))])
     check(scene, fr, resolution=s.Resolution(w, h), out_format=NV12)
+
+
+def test_two_ticks_in_flight_give_the_same_frames():
+    """smr_render_begin(k+1) before smr_render_end(k): uploads of the next tick overlap the kernels of the
+    current one (double-buffered staging); every tick's output must equal the synchronous result."""
+    import ctypes as C
+    from smelter_b200 import _ffi as F
+    w, h, n = 640, 360, 3
+    scene = s.TilesComponent(children=streams(n), background_color=BG)
+    ticks = [{f"input_{i}": yuv_frame(harness.random_yuv420(1000 + 10 * k + i, w, h), w, h) for i in range(1, n + 1)}
+             for k in range(5)]
+    ref = s.Renderer()
+    for i in range(1, n + 1):
+        ref.register_input(f"input_{i}")
+    ref.update_scene(OUTPUT_ID, RES, YUV, scene)
+    expected = [[np.array(p) for p in ref.render(s.FrameSet(frames=t, pts=0.0)).frames[OUTPUT_ID].data.planes] for t in ticks]
+
+    r = s.Renderer()
+    for i in range(1, n + 1):
+        r.register_input(f"input_{i}")
+    r.update_scene(OUTPUT_ID, RES, YUV, scene)
+    keep, outs = [], []
+    def submit(t):
+        arr = r._input_frames(s.FrameSet(frames=t, pts=0.0), keep)
+        planes = [np.empty(w * h, np.uint8), np.empty(w * h // 4, np.uint8), np.empty(w * h // 4, np.uint8)]
+        o = (F.OutputFrame * 1)()
+        o[0].output_id = OUTPUT_ID.encode()
+        o[0].mem_kind = F.MEM_HOST
+        for p in range(3):
+            o[0].planes[p] = planes[p].ctypes.data
+        keep.append((arr, o))
+        outs.append(planes)
+        r.render_raw(0, arr, len(t), o, 1, wait=False)
+    submit(ticks[0])
+    for k in range(1, len(ticks)):
+        submit(ticks[k])
+        r.wait()  # retires tick k-1
+        for got, exp in zip(outs[k - 1], expected[k - 1]):
+            assert np.array_equal(got, exp.reshape(-1)), f"tick {k - 1}"
+    r.wait()
+    for got, exp in zip(outs[-1], expected[-1]):
+        assert np.array_equal(got, exp.reshape(-1))
