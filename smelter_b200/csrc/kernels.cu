@@ -398,122 +398,18 @@ int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, i
 // ------------------------------------------------------------------------------------------------
 // K1/K2 + K8 + K8 fused: the common resample (YUV input, horizontal pass first, then vertical).
 //
-// One block owns a strip of FS_TW output columns and a run of output rows and streams DOWN the source:
+// One block owns a strip of 64 output columns and a run of output rows and streams DOWN the source:
 //   phase A  each warp takes whole source rows: converts the strip's source pixels ONCE (K1/K2 -> RGBA8
 //            quantisation -> sRGB decode), runs the horizontal Lanczos pass out of a per-warp shared-memory
 //            row and stores the f16-quantised result into a ring of intermediate rows in shared memory;
 //   phase B  each warp produces one output row: vertical Lanczos pass out of the ring, sRGB8 encode,
-//            coalesced uchar4 store.
+//            coalesced stores.
 // Neither the RGBA8 node texture (4 B/px of the INPUT resolution) nor the Rgba16Float intermediate ever
 // reaches HBM; a source row is converted once per strip.  Bit-identical to running K1, resample.wgsl pass 1
 // (-> f16) and pass 2 (-> sRGB8) separately: every quantisation point is reproduced.
-// ------------------------------------------------------------------------------------------------
-#define FS_TW 32         // output columns per block (one lane each)
-#define FS_WARPS 8
-#define FS_RING 64       // intermediate rows resident in shared memory (power of two)
-#define FS_SPAN 160      // max source pixels a strip's horizontal taps touch
-#define FS_MAXTAPS 32
-
-struct FusedSmem {
-    Tables T;
-    float hw[FS_TW * FS_MAXTAPS];           // horizontal weights of the strip's columns [lane][tap]
-    float ring[FS_RING][3][FS_TW];          // f16-quantised intermediate rows (kept as f32 values)
-    float srow[FS_WARPS][3][FS_SPAN];       // per-warp converted + decoded source row
-};
-
-// K1/K2 for one pixel of an even-sized YUV texture, returning decoded linear rgb (alpha is 1)
-__device__ __forceinline__ void yuv_px_linear(const Tables &T, const Tex &s, int x, int y, float &r, float &g, float &b) {
-    uchar4 p = node_texel(T, s, x, y);
-    r = T.dec[p.x]; g = T.dec[p.y]; b = T.dec[p.z];
-}
-
-__global__ void __launch_bounds__(FS_TW *FS_WARPS) k_resample_fused(const FusedJob *jobs) {
-    extern __shared__ __align__(16) unsigned char fs_raw[];
-    FusedSmem &S = *reinterpret_cast<FusedSmem *>(fs_raw);
-    const FusedJob &J = jobs[blockIdx.z];
-    if (J.variant != 0) return;  // handled by k_resample_fused_int
-    load_tables(S.T);
-    const int lane = threadIdx.x, warp = threadIdx.y;
-    const int ox0 = blockIdx.x * FS_TW;
-    if (ox0 >= J.dst_w) return;
-    const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
-    if (oy_begin >= J.dst_h) return;
-    const Tex &src = J.src;
-    const int W = src.width, H = src.height;
-    const int th = J.taps_h, tv = J.taps_v;
-
-    // horizontal tables of this strip
-    const int ox = min(ox0 + lane, J.dst_w - 1);
-    const int first_h = __ldg(J.first_h + ox);
-    const float inv_h = __ldg(J.inv_h + ox);
-    for (int t = warp; t < th; t += FS_WARPS) S.hw[lane * th + t] = __ldg(J.w_h + (size_t)ox * th + t);
-    const int xa = __shfl_sync(0xffffffffu, first_h, 0);  // first_h is non-decreasing in ox
-    const int o_last = min(ox0 + FS_TW - 1, J.dst_w - 1);
-    const int span = (__ldg(J.first_h + o_last) + th - 1) - xa + 1;  // <= FS_SPAN (host checked)
-    const int off = first_h - xa;
-    __syncthreads();
-
-    int produced_hi = -0x40000000;  // highest source row already in the ring
-    for (int o0 = oy_begin; o0 < oy_end; o0 += FS_WARPS) {
-        const int o_l = min(o0 + FS_WARPS - 1, oy_end - 1);
-        const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
-        const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
-        const int start = max(produced_hi + 1, need_lo);
-        // ---- phase A: produce intermediate rows [start, need_hi] ---------------------------------
-        for (int r = start + warp; r <= need_hi; r += FS_WARPS) {
-            float *sr = S.srow[warp][0], *sg = S.srow[warp][1], *sb = S.srow[warp][2];
-            for (int i = lane; i < span; i += 32) {
-                int x = min(max(xa + i, 0), W - 1);
-                float rr, gg, bb;
-                yuv_px_linear(S.T, src, x, r, rr, gg, bb);
-                sr[i] = rr; sg[i] = gg; sb[i] = bb;
-            }
-            __syncwarp();
-            float ar = 0.f, ag = 0.f, ab = 0.f;
-            const float *w = &S.hw[lane * th];
-            for (int t = 0; t < th; t++) {
-                float wt = w[t];
-                ar = fmaf(sr[off + t], wt, ar);
-                ag = fmaf(sg[off + t], wt, ag);
-                ab = fmaf(sb[off + t], wt, ab);
-            }
-            float *dst = &S.ring[r & (FS_RING - 1)][0][0];
-            dst[lane] = __half2float(__float2half_rn(ar * inv_h));               // NC-5
-            dst[FS_TW + lane] = __half2float(__float2half_rn(ag * inv_h));
-            dst[2 * FS_TW + lane] = __half2float(__float2half_rn(ab * inv_h));
-            __syncwarp();
-        }
-        produced_hi = max(produced_hi, need_hi);
-        __syncthreads();
-        // ---- phase B: one output row per warp ---------------------------------------------------------
-        const int oy = o0 + warp;
-        if (oy < oy_end) {
-            const int fv = __ldg(J.first_v + oy);
-            const float *wv = J.w_v + (size_t)oy * tv;
-            float ar = 0.f, ag = 0.f, ab = 0.f;
-            for (int t = 0; t < tv; t++) {
-                float wt = __ldg(wv + t);
-                if (wt == 0.0f) continue;
-                int row = min(max(fv + t, 0), H - 1);
-                const float *p = &S.ring[row & (FS_RING - 1)][0][0];
-                ar = fmaf(p[lane], wt, ar);
-                ag = fmaf(p[FS_TW + lane], wt, ag);
-                ab = fmaf(p[2 * FS_TW + lane], wt, ab);
-            }
-            float inv_v = __ldg(J.inv_v + oy);
-            if (ox0 + lane < J.dst_w) {
-                uchar4 o = make_uchar4((unsigned char)srgb_encode(S.T, ar * inv_v), (unsigned char)srgb_encode(S.T, ag * inv_v),
-                                       (unsigned char)srgb_encode(S.T, ab * inv_v), 255);
-                reinterpret_cast<uchar4 *>(J.dst + (size_t)oy * J.dst_pitch)[ox0 + lane] = o;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same fused resample specialised for an INTEGER horizontal ratio S (2:1, 3:1, 4:1 with a zero crop
-// offset -- every grid / mosaic of the BASELINE configs).  Then first(o) = S*o + const and every output column
+//
+// Template parameter S: 0 = any ratio <= 4 (per-column weights and first-tap indices from shared memory);
+// 2, 3, 4 = INTEGER horizontal ratio with a zero crop offset -- every grid / mosaic of the BASELINE configs.  Then first(o) = S*o + const and every output column
 // has the same TAPS = 6S+1 weights (exact small-integer arithmetic in resample.wgsl:45-50), which allows:
 //   * weights in CONSTANT memory: the FFMA reads them as c[bank][offset] operands, no register, no load;
 //   * register blocking: a lane produces 2 adjacent output columns from one (S+TAPS)-long window;
@@ -537,17 +433,19 @@ void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int 
     cudaMemcpyToSymbolAsync(c_winv, inv_dev, sizeof(float), sizeof(float) * S, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
 }
 
-template <int S>
+template <int S>   // S = 0: any ratio <= 4 (weights per column from shared memory)
 struct W64 {
-    static constexpr int TAPS = 6 * S + 1;
-    static constexpr int SPAN = (W64_TW - 1) * S + TAPS + 1;          // + chroma alignment
-    static constexpr int ROWLEN = ((SPAN + SPAN / (2 * S) + 2) + 7) & ~7;
+    static constexpr int SS = S == 0 ? 4 : S;                           // sizing ratio
+    static constexpr int TAPS = 6 * SS + 1;
+    static constexpr int SPAN = (W64_TW - 1) * SS + TAPS + 3;          // + chroma alignment / ceil slack
+    static constexpr int ROWLEN = ((SPAN + SPAN / (2 * SS) + 2) + 7) & ~7;
     struct Smem {
         Tables T;
         __half2 ring[W64_RING][3][W64_TW / 2];
         float srow[W64_WARPS][3][ROWLEN];
+        float hw[S == 0 ? W64_TW * TAPS : 1];                          // generic: [column][tap]
     };
-    static __device__ __forceinline__ int pos(int i) { return i + i / (2 * S); }
+    static __device__ __forceinline__ int pos(int i) { return i + i / (2 * SS); }
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -555,12 +453,13 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 template <int S, bool NV12>
 __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const FusedJob *jobs) {
     using K = W64<S>;
-    constexpr int TAPS = K::TAPS;
-    constexpr int WIN = S + TAPS;  // window feeding 2 adjacent output columns
+    constexpr int TAPS = K::TAPS;  // S > 0: exact tap count; S == 0: upper bound (the job's taps_h is used)
+    constexpr int WIN = S + TAPS;  // S > 0: window feeding 2 adjacent output columns
     extern __shared__ __align__(16) unsigned char fs_raw[];
     typename K::Smem &M = *reinterpret_cast<typename K::Smem *>(fs_raw);
     const FusedJob &J = jobs[blockIdx.z];
     if (J.variant != S || (J.src.kind == TEX_NV12) != NV12) return;
+    const int th = S == 0 ? J.taps_h : TAPS;
     const int ox0 = blockIdx.x * W64_TW;
     if (ox0 >= J.dst_w) return;
     const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
@@ -570,11 +469,28 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
     const Tex &src = J.src;
     const int W = src.width, H = src.height, chei = H >> 1;
     const int tv = J.taps_v;
-    const float inv_h = c_winv[S];
-    const int xa = __ldg(J.first_h + ox0);      // first(o) = S*o + const
+    const int xa = __ldg(J.first_h + ox0);      // S > 0: first(o) = S*o + const
     const int xa_e = xa & ~1;                   // chroma-aligned start
     const int d0 = xa - xa_e;
-    const int npairs = ((W64_TW - 1) * S + TAPS + d0 + 1) >> 1;
+    // generic ratio: per-column first tap, 1/weight_sum and weights (columns 2*lane and 2*lane+1)
+    const int oc0 = min(ox0 + 2 * lane, J.dst_w - 1), oc1 = min(ox0 + 2 * lane + 1, J.dst_w - 1);
+    int gi0 = 0, gD = 0, npairs_g = 0;
+    float inv0, inv1;
+    if constexpr (S == 0) {
+        const int f0 = __ldg(J.first_h + oc0), f1 = __ldg(J.first_h + oc1);
+        gi0 = f0 - xa_e; gD = f1 - f0;
+        inv0 = __ldg(J.inv_h + oc0); inv1 = __ldg(J.inv_h + oc1);
+        const int o_last = min(ox0 + W64_TW - 1, J.dst_w - 1);
+        npairs_g = (min(__ldg(J.first_h + o_last) + th - xa_e, K::SPAN) + 1) >> 1;
+        for (int t = warp; t < th; t += W64_WARPS) {
+            M.hw[(2 * lane) * TAPS + t] = __ldg(J.w_h + (size_t)oc0 * th + t);
+            M.hw[(2 * lane + 1) * TAPS + t] = __ldg(J.w_h + (size_t)oc1 * th + t);
+        }
+        __syncthreads();
+    } else {
+        inv0 = inv1 = c_winv[S];
+    }
+    const int npairs = S == 0 ? npairs_g : (((W64_TW - 1) * S + TAPS + d0 + 1) >> 1);
     const int full_range = src.full_range;
     // pairs whose pixels and chroma taps need no clamping: x = xa_e + 2p >= 2 and x + 3 <= W - 1
     const int p_in_lo = xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1, p_in_hi = (W - 4 - xa_e) >> 1;
@@ -659,19 +575,35 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
             __syncwarp();
             // A2: horizontal Lanczos, each lane 2 adjacent output columns, weights from the constant bank
             {
-                const int i0 = 2 * S * lane + d0;
                 __half2 *ringrow = &M.ring[r & (W64_RING - 1)][0][0];
+                if constexpr (S == 0) {
+                    const float *w0 = &M.hw[(2 * lane) * TAPS], *w1 = &M.hw[(2 * lane + 1) * TAPS];
+                    const int win = th + gD;  // union of the two columns' windows (first is non-decreasing)
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    const float *sp = M.srow[warp][ch];
-                    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < WIN; j++) {
-                        const float v = sp[K::pos(i0 + j)];
-                        if (j < TAPS) a0 = fmaf(v, c_wint[S][j], a0);
-                        if (j >= S) a1 = fmaf(v, c_wint[S][j - S], a1);
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float *sp = M.srow[warp][ch];
+                        float a0 = 0.f, a1 = 0.f;
+                        for (int j = 0; j < win; j++) {
+                            const float v = sp[K::pos(gi0 + j)];
+                            if (j < th) a0 = fmaf(v, w0[j], a0);
+                            if (j >= gD) a1 = fmaf(v, w1[j - gD], a1);
+                        }
+                        ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv0, a1 * inv1);  // NC-5
                     }
-                    ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv_h, a1 * inv_h);  // NC-5
+                } else {
+                    const int i0 = 2 * S * lane + d0;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float *sp = M.srow[warp][ch];
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < WIN; j++) {
+                            const float v = sp[K::pos(i0 + j)];
+                            if (j < TAPS) a0 = fmaf(v, c_wint[S][j], a0);
+                            if (j >= S) a1 = fmaf(v, c_wint[S][j - S], a1);
+                        }
+                        ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv0, a1 * inv1);  // NC-5
+                    }
                 }
             }
             __syncwarp();
@@ -729,15 +661,10 @@ static bool launch_fused_int(const FusedJob *jobs_dev, dim3 g, cudaStream_t s) {
 
 int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n, Stream s) {
     if (n <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_resample_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
-        attr_set = true;
-    }
     int mx = 1, my = 1, mx64 = 1;
     bool have[5][2] = {};
     for (int i = 0; i < n; i++) {
-        int sx = (jobs_host[i].dst_w + FS_TW - 1) / FS_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
+        int sx = (jobs_host[i].dst_w + W64_TW - 1) / W64_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
         int sx64 = (jobs_host[i].dst_w + W64_TW - 1) / W64_TW;
         mx = sx > mx ? sx : mx;
         mx64 = sx64 > mx64 ? sx64 : mx64;
@@ -749,11 +676,8 @@ int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, i
     cudaStream_t st = (cudaStream_t)s;
     int launches = 0;
     // one launch per kernel variant present in the tick; blocks of jobs of another variant exit at once
-    if (have[0][0] || have[0][1]) {
-        k_resample_fused<<<g, dim3(FS_TW, FS_WARPS), sizeof(FusedSmem), st>>>(jobs_dev);
-        if (!check_launch("k_resample_fused")) return -1;
-        launches++;
-    }
+    if (have[0][0]) { if (!launch_fused_int<0, false>(jobs_dev, g64, st)) return -1; launches++; }
+    if (have[0][1]) { if (!launch_fused_int<0, true>(jobs_dev, g64, st)) return -1; launches++; }
 #define SMR_LAUNCH_INT(SV)                                                                   \
     if (have[SV][0]) { if (!launch_fused_int<SV, false>(jobs_dev, g64, st)) return -1; launches++; } \
     if (have[SV][1]) { if (!launch_fused_int<SV, true>(jobs_dev, g64, st)) return -1; launches++; }

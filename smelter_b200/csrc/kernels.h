@@ -104,7 +104,7 @@ struct FusedJob {
     int32_t variant;        // 0: generic kernel; 2,3,4: integer horizontal ratio (k_resample_fused_int<S>)
 };
 // limits the host checks before choosing the fused kernel (mirrors FS_* in kernels.cu)
-constexpr int kFusedStripCols = 32, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 160, kFusedMaxTaps = 32;
+constexpr int kFusedStripCols = 64, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 280, kFusedMaxTaps = 25;
 
 struct WeightJob {          // resample.wgsl:42-86 evaluated once per output coordinate
     float scale, offset;
