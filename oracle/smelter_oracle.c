@@ -12,6 +12,7 @@
  *   NC-3 sRGB8 fetch       f32( eotf_f64(v/255) )  (exact 256-entry table)
  *   NC-4 sRGB8 store       number of k in 0..254 with x >= f32(eotf_f64((k+.5)/255))  (ideal encode + RN)
  *   NC-5 Rgba16Float store round-to-nearest-even f32 -> f16
+ *   NC-6u UNORM8 views     linear filter in exact integer arithmetic on the 8-bit texels, rounded once (see filter_u8)
  *   NC-6 linear sampler    texel coord c = t*dim-.5 (f32); weights quantised to 8 fractional bits
  *                          (what llvmpipe's AoS path and NVIDIA's texture units both do); taps clamped;
  *                          h0=fma(t10,fx,t00*(1-fx)) h1=fma(t11,fx,t01*(1-fx)) v=fma(h1,fy,h0*(1-fy))
@@ -135,13 +136,24 @@ static inline float bilerp(float t00, float t10, float t01, float t11, float fx,
     return fmaf(h1, fy, h0 * (1.0f - fy));
 }
 
+/* NC-6u: linear filtering of a UNORM8 (non-sRGB) view is carried out on the 8-bit texel integers with the
+ * 8-bit weights in EXACT arithmetic and rounded once: value = f32( N / (255 * 65536) ),
+ * N = (t00*(256-wx) + t10*wx)*(256-wy) + (t01*(256-wx) + t11*wx)*wy.  This is the infinitely precise result
+ * of the fixed-point filter of a texture unit, independent of any float operation order; a texel hit gives
+ * exactly v/255 (NC-1). */
+static inline float filter_u8(int t00, int t10, int t01, int t11, float fx, float fy) {
+    int wx = (int)(fx * 256.0f), wy = (int)(fy * 256.0f); /* fx, fy are multiples of 1/256 */
+    int n = (t00 * (256 - wx) + t10 * wx) * (256 - wy) + (t01 * (256 - wx) + t11 * wx) * wy;
+    return (float)n / 16711680.0f;
+}
+
 /* bilinear fetch of one 8-bit channel, UNORM view */
 static inline float sample_u8_plane(const uint8_t *p, int w, int h, int pitch_px, int stride,
                                     int ch, float tx, float ty) {
     lin_tap ax = linear_tap(tx, w), ay = linear_tap(ty, h);
     const uint8_t *r0 = p + (size_t)ay.i0 * pitch_px * stride, *r1 = p + (size_t)ay.i1 * pitch_px * stride;
-    return bilerp(g_u8n[r0[ax.i0 * stride + ch]], g_u8n[r0[ax.i1 * stride + ch]],
-                  g_u8n[r1[ax.i0 * stride + ch]], g_u8n[r1[ax.i1 * stride + ch]], ax.f, ay.f);
+    return filter_u8(r0[ax.i0 * stride + ch], r0[ax.i1 * stride + ch], r1[ax.i0 * stride + ch],
+                     r1[ax.i1 * stride + ch], ax.f, ay.f);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -603,9 +615,12 @@ static inline void sample_node(const orc_texture *t, int mode, float tx, float t
     lin_tap ax = linear_tap(tx, w), ay = linear_tap(ty, h);
     const uint8_t *p00 = d + ((size_t)ay.i0 * w + ax.i0) * 4, *p10 = d + ((size_t)ay.i0 * w + ax.i1) * 4;
     const uint8_t *p01 = d + ((size_t)ay.i1 * w + ax.i0) * 4, *p11 = d + ((size_t)ay.i1 * w + ax.i1) * 4;
-    const float *lut = mode == ORC_MODE_GPU_OPTIMIZED ? g_dec : g_u8n;
-    for (int c = 0; c < 3; c++) out[c] = bilerp(lut[p00[c]], lut[p10[c]], lut[p01[c]], lut[p11[c]], ax.f, ay.f);
-    out[3] = bilerp(g_u8n[p00[3]], g_u8n[p10[3]], g_u8n[p01[3]], g_u8n[p11[3]], ax.f, ay.f);
+    if (mode == ORC_MODE_GPU_OPTIMIZED) { /* srgb view: texels are decoded to float, then filtered (NC-6) */
+        for (int c = 0; c < 3; c++) out[c] = bilerp(g_dec[p00[c]], g_dec[p10[c]], g_dec[p01[c]], g_dec[p11[c]], ax.f, ay.f);
+        out[3] = bilerp(g_u8n[p00[3]], g_u8n[p10[3]], g_u8n[p01[3]], g_u8n[p11[3]], ax.f, ay.f);
+    } else { /* plain Rgba8Unorm node texture: NC-6u on all four channels */
+        for (int c = 0; c < 4; c++) out[c] = filter_u8(p00[c], p10[c], p01[c], p11[c], ax.f, ay.f);
+    }
 }
 
 /* PREMULTIPLIED_ALPHA_BLENDING through the node texture's view (common_pipeline.rs:125) */

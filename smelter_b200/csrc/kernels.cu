@@ -108,16 +108,25 @@ __device__ __forceinline__ float bilerp(float t00, float t10, float t01, float t
     return fmaf(h1, fy, h0 * (1.0f - fy));
 }
 
+// NC-6u: UNORM8 (non-sRGB) views are filtered in exact integer arithmetic on the 8-bit texels and rounded once:
+// value = f32(N / (255*65536)).  f32(n/255) is evaluated division-free and EXACTLY as fma(n, c, n*lo) with
+// c = f32(1/255), lo = f32(1/255 - c) (checked for every n <= 255*65536); powers of two scale exactly.
+__device__ __forceinline__ float div255(float nf, float pow2) {
+    const float c = __uint_as_float(0x3b808081u) * pow2, lo = __uint_as_float(0xaf7efeffu) * pow2;  // folded at compile time
+    return fmaf(nf, c, nf * lo);
+}
+__device__ __forceinline__ float filter_u8(int t00, int t10, int t01, int t11, float fx, float fy) {
+    const int wx = (int)(fx * 256.0f), wy = (int)(fy * 256.0f);
+    const int n = (t00 * (256 - wx) + t10 * wx) * (256 - wy) + (t01 * (256 - wx) + t11 * wx) * wy;
+    return div255((float)n, 1.0f / 65536.0f);
+}
+
 __device__ __forceinline__ float sample_plane(const Tables &T, const uint8_t *p, int pitch, int stride, int ch,
                                               const LinTap &ax, const LinTap &ay) {
     const uint8_t *r0 = p + (size_t)ay.i0 * pitch, *r1 = p + (size_t)ay.i1 * pitch;
-    // a zero weight multiplies a finite texel: skipping the tap is exact
-    float t00 = T.u8n[__ldg(r0 + ax.i0 * stride + ch)];
-    float t10 = ax.f != 0.0f ? T.u8n[__ldg(r0 + ax.i1 * stride + ch)] : t00;
-    if (ay.f == 0.0f) return fmaf(t10, ax.f, t00 * (1.0f - ax.f));
-    float t01 = T.u8n[__ldg(r1 + ax.i0 * stride + ch)];
-    float t11 = ax.f != 0.0f ? T.u8n[__ldg(r1 + ax.i1 * stride + ch)] : t01;
-    return bilerp(t00, t10, t01, t11, ax.f, ay.f);
+    const int t00 = __ldg(r0 + ax.i0 * stride + ch), t10 = __ldg(r0 + ax.i1 * stride + ch);
+    const int t01 = __ldg(r1 + ax.i0 * stride + ch), t11 = __ldg(r1 + ax.i1 * stride + ch);
+    return filter_u8(t00, t10, t01, t11, ax.f, ay.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -174,21 +183,24 @@ __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int 
                 // (proved for every even size <= 8192 by oracle test test_even_size_sampler_phases_exhaustive).
                 int x0 = (x & 1) ? (x >> 1) : max((x >> 1) - 1, 0), x1 = (x & 1) ? min((x >> 1) + 1, cw - 1) : (x >> 1);
                 int y0 = (y & 1) ? (y >> 1) : max((y >> 1) - 1, 0), y1 = (y & 1) ? min((y >> 1) + 1, ch - 1) : (y >> 1);
-                float fx = (x & 1) ? 0.25f : 0.75f, fy = (y & 1) ? 0.25f : 0.75f;
+                const int kx = (x & 1) ? 1 : 3, ky = (y & 1) ? 1 : 3;   // weight of the second tap, in quarters
                 float yy = T.u8n[__ldg(s.p0 + (size_t)y * s.pitch0 + x)];
-                float uu, vv;
+                int nu, nv;   // 16 x the interpolated chroma byte value (NC-6u with the .25/.75 taps)
                 if (s.kind == TEX_YUV420) {
                     const uint8_t *u0 = s.p1 + (size_t)y0 * s.pitch1, *u1 = s.p1 + (size_t)y1 * s.pitch1;
                     const uint8_t *v0 = s.p2 + (size_t)y0 * s.pitch2, *v1 = s.p2 + (size_t)y1 * s.pitch2;
-                    uu = bilerp(T.u8n[__ldg(u0 + x0)], T.u8n[__ldg(u0 + x1)], T.u8n[__ldg(u1 + x0)], T.u8n[__ldg(u1 + x1)], fx, fy);
-                    vv = bilerp(T.u8n[__ldg(v0 + x0)], T.u8n[__ldg(v0 + x1)], T.u8n[__ldg(v1 + x0)], T.u8n[__ldg(v1 + x1)], fx, fy);
+                    nu = ((int)__ldg(u0 + x0) * (4 - kx) + (int)__ldg(u0 + x1) * kx) * (4 - ky) +
+                         ((int)__ldg(u1 + x0) * (4 - kx) + (int)__ldg(u1 + x1) * kx) * ky;
+                    nv = ((int)__ldg(v0 + x0) * (4 - kx) + (int)__ldg(v0 + x1) * kx) * (4 - ky) +
+                         ((int)__ldg(v1 + x0) * (4 - kx) + (int)__ldg(v1 + x1) * kx) * ky;
                 } else {
                     const uchar2 *r0 = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)y0 * s.pitch1);
                     const uchar2 *r1 = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)y1 * s.pitch1);
                     uchar2 a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
-                    uu = bilerp(T.u8n[a.x], T.u8n[b.x], T.u8n[c.x], T.u8n[d.x], fx, fy);
-                    vv = bilerp(T.u8n[a.y], T.u8n[b.y], T.u8n[c.y], T.u8n[d.y], fx, fy);
+                    nu = ((int)a.x * (4 - kx) + (int)b.x * kx) * (4 - ky) + ((int)c.x * (4 - kx) + (int)d.x * kx) * ky;
+                    nv = ((int)a.y * (4 - kx) + (int)b.y * kx) * (4 - ky) + ((int)c.y * (4 - kx) + (int)d.y * kx) * ky;
                 }
+                const float uu = div255((float)nu, 0.0625f), vv = div255((float)nv, 0.0625f);
                 return yuv_to_rgba8(yy, uu, vv, s.full_range);
             }
             float tx = ((float)x + 0.5f) / (float)s.width, ty = ((float)y + 0.5f) / (float)s.height;
@@ -220,30 +232,30 @@ __device__ __forceinline__ bool yuv_quad_ok(const Tex &s, int x, int y) {
 __device__ __forceinline__ void yuv_quad(const Tables &T, const Tex &s, int x, int y, uchar4 &p00, uchar4 &p10,
                                          uchar4 &p01, uchar4 &p11) {
     const int cx = x >> 1, cy = y >> 1;
-    float hue[3], huo[3], hve[3], hvo[3];
+    // u in bits 0..15, v in bits 16..31: both channels share every integer multiply-add (max 4080 < 65536)
+    unsigned he[3], ho[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        float ua, ub, ud, va, vb, vd;
+        unsigned a, b, d;
         if (s.kind == TEX_NV12) {
             const uchar2 *rp = reinterpret_cast<const uchar2 *>(s.p1 + (size_t)(cy - 1 + i) * s.pitch1) + cx;
-            const uchar2 a = __ldg(rp - 1), b = __ldg(rp), d = __ldg(rp + 1);
-            ua = T.u8n[a.x]; ub = T.u8n[b.x]; ud = T.u8n[d.x];
-            va = T.u8n[a.y]; vb = T.u8n[b.y]; vd = T.u8n[d.y];
+            const uchar2 ta = __ldg(rp - 1), tb = __ldg(rp), td = __ldg(rp + 1);
+            a = ta.x | (ta.y << 16); b = tb.x | (tb.y << 16); d = td.x | (td.y << 16);
         } else {
             const uint8_t *ru = s.p1 + (size_t)(cy - 1 + i) * s.pitch1 + cx, *rv = s.p2 + (size_t)(cy - 1 + i) * s.pitch2 + cx;
-            ua = T.u8n[__ldg(ru - 1)]; ub = T.u8n[__ldg(ru)]; ud = T.u8n[__ldg(ru + 1)];
-            va = T.u8n[__ldg(rv - 1)]; vb = T.u8n[__ldg(rv)]; vd = T.u8n[__ldg(rv + 1)];
+            a = __ldg(ru - 1) | (__ldg(rv - 1) << 16); b = __ldg(ru) | (__ldg(rv) << 16); d = __ldg(ru + 1) | (__ldg(rv + 1) << 16);
         }
-        hue[i] = fmaf(ub, 0.75f, ua * 0.25f); huo[i] = fmaf(ud, 0.25f, ub * 0.75f);
-        hve[i] = fmaf(vb, 0.75f, va * 0.25f); hvo[i] = fmaf(vd, 0.25f, vb * 0.75f);
+        he[i] = a + 3u * b;   // even pixel: taps (cx-1, cx), weights (1/4, 3/4)
+        ho[i] = 3u * b + d;   // odd pixel:  taps (cx, cx+1), weights (3/4, 1/4)
     }
     const uchar2 y0 = __ldg(reinterpret_cast<const uchar2 *>(s.p0 + (size_t)y * s.pitch0 + x));
     const uchar2 y1 = __ldg(reinterpret_cast<const uchar2 *>(s.p0 + (size_t)(y + 1) * s.pitch0 + x));
-    // even row: chroma rows (cy-1, cy), fy = .75 ; odd row: (cy, cy+1), fy = .25
-    p00 = yuv_to_rgba8(T.u8n[y0.x], fmaf(hue[1], 0.75f, hue[0] * 0.25f), fmaf(hve[1], 0.75f, hve[0] * 0.25f), s.full_range);
-    p10 = yuv_to_rgba8(T.u8n[y0.y], fmaf(huo[1], 0.75f, huo[0] * 0.25f), fmaf(hvo[1], 0.75f, hvo[0] * 0.25f), s.full_range);
-    p01 = yuv_to_rgba8(T.u8n[y1.x], fmaf(hue[2], 0.25f, hue[1] * 0.75f), fmaf(hve[2], 0.25f, hve[1] * 0.75f), s.full_range);
-    p11 = yuv_to_rgba8(T.u8n[y1.y], fmaf(huo[2], 0.25f, huo[1] * 0.75f), fmaf(hvo[2], 0.25f, hvo[1] * 0.75f), s.full_range);
+    // even row: chroma rows (cy-1, cy) weights (1/4, 3/4) ; odd row: (cy, cy+1) weights (3/4, 1/4)
+    const unsigned n00 = he[0] + 3u * he[1], n10 = ho[0] + 3u * ho[1], n01 = 3u * he[1] + he[2], n11 = 3u * ho[1] + ho[2];
+    p00 = yuv_to_rgba8(T.u8n[y0.x], div255((float)(n00 & 0xffffu), 0.0625f), div255((float)(n00 >> 16), 0.0625f), s.full_range);
+    p10 = yuv_to_rgba8(T.u8n[y0.y], div255((float)(n10 & 0xffffu), 0.0625f), div255((float)(n10 >> 16), 0.0625f), s.full_range);
+    p01 = yuv_to_rgba8(T.u8n[y1.x], div255((float)(n01 & 0xffffu), 0.0625f), div255((float)(n01 >> 16), 0.0625f), s.full_range);
+    p11 = yuv_to_rgba8(T.u8n[y1.y], div255((float)(n11 & 0xffffu), 0.0625f), div255((float)(n11 >> 16), 0.0625f), s.full_range);
 }
 
 __global__ void __launch_bounds__(256) k_convert(Tex src, uint8_t *dst, int dst_pitch) {
@@ -521,7 +533,6 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
             {
                 const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
                 const int cy0 = (r & 1) ? (r >> 1) : max((r >> 1) - 1, 0), cy1 = (r & 1) ? min((r >> 1) + 1, chei - 1) : (r >> 1);
-                const float fy = (r & 1) ? 0.25f : 0.75f, ify = (r & 1) ? 0.75f : 0.25f;
                 const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
                 const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
                 const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
@@ -548,15 +559,16 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                     Raw nxt;
                     if (p + 32 < npairs && interior(p + 32)) load_raw(p + 32, nxt);
                     if (interior(p)) {
-                        const float ua0 = M.T.u8n[cur.a0.x], ub0 = M.T.u8n[cur.b0.x], ud0 = M.T.u8n[cur.d0.x];
-                        const float ua1 = M.T.u8n[cur.a1.x], ub1 = M.T.u8n[cur.b1.x], ud1 = M.T.u8n[cur.d1.x];
-                        const float va0 = M.T.u8n[cur.a0.y], vb0 = M.T.u8n[cur.b0.y], vd0 = M.T.u8n[cur.d0.y];
-                        const float va1 = M.T.u8n[cur.a1.y], vb1 = M.T.u8n[cur.b1.y], vd1 = M.T.u8n[cur.d1.y];
-                        // even pixel: taps (cx-1, cx) fx=.75 ; odd pixel: taps (cx, cx+1) fx=.25   (bilerp of NC-6)
-                        const float ue = fmaf(fmaf(ub1, 0.75f, ua1 * 0.25f), fy, fmaf(ub0, 0.75f, ua0 * 0.25f) * ify);
-                        const float uo = fmaf(fmaf(ud1, 0.25f, ub1 * 0.75f), fy, fmaf(ud0, 0.25f, ub0 * 0.75f) * ify);
-                        const float ve = fmaf(fmaf(vb1, 0.75f, va1 * 0.25f), fy, fmaf(vb0, 0.75f, va0 * 0.25f) * ify);
-                        const float vo = fmaf(fmaf(vd1, 0.25f, vb1 * 0.75f), fy, fmaf(vd0, 0.25f, vb0 * 0.75f) * ify);
+                        // NC-6u chroma: u in bits 0..15, v in bits 16..31 of one register (max 4080 < 65536)
+                        const unsigned a0 = cur.a0.x | (cur.a0.y << 16), b0 = cur.b0.x | (cur.b0.y << 16), d0c = cur.d0.x | (cur.d0.y << 16);
+                        const unsigned a1 = cur.a1.x | (cur.a1.y << 16), b1 = cur.b1.x | (cur.b1.y << 16), d1c = cur.d1.x | (cur.d1.y << 16);
+                        // even pixel: taps (cx-1, cx) weights (1/4, 3/4); odd pixel: taps (cx, cx+1) weights (3/4, 1/4)
+                        const unsigned he0 = a0 + 3u * b0, ho0 = 3u * b0 + d0c, he1 = a1 + 3u * b1, ho1 = 3u * b1 + d1c;
+                        // row weights: even row (1/4, 3/4) on chroma rows (cy0, cy1); odd row (3/4, 1/4)
+                        const unsigned ne = (r & 1) ? 3u * he0 + he1 : he0 + 3u * he1;
+                        const unsigned no = (r & 1) ? 3u * ho0 + ho1 : ho0 + 3u * ho1;
+                        const float ue = div255((float)(ne & 0xffffu), 0.0625f), ve = div255((float)(ne >> 16), 0.0625f);
+                        const float uo = div255((float)(no & 0xffffu), 0.0625f), vo = div255((float)(no >> 16), 0.0625f);
                         int r8, g8, b8;
                         yuv_to_rgb8i(M.T.u8n[cur.y.x], ue, ve, full_range, r8, g8, b8);
                         sr[q] = M.T.dec[r8]; sg[q] = M.T.dec[g8]; sb[q] = M.T.dec[b8];
@@ -748,6 +760,13 @@ __device__ __forceinline__ float4 sample_node(const Tables &T, const Tex *tex, i
         p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
     }
     float4 r;
+    if (mode != 0) {   // CpuOptimized: plain Rgba8Unorm node textures -> NC-6u on all four channels
+        r.x = filter_u8(p00.x, p10.x, p01.x, p11.x, ax.f, ay.f);
+        r.y = filter_u8(p00.y, p10.y, p01.y, p11.y, ax.f, ay.f);
+        r.z = filter_u8(p00.z, p10.z, p01.z, p11.z, ax.f, ay.f);
+        r.w = filter_u8(p00.w, p10.w, p01.w, p11.w, ax.f, ay.f);
+        return r;
+    }
     r.x = bilerp(lut[p00.x], lut[p10.x], lut[p01.x], lut[p11.x], ax.f, ay.f);
     r.y = bilerp(lut[p00.y], lut[p10.y], lut[p01.y], lut[p11.y], ax.f, ay.f);
     r.z = bilerp(lut[p00.z], lut[p10.z], lut[p01.z], lut[p11.z], ax.f, ay.f);
@@ -1119,9 +1138,10 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         const uchar4 a = px[0][2 * c], b = px[0][2 * c + 1], d = px[1][2 * c], e = px[1][2 * c + 1];
-        float r = bilerp(T.u8n[a.x], T.u8n[b.x], T.u8n[d.x], T.u8n[e.x], 0.5f, 0.5f);
-        float g = bilerp(T.u8n[a.y], T.u8n[b.y], T.u8n[d.y], T.u8n[e.y], 0.5f, 0.5f);
-        float bb = bilerp(T.u8n[a.z], T.u8n[b.z], T.u8n[d.z], T.u8n[e.z], 0.5f, 0.5f);
+        // NC-6u with the .5/.5 taps of an even-sized target: the exact mean of the four raw bytes
+        float r = div255((float)((int)a.x + b.x + d.x + e.x), 0.25f);
+        float g = div255((float)((int)a.y + b.y + d.y + e.y), 0.25f);
+        float bb = div255((float)((int)a.z + b.z + d.z + e.z), 0.25f);
         uo[c] = (unsigned char)unorm8(to_u(r, g, bb));
         vo[c] = (unsigned char)unorm8(to_v(r, g, bb));
     }
@@ -1170,9 +1190,9 @@ __device__ __forceinline__ void sample_raw_rgb(const Tables &T, const Tex &S, fl
     uchar4 p10 = ax.f != 0.0f ? node_texel(T, S, ax.i1, ay.i0) : p00;
     uchar4 p01 = ay.f != 0.0f ? node_texel(T, S, ax.i0, ay.i1) : p00;
     uchar4 p11 = (ax.f != 0.0f && ay.f != 0.0f) ? node_texel(T, S, ax.i1, ay.i1) : (ax.f != 0.0f ? p10 : p01);
-    r = bilerp(T.u8n[p00.x], T.u8n[p10.x], T.u8n[p01.x], T.u8n[p11.x], ax.f, ay.f);
-    g = bilerp(T.u8n[p00.y], T.u8n[p10.y], T.u8n[p01.y], T.u8n[p11.y], ax.f, ay.f);
-    b = bilerp(T.u8n[p00.z], T.u8n[p10.z], T.u8n[p01.z], T.u8n[p11.z], ax.f, ay.f);
+    r = filter_u8(p00.x, p10.x, p01.x, p11.x, ax.f, ay.f);   // raw bytes through the Rgba8Unorm view: NC-6u
+    g = filter_u8(p00.y, p10.y, p01.y, p11.y, ax.f, ay.f);
+    b = filter_u8(p00.z, p10.z, p01.z, p11.z, ax.f, ay.f);
 }
 
 __global__ void __launch_bounds__(256) k_output(OutputJob J) {
