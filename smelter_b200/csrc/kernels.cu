@@ -30,6 +30,7 @@ namespace dev {
 __constant__ float c_u8n[256];
 __constant__ float c_dec[256];
 __constant__ float c_thr[256];  // 255 used
+__constant__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
 
 static char g_err[256] = {0};
 const char *last_launch_error() { return g_err; }
@@ -49,12 +50,20 @@ void upload_tables(const float *u8n, const float *dec, const float *thr) {
     cudaMemcpyToSymbol(c_u8n, u8n, sizeof(float) * 256);
     cudaMemcpyToSymbol(c_dec, dec, sizeof(float) * 256);
     cudaMemcpyToSymbol(c_thr, t, sizeof(float) * 256);
+    float yl[256];  // same two f32 operations as yuv_to_rgba8's limited-range branch (no contraction possible)
+    for (int i = 0; i < 256; i++) {
+        volatile float d = u8n[i] - (16.0f / 255.0f);
+        volatile float m = d * (1.0f / 0.85882352941f);
+        yl[i] = m < 0.0f ? 0.0f : (m > 1.0f ? 1.0f : m);
+    }
+    cudaMemcpyToSymbol(c_yl, yl, sizeof(float) * 256);
 }
 
 struct Tables {  // per-block shared-memory copies (divergent indices would serialise in constant memory)
     float u8n[256];
     float dec[256];
     float thr[256];
+    float yl[256];
 };
 
 __device__ __forceinline__ void load_tables(Tables &t) {
@@ -62,6 +71,7 @@ __device__ __forceinline__ void load_tables(Tables &t) {
         t.u8n[i] = c_u8n[i];
         t.dec[i] = c_dec[i];
         t.thr[i] = c_thr[i];
+        t.yl[i] = c_yl[i];
     }
     __syncthreads();
 }
@@ -161,6 +171,18 @@ __device__ __forceinline__ void yuv_to_rgb8i(float y, float u, float v, int full
     r8 = unorm8(fmaf(1.5748f, vm, y));
     g8 = unorm8(fmaf(-0.4681f, vm, fmaf(-0.1873f, um, y)));
     b8 = unorm8(fmaf(1.8556f, um, y));
+}
+
+// luma already expanded (Tables::yl or Tables::u8n), chroma still raw
+__device__ __forceinline__ void yuv_to_rgb8n(float yn, float u, float v, int full_range, int &r8, int &g8, int &b8) {
+    if (!full_range) {
+        u = clamp01((u - K16) * RCP_C);
+        v = clamp01((v - K16) * RCP_C);
+    }
+    float um = u - 0.5f, vm = v - 0.5f;
+    r8 = unorm8(fmaf(1.5748f, vm, yn));
+    g8 = unorm8(fmaf(-0.4681f, vm, fmaf(-0.1873f, um, yn)));
+    b8 = unorm8(fmaf(1.8556f, um, yn));
 }
 
 __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int x, int y) {
@@ -454,8 +476,7 @@ struct W64 {
     struct Smem {
         Tables T;
         __half2 ring[W64_RING][3][W64_TW / 2];
-        float srow[W64_WARPS][3][ROWLEN];
-        float hw[S == 0 ? W64_TW * TAPS : 1];                          // generic: [column][tap]
+        float4 srow[W64_WARPS][ROWLEN];                                // decoded source row, (r, g, b, -) per pixel
     };
     static __device__ __forceinline__ int pos(int i) { return i + i / (2 * SS); }
 };
@@ -463,21 +484,23 @@ struct W64 {
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int S, bool NV12>
-__global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const FusedJob *jobs) {
+__global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const FusedJob *jobs, const FusedPiece *pieces,
+                                                                            const int *piece_begin) {
     using K = W64<S>;
     constexpr int TAPS = K::TAPS;  // S > 0: exact tap count; S == 0: upper bound (the job's taps_h is used)
     constexpr int WIN = S + TAPS;  // S > 0: window feeding 2 adjacent output columns
     extern __shared__ __align__(16) unsigned char fs_raw[];
     typename K::Smem &M = *reinterpret_cast<typename K::Smem *>(fs_raw);
-    const FusedJob &J = jobs[blockIdx.z];
-    if (J.variant != S || (J.src.kind == TEX_NV12) != NV12) return;
-    const int th = S == 0 ? J.taps_h : TAPS;
-    const int ox0 = blockIdx.x * W64_TW;
-    if (ox0 >= J.dst_w) return;
-    const int oy_begin = blockIdx.y * J.seg_rows, oy_end = min(oy_begin + J.seg_rows, J.dst_h);
-    if (oy_begin >= J.dst_h) return;
     load_tables(M.T);
     const int lane = threadIdx.x, warp = threadIdx.y;
+    // Persistent grid: exactly (SMs x resident blocks) blocks, each owning an EQUAL share of the launch's output
+    // rows as a short list of pieces (job, strip, row range) cut by the host -- no partial last wave.
+    for (int pi = __ldg(piece_begin + blockIdx.x); pi < __ldg(piece_begin + blockIdx.x + 1); pi++) {
+    const FusedPiece P = pieces[pi];
+    const FusedJob &J = jobs[P.job];
+    const int th = S == 0 ? J.taps_h : TAPS;
+    const int ox0 = P.strip * W64_TW;
+    const int oy_begin = P.oy_begin, oy_end = P.oy_end;
     const Tex &src = J.src;
     const int W = src.width, H = src.height, chei = H >> 1;
     const int tv = J.taps_v;
@@ -494,18 +517,19 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
         inv0 = __ldg(J.inv_h + oc0); inv1 = __ldg(J.inv_h + oc1);
         const int o_last = min(ox0 + W64_TW - 1, J.dst_w - 1);
         npairs_g = (min(__ldg(J.first_h + o_last) + th - xa_e, K::SPAN) + 1) >> 1;
-        for (int t = warp; t < th; t += W64_WARPS) {
-            M.hw[(2 * lane) * TAPS + t] = __ldg(J.w_h + (size_t)oc0 * th + t);
-            M.hw[(2 * lane + 1) * TAPS + t] = __ldg(J.w_h + (size_t)oc1 * th + t);
-        }
-        __syncthreads();
     } else {
         inv0 = inv1 = c_winv[S];
     }
-    const int npairs = S == 0 ? npairs_g : (((W64_TW - 1) * S + TAPS + d0 + 1) >> 1);
+    // S > 0: the strip's pair count is a constant (d0 = 1 needs one pair less for S = 3; the extra one is harmless)
+    constexpr int NP = ((W64_TW - 1) * K::SS + TAPS + 2) >> 1, NIT = (NP + 31) / 32;
+    const int npairs = S == 0 ? npairs_g : NP;
     const int full_range = src.full_range;
+    const float *ytab = full_range ? M.T.u8n : M.T.yl;
     // pairs whose pixels and chroma taps need no clamping: x = xa_e + 2p >= 2 and x + 3 <= W - 1
     const int p_in_lo = xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1, p_in_hi = (W - 4 - xa_e) >> 1;
+    const bool strip_inside = S != 0 && p_in_lo == 0 && p_in_hi >= NP - 1;
+    // S > 0: pixel x is stored at slot x - xa so that lane l's window starts at slot 2*S*l (compile-time offsets)
+    const int dsh = S == 0 ? 0 : d0;
 
     int produced_hi = -0x40000000;
     for (int o0 = oy_begin; o0 < oy_end; o0 += W64_WARPS) {
@@ -528,7 +552,7 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
         }
         // ---- phase A: one source row per warp step -----------------------------------------------------
         for (int r = start + warp; r <= need_hi; r += W64_WARPS) {
-            float *sr = M.srow[warp][0], *sg = M.srow[warp][1], *sb = M.srow[warp][2];
+            float4 *row = M.srow[warp];
             // A1: K1/K2 -> u8 -> sRGB decode of the strip's pixels of row r
             {
                 const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
@@ -536,87 +560,103 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                 const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
                 const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
                 const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
-                struct Raw { uchar2 y, a0, b0, d0, a1, b1, d1; };
-                auto interior = [&](int pp) { return pp >= p_in_lo && pp <= p_in_hi; };
+                const bool odd = r & 1;
+                // raw bytes of one pixel pair, each in a full register: luma pair (y0 | y1 << 8) and the three chroma
+                // taps of both chroma rows (NV12: u | v << 8 as loaded; planar: u | v << 16)
+                struct Raw { unsigned y, a0, b0, d0, a1, b1, d1; };
                 auto load_raw = [&](int pp, Raw &R) {
                     const int x = xa_e + 2 * pp, cx = x >> 1;
                     if (NV12) {
-                        const uchar2 *r0 = reinterpret_cast<const uchar2 *>(c0a) + cx, *r1 = reinterpret_cast<const uchar2 *>(c1a) + cx;
+                        const unsigned short *r0 = reinterpret_cast<const unsigned short *>(c0a) + cx;
+                        const unsigned short *r1 = reinterpret_cast<const unsigned short *>(c1a) + cx;
                         R.a0 = __ldg(r0 - 1); R.b0 = __ldg(r0); R.d0 = __ldg(r0 + 1);
                         R.a1 = __ldg(r1 - 1); R.b1 = __ldg(r1); R.d1 = __ldg(r1 + 1);
                     } else {
-                        R.a0 = make_uchar2(__ldg(c0a + cx - 1), __ldg(c0b + cx - 1)); R.b0 = make_uchar2(__ldg(c0a + cx), __ldg(c0b + cx));
-                        R.d0 = make_uchar2(__ldg(c0a + cx + 1), __ldg(c0b + cx + 1));
-                        R.a1 = make_uchar2(__ldg(c1a + cx - 1), __ldg(c1b + cx - 1)); R.b1 = make_uchar2(__ldg(c1a + cx), __ldg(c1b + cx));
-                        R.d1 = make_uchar2(__ldg(c1a + cx + 1), __ldg(c1b + cx + 1));
+                        R.a0 = __ldg(c0a + cx - 1) | ((unsigned)__ldg(c0b + cx - 1) << 16);
+                        R.b0 = __ldg(c0a + cx) | ((unsigned)__ldg(c0b + cx) << 16);
+                        R.d0 = __ldg(c0a + cx + 1) | ((unsigned)__ldg(c0b + cx + 1) << 16);
+                        R.a1 = __ldg(c1a + cx - 1) | ((unsigned)__ldg(c1b + cx - 1) << 16);
+                        R.b1 = __ldg(c1a + cx) | ((unsigned)__ldg(c1b + cx) << 16);
+                        R.d1 = __ldg(c1a + cx + 1) | ((unsigned)__ldg(c1b + cx + 1) << 16);
                     }
-                    R.y = __ldg(reinterpret_cast<const uchar2 *>(yrow + x));
+                    R.y = __ldg(reinterpret_cast<const unsigned short *>(yrow + x));
                 };
-                Raw cur;
-                if (lane < npairs && interior(lane)) load_raw(lane, cur);
-                for (int p = lane; p < npairs; p += 32) {
-                    const int q = K::pos(2 * p);
-                    Raw nxt;
-                    if (p + 32 < npairs && interior(p + 32)) load_raw(p + 32, nxt);
-                    if (interior(p)) {
-                        // NC-6u chroma: u in bits 0..15, v in bits 16..31 of one register (max 4080 < 65536)
-                        const unsigned a0 = cur.a0.x | (cur.a0.y << 16), b0 = cur.b0.x | (cur.b0.y << 16), d0c = cur.d0.x | (cur.d0.y << 16);
-                        const unsigned a1 = cur.a1.x | (cur.a1.y << 16), b1 = cur.b1.x | (cur.b1.y << 16), d1c = cur.d1.x | (cur.d1.y << 16);
-                        // even pixel: taps (cx-1, cx) weights (1/4, 3/4); odd pixel: taps (cx, cx+1) weights (3/4, 1/4)
-                        const unsigned he0 = a0 + 3u * b0, ho0 = 3u * b0 + d0c, he1 = a1 + 3u * b1, ho1 = 3u * b1 + d1c;
-                        // row weights: even row (1/4, 3/4) on chroma rows (cy0, cy1); odd row (3/4, 1/4)
-                        const unsigned ne = (r & 1) ? 3u * he0 + he1 : he0 + 3u * he1;
-                        const unsigned no = (r & 1) ? 3u * ho0 + ho1 : ho0 + 3u * ho1;
-                        const float ue = div255((float)(ne & 0xffffu), 0.0625f), ve = div255((float)(ne >> 16), 0.0625f);
-                        const float uo = div255((float)(no & 0xffffu), 0.0625f), vo = div255((float)(no >> 16), 0.0625f);
-                        int r8, g8, b8;
-                        yuv_to_rgb8i(M.T.u8n[cur.y.x], ue, ve, full_range, r8, g8, b8);
-                        sr[q] = M.T.dec[r8]; sg[q] = M.T.dec[g8]; sb[q] = M.T.dec[b8];
-                        yuv_to_rgb8i(M.T.u8n[cur.y.y], uo, vo, full_range, r8, g8, b8);
-                        sr[q + 1] = M.T.dec[r8]; sg[q + 1] = M.T.dec[g8]; sb[q + 1] = M.T.dec[b8];
-                    } else {  // image border: resample.wgsl clamps the tap index
-                        const int x = xa_e + 2 * p;
-                        const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
-                        const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
-                        sr[q] = M.T.dec[pe.x]; sg[q] = M.T.dec[pe.y]; sb[q] = M.T.dec[pe.z];
-                        sr[q + 1] = M.T.dec[po.x]; sg[q + 1] = M.T.dec[po.y]; sb[q + 1] = M.T.dec[po.z];
+                auto spread = [&](unsigned c) { return NV12 ? __byte_perm(c, 0, 0x4140) : c; };  // -> u | v << 16
+                auto put = [&](int i, int r8, int g8, int b8) {
+                    row[K::pos(i)] = make_float4(M.T.dec[r8], M.T.dec[g8], M.T.dec[b8], 0.0f);
+                };
+                auto convert_store = [&](const Raw &R, int p) {
+                    // NC-6u chroma: u in bits 0..15, v in bits 16..31 of one register (max 4080 < 65536)
+                    const unsigned a0 = spread(R.a0), b0 = 3u * spread(R.b0), e0 = spread(R.d0);
+                    const unsigned a1 = spread(R.a1), b1 = 3u * spread(R.b1), e1 = spread(R.d1);
+                    // even pixel: taps (cx-1, cx) weights (1/4, 3/4); odd pixel: taps (cx, cx+1) weights (3/4, 1/4)
+                    const unsigned he0 = a0 + b0, ho0 = b0 + e0, he1 = a1 + b1, ho1 = b1 + e1;
+                    // row weights: even row (1/4, 3/4) on chroma rows (cy0, cy1); odd row (3/4, 1/4)
+                    const unsigned ne = odd ? 3u * he0 + he1 : he0 + 3u * he1;
+                    const unsigned no = odd ? 3u * ho0 + ho1 : ho0 + 3u * ho1;
+                    const float ue = div255((float)(ne & 0xffffu), 0.0625f), ve = div255((float)(ne >> 16), 0.0625f);
+                    const float uo = div255((float)(no & 0xffffu), 0.0625f), vo = div255((float)(no >> 16), 0.0625f);
+                    const int i = 2 * p - dsh;
+                    int r8, g8, b8;
+                    yuv_to_rgb8n(ytab[R.y & 0xffu], ue, ve, full_range, r8, g8, b8);
+                    if (i >= 0) put(i, r8, g8, b8);
+                    yuv_to_rgb8n(ytab[R.y >> 8], uo, vo, full_range, r8, g8, b8);
+                    put(i + 1, r8, g8, b8);
+                };
+                if (strip_inside) {   // no clamping anywhere in the strip: fully unrolled, next pair's bytes in flight
+                    Raw cur, nxt;
+                    load_raw(lane, cur);
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        const int p = lane + 32 * it;
+                        if (it + 1 < NIT && ((it + 2) * 32 <= NP || p + 32 < NP)) load_raw(p + 32, nxt);
+                        if ((it + 1) * 32 <= NP || p < NP) convert_store(cur, p);
+                        cur = nxt;
                     }
-                    cur = nxt;
+                } else {
+                    auto interior = [&](int pp) { return pp >= p_in_lo && pp <= p_in_hi; };
+                    Raw cur, nxt;
+                    if (lane < npairs && interior(lane)) load_raw(lane, cur);
+                    for (int p = lane; p < npairs; p += 32) {
+                        if (p + 32 < npairs && interior(p + 32)) load_raw(p + 32, nxt);
+                        if (interior(p)) {
+                            convert_store(cur, p);
+                        } else {  // image border: resample.wgsl clamps the tap index
+                            const int x = xa_e + 2 * p, i = 2 * p - dsh;
+                            const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
+                            const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
+                            if (i >= 0) put(i, pe.x, pe.y, pe.z);
+                            put(i + 1, po.x, po.y, po.z);
+                        }
+                        cur = nxt;
+                    }
                 }
             }
             __syncwarp();
-            // A2: horizontal Lanczos, each lane 2 adjacent output columns, weights from the constant bank
+            // A2: horizontal Lanczos, each lane 2 adjacent output columns; one LDS.128 feeds six FMAs
             {
                 __half2 *ringrow = &M.ring[r & (W64_RING - 1)][0][0];
+                float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
                 if constexpr (S == 0) {
-                    const float *w0 = &M.hw[(2 * lane) * TAPS], *w1 = &M.hw[(2 * lane + 1) * TAPS];
+                    const float *w0 = J.w_h + (size_t)oc0 * th, *w1 = J.w_h + (size_t)oc1 * th;  // L1-resident
                     const int win = th + gD;  // union of the two columns' windows (first is non-decreasing)
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float *sp = M.srow[warp][ch];
-                        float a0 = 0.f, a1 = 0.f;
-                        for (int j = 0; j < win; j++) {
-                            const float v = sp[K::pos(gi0 + j)];
-                            if (j < th) a0 = fmaf(v, w0[j], a0);
-                            if (j >= gD) a1 = fmaf(v, w1[j - gD], a1);
-                        }
-                        ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv0, a1 * inv1);  // NC-5
+                    for (int j = 0; j < win; j++) {
+                        const float4 v = row[K::pos(gi0 + j)];
+                        if (j < th) { const float w = __ldg(w0 + j); r0 = fmaf(v.x, w, r0); g0 = fmaf(v.y, w, g0); b0 = fmaf(v.z, w, b0); }
+                        if (j >= gD) { const float w = __ldg(w1 + j - gD); r1 = fmaf(v.x, w, r1); g1 = fmaf(v.y, w, g1); b1 = fmaf(v.z, w, b1); }
                     }
                 } else {
-                    const int i0 = 2 * S * lane + d0;
+                    const float4 *sp = row + (2 * S + 1) * lane;   // pos(2*S*lane + j) = (2*S+1)*lane + pos(j)
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float *sp = M.srow[warp][ch];
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < WIN; j++) {
-                            const float v = sp[K::pos(i0 + j)];
-                            if (j < TAPS) a0 = fmaf(v, c_wint[S][j], a0);
-                            if (j >= S) a1 = fmaf(v, c_wint[S][j - S], a1);
-                        }
-                        ringrow[ch * (W64_TW / 2) + lane] = __floats2half2_rn(a0 * inv0, a1 * inv1);  // NC-5
+                    for (int j = 0; j < WIN; j++) {
+                        const float4 v = sp[K::pos(j)];
+                        if (j < TAPS) { const float w = c_wint[S][j]; r0 = fmaf(v.x, w, r0); g0 = fmaf(v.y, w, g0); b0 = fmaf(v.z, w, b0); }
+                        if (j >= S) { const float w = c_wint[S][j - S]; r1 = fmaf(v.x, w, r1); g1 = fmaf(v.y, w, g1); b1 = fmaf(v.z, w, b1); }
                     }
                 }
+                ringrow[lane] = __floats2half2_rn(r0 * inv0, r1 * inv1);  // NC-5
+                ringrow[W64_TW / 2 + lane] = __floats2half2_rn(g0 * inv0, g1 * inv1);
+                ringrow[W64_TW + lane] = __floats2half2_rn(b0 * inv0, b1 * inv1);
             }
             __syncwarp();
         }
@@ -657,47 +697,38 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
         }
         __syncthreads();
     }
+    }  // pieces
 }
 
 template <int S, bool NV12>
-static bool launch_fused_int(const FusedJob *jobs_dev, dim3 g, cudaStream_t s) {
+static bool launch_fused_int(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks,
+                             cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_resample_fused_int<S, NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(typename W64<S>::Smem));
         attr_set = true;
     }
-    k_resample_fused_int<S, NV12><<<g, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev);
+    k_resample_fused_int<S, NV12><<<nblocks, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev, pieces, piece_begin);
     return check_launch("k_resample_fused_int");
 }
 
-int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n, Stream s) {
-    if (n <= 0) return 0;
-    int mx = 1, my = 1, mx64 = 1;
-    bool have[5][2] = {};
-    for (int i = 0; i < n; i++) {
-        int sx = (jobs_host[i].dst_w + W64_TW - 1) / W64_TW, sy = (jobs_host[i].dst_h + jobs_host[i].seg_rows - 1) / jobs_host[i].seg_rows;
-        int sx64 = (jobs_host[i].dst_w + W64_TW - 1) / W64_TW;
-        mx = sx > mx ? sx : mx;
-        mx64 = sx64 > mx64 ? sx64 : mx64;
-        my = sy > my ? sy : my;
-        int v = jobs_host[i].variant;
-        have[(v >= 2 && v <= 4) ? v : 0][jobs_host[i].src.kind == TEX_NV12 ? 1 : 0] = true;
-    }
-    dim3 g(mx, my, n), g64(mx64, my, n);
+int launch_resample_fused(int variant, bool nv12, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
+                          const int *piece_begin_dev, int nblocks, Stream s) {
+    if (nblocks <= 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
-    int launches = 0;
-    // one launch per kernel variant present in the tick; blocks of jobs of another variant exit at once
-    if (have[0][0]) { if (!launch_fused_int<0, false>(jobs_dev, g64, st)) return -1; launches++; }
-    if (have[0][1]) { if (!launch_fused_int<0, true>(jobs_dev, g64, st)) return -1; launches++; }
-#define SMR_LAUNCH_INT(SV)                                                                   \
-    if (have[SV][0]) { if (!launch_fused_int<SV, false>(jobs_dev, g64, st)) return -1; launches++; } \
-    if (have[SV][1]) { if (!launch_fused_int<SV, true>(jobs_dev, g64, st)) return -1; launches++; }
-    SMR_LAUNCH_INT(2)
-    SMR_LAUNCH_INT(3)
-    SMR_LAUNCH_INT(4)
-#undef SMR_LAUNCH_INT
-    return launches;
+    bool ok = false;
+    switch (variant) {
+        case 2: ok = nv12 ? launch_fused_int<2, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                          : launch_fused_int<2, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 3: ok = nv12 ? launch_fused_int<3, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                          : launch_fused_int<3, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 4: ok = nv12 ? launch_fused_int<4, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                          : launch_fused_int<4, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        default: ok = nv12 ? launch_fused_int<0, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                           : launch_fused_int<0, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+    }
+    return ok ? 1 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,8 +100,12 @@ struct FusedJob {
     const int32_t *first_h;
     const float *w_v, *inv_v;
     const int32_t *first_v;
-    int32_t seg_rows;       // output rows per block (multiple of 8)
-    int32_t variant;        // 0: generic kernel; 2,3,4: integer horizontal ratio (k_resample_fused_int<S>)
+    int32_t variant;        // 0: any ratio (weights from smem); 2,3,4: integer horizontal ratio (constant-bank weights)
+};
+// a contiguous run of output rows of one 64-column strip of one job; each block of the persistent grid gets an
+// equal share of the launch's rows as a short list of pieces (renderer.cpp: partition_fused)
+struct FusedPiece {
+    int32_t job, strip, oy_begin, oy_end;
 };
 // limits the host checks before choosing the fused kernel (mirrors FS_* in kernels.cu)
 constexpr int kFusedStripCols = 64, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 280, kFusedMaxTaps = 25;
@@ -131,7 +135,8 @@ typedef void *Stream;  // cudaStream_t
 int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s);
 int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n_jobs, Stream s);
 int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n_jobs, Stream s);
-int launch_resample_fused(const FusedJob *jobs_dev, const FusedJob *jobs_host, int n_jobs, Stream s);
+int launch_resample_fused(int variant, bool nv12, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
+                          const int *piece_begin_dev, int nblocks, Stream s);
 // integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping
 void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s);
 int launch_composite(const CompositeJob &job, Stream s);

@@ -281,6 +281,7 @@ class Renderer {
     std::deque<int> inflight_;
     int slot_ = 0;
     bool uploaded_ = false;
+    int sm_count_ = 148;
     void drain() {
         if (stream_) cudaStreamSynchronize(stream_);
         if (copy_stream_) cudaStreamSynchronize(copy_stream_);
@@ -344,6 +345,7 @@ smr_status Renderer::init() {
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, opts_.cuda_device));
     for (int i = 0; i < 2; i++) {
         CUDA_OK(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&tick_done_[i], cudaEventDisableTiming));
@@ -536,8 +538,6 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     j.taps_h = wh.taps; j.taps_v = wv.taps;
     j.w_h = wh.weights; j.inv_h = wh.inv; j.first_h = wh.first;
     j.w_v = wv.weights; j.inv_v = wv.inv; j.first_v = wv.first;
-    int seg = ((dh + 3) / 4 + 7) & ~7;
-    j.seg_rows = std::max(seg, 64);
     j.variant = 0;
     if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) {
         j.variant = (int)sh;
@@ -1064,6 +1064,51 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     for (int s = 0; s < 3; s++) stage_off[s] = param_alloc(sizeof(dev::ResampleJob) * std::max<size_t>(stage_jobs_[s].size(), 1));
     wj_off = param_alloc(sizeof(dev::WeightJob) * std::max<size_t>(weight_jobs_.size(), 1));
     size_t fj_off = param_alloc(sizeof(dev::FusedJob) * std::max<size_t>(fused_jobs_.size(), 1));
+    // partition the fused resamples of the tick over a persistent grid, one launch per kernel variant
+    struct FusedLaunch { int variant; bool nv12; size_t pieces_off, begin_off; int nblocks; };
+    std::vector<FusedLaunch> fused_launches;
+    {
+        std::vector<std::pair<int, bool>> variants;
+        for (const dev::FusedJob &j : fused_jobs_) {
+            std::pair<int, bool> v{j.variant, j.src.kind == dev::TEX_NV12};
+            if (std::find(variants.begin(), variants.end(), v) == variants.end()) variants.push_back(v);
+        }
+        for (auto &v : variants) {
+            long long total = 0;
+            for (const dev::FusedJob &j : fused_jobs_)
+                if (j.variant == v.first && (j.src.kind == dev::TEX_NV12) == v.second)
+                    total += (long long)((j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols) * j.dst_h;
+            if (total <= 0) continue;
+            int nblocks = (int)std::min<long long>((long long)sm_count_ * 3, (total + 7) / 8);
+            long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
+            std::vector<dev::FusedPiece> pieces;
+            std::vector<int> begin{0};
+            long long room = per_block;
+            for (size_t ji = 0; ji < fused_jobs_.size(); ji++) {
+                const dev::FusedJob &j = fused_jobs_[ji];
+                if (j.variant != v.first || (j.src.kind == dev::TEX_NV12) != v.second) continue;
+                int strips = (j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols;
+                for (int st = 0; st < strips; st++) {
+                    int y = 0;
+                    while (y < j.dst_h) {
+                        int take = (int)std::min<long long>(room, j.dst_h - y);
+                        pieces.push_back({(int)ji, st, y, y + take});
+                        y += take; room -= take;
+                        if (room == 0) { begin.push_back((int)pieces.size()); room = per_block; }
+                    }
+                }
+            }
+            if (begin.back() != (int)pieces.size()) begin.push_back((int)pieces.size());
+            FusedLaunch fl;
+            fl.variant = v.first; fl.nv12 = v.second; fl.nblocks = (int)begin.size() - 1;
+            fl.pieces_off = param_alloc(sizeof(dev::FusedPiece) * pieces.size());
+            fl.begin_off = param_alloc(sizeof(int) * begin.size());
+            if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
+            memcpy(param_host_.data() + fl.pieces_off, pieces.data(), sizeof(dev::FusedPiece) * pieces.size());
+            memcpy(param_host_.data() + fl.begin_off, begin.data(), sizeof(int) * begin.size());
+            fused_launches.push_back(fl);
+        }
+    }
     if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
     if (!tex_table_.empty()) memcpy(param_host_.data() + tex_off, tex_table_.data(), sizeof(dev::Tex) * tex_table_.size());
     for (int s = 0; s < 3; s++)
@@ -1089,8 +1134,12 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     if (!weight_jobs_.empty()) prof_mark(SMR_KERNEL_WEIGHTS);
     for (auto &pw : pending_int_weights_) dev::set_int_weights(pw.first, pw.second.weights, pw.second.inv, pw.second.taps, stream_);
     pending_int_weights_.clear();
-    if (!launched(dev::launch_resample_fused((const dev::FusedJob *)(pd + fj_off), fused_jobs_.data(), (int)fused_jobs_.size(), stream_))) goto fail;
-    if (!fused_jobs_.empty()) prof_mark(SMR_KERNEL_RESAMPLE_FUSED);
+    for (const FusedLaunch &fl : fused_launches) {
+        if (!launched(dev::launch_resample_fused(fl.variant, fl.nv12, (const dev::FusedJob *)(pd + fj_off),
+                                                 (const dev::FusedPiece *)(pd + fl.pieces_off), (const int *)(pd + fl.begin_off),
+                                                 fl.nblocks, stream_))) goto fail;
+        prof_mark(SMR_KERNEL_RESAMPLE_FUSED);
+    }
     for (int s = 0; s < 3; s++) {
         if (!launched(dev::launch_resample((const dev::ResampleJob *)(pd + stage_off[s]), stage_jobs_[s].data(),
                                            (int)stage_jobs_[s].size(), stream_))) goto fail;
