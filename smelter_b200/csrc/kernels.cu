@@ -25,12 +25,14 @@ namespace smr {
 namespace dev {
 
 // ------------------------------------------------------------------------------------------------
-// tables (NC-1, NC-3, NC-4) -- pushed from the host so host and device agree bit-for-bit
+// tables (NC-1, NC-3, NC-4) -- pushed from the host so host and device agree bit-for-bit.  Plain global
+// memory: every block copies them to shared memory with one coalesced load per warp (a per-thread index into
+// the constant bank would serialise 32 ways).
 // ------------------------------------------------------------------------------------------------
-__constant__ float c_u8n[256];
-__constant__ float c_dec[256];
-__constant__ float c_thr[256];  // 255 used
-__constant__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
+__device__ float c_u8n[256];
+__device__ float c_dec[256];
+__device__ float c_thr[256];  // 255 used
+__device__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
 
 static char g_err[256] = {0};
 const char *last_launch_error() { return g_err; }
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
     const float *ytab = full_range ? M.T.u8n : M.T.yl;
     // pairs whose pixels and chroma taps need no clamping: x = xa_e + 2p >= 2 and x + 3 <= W - 1
     const int p_in_lo = xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1, p_in_hi = (W - 4 - xa_e) >> 1;
-    const bool strip_inside = S != 0 && p_in_lo == 0 && p_in_hi >= NP - 1;
+    const int p_hi = min(p_in_hi, npairs - 1);   // last pair of the strip on the unclamped path
     // S > 0: pixel x is stored at slot x - xa so that lane l's window starts at slot 2*S*l (compile-time offsets)
     const int dsh = S == 0 ? 0 : d0;
 
@@ -603,34 +605,38 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                     yuv_to_rgb8n(ytab[R.y >> 8], uo, vo, full_range, r8, g8, b8);
                     put(i + 1, r8, g8, b8);
                 };
-                if (strip_inside) {   // no clamping anywhere in the strip: fully unrolled, next pair's bytes in flight
-                    Raw cur, nxt;
-                    load_raw(lane, cur);
+                auto inside = [&](int pp) { return pp >= p_in_lo && pp <= p_hi; };
+                auto border = [&](int p) {   // image border: resample.wgsl clamps the tap index
+                    const int x = xa_e + 2 * p, i = 2 * p - dsh;
+                    const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
+                    const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
+                    if (i >= 0) put(i, pe.x, pe.y, pe.z);
+                    put(i + 1, po.x, po.y, po.z);
+                };
+                // unclamped pairs: the next pair's bytes are in flight while this one converts
+                Raw cur, nxt;
+                bool ok = inside(lane);
+                if (ok) load_raw(lane, cur);
+                if constexpr (S != 0) {
 #pragma unroll
                     for (int it = 0; it < NIT; it++) {
                         const int p = lane + 32 * it;
-                        if (it + 1 < NIT && ((it + 2) * 32 <= NP || p + 32 < NP)) load_raw(p + 32, nxt);
-                        if ((it + 1) * 32 <= NP || p < NP) convert_store(cur, p);
-                        cur = nxt;
+                        const bool ok_n = it + 1 < NIT && inside(p + 32);
+                        if (ok_n) load_raw(p + 32, nxt);
+                        if (ok) convert_store(cur, p);
+                        cur = nxt; ok = ok_n;
                     }
                 } else {
-                    auto interior = [&](int pp) { return pp >= p_in_lo && pp <= p_in_hi; };
-                    Raw cur, nxt;
-                    if (lane < npairs && interior(lane)) load_raw(lane, cur);
                     for (int p = lane; p < npairs; p += 32) {
-                        if (p + 32 < npairs && interior(p + 32)) load_raw(p + 32, nxt);
-                        if (interior(p)) {
-                            convert_store(cur, p);
-                        } else {  // image border: resample.wgsl clamps the tap index
-                            const int x = xa_e + 2 * p, i = 2 * p - dsh;
-                            const uchar4 pe = node_texel(M.T, src, min(max(x, 0), W - 1), r);
-                            const uchar4 po = node_texel(M.T, src, min(max(x + 1, 0), W - 1), r);
-                            if (i >= 0) put(i, pe.x, pe.y, pe.z);
-                            put(i + 1, po.x, po.y, po.z);
-                        }
-                        cur = nxt;
+                        const bool ok_n = inside(p + 32);
+                        if (ok_n) load_raw(p + 32, nxt);
+                        if (ok) convert_store(cur, p);
+                        cur = nxt; ok = ok_n;
                     }
                 }
+                if (p_in_lo > 0 || p_hi < npairs - 1)   // strips touching the left / right image edge only
+                    for (int p = lane; p < npairs; p += 32)
+                        if (!inside(p)) border(p);
             }
             __syncwarp();
             // A2: horizontal Lanczos, each lane 2 adjacent output columns; one LDS.128 feeds six FMAs
@@ -1000,6 +1006,7 @@ __device__ __noinline__ uchar4 shade_blend(const Tables &T, const CompositeJob &
 // PARAM: the layer list travels in the kernel parameter block (constant bank): the per-tile culling and the
 // per-pixel loop read it with no global round trip and no shared-memory copy; used whenever it fits.
 #define PARAM_LAYERS 96
+#define MAX_LUT 4          // translucent colour layers of a tile that get a blend table (FAST_LUT)
 struct CompositeParams {
     CompositeJob job;
     LayerDev layers[PARAM_LAYERS];
@@ -1058,6 +1065,24 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     }
     __syncthreads();
 
+    // FAST_LUT layers of this tile: blend() of the layer's constant source over each possible target byte, one
+    // entry per thread (the four channels of blend() are independent, so one call fills all four maps)
+    __shared__ uchar4 s_lut[MAX_LUT][CB_X * CB_Y];
+    static_assert(CB_X * CB_Y == 256, "one table entry per thread");
+    {
+        const int tid = threadIdx.y * CB_X + threadIdx.x;
+        int nl = 0;
+        for (int li = 0; li < s_count && nl < MAX_LUT; li++) {
+            const LayerDev &L = PARAM ? LAYERS[s_list[li]] : (li < SM_LAYERS ? s_layers[li] : LAYERS[s_list[li]]);
+            if (L.fast & FAST_LUT) {
+                s_lut[nl][tid] = blend(T, J.mode, make_uchar4(tid, tid, tid, tid),
+                                       make_float4(L.color[0], L.color[1], L.color[2], L.color[3]));
+                nl++;
+            }
+        }
+        if (nl) __syncthreads();
+    }
+
     for (int it = 0; it < CT_ITERS; it++) {
     const int x0 = tile_x0 + threadIdx.x * CT_W, y0 = tile_y0 + (it * CB_Y + threadIdx.y) * CT_H;
     uchar4 px[CT_H][CT_W];
@@ -1067,16 +1092,30 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
         for (int i = 0; i < CT_W; i++) px[j][i] = make_uchar4(0, 0, 0, 0);  // LoadOp::Clear(TRANSPARENT)
 
     const int n = s_count;
+    int lut_next = 0;
     for (int li = 0; li < n; li++) {
         const LayerDev &L = PARAM ? LAYERS[s_list[li]] : (li < SM_LAYERS ? s_layers[li] : LAYERS[s_list[li]]);
+        const int lut_i = (L.fast & FAST_LUT) ? lut_next++ : MAX_LUT;   // same numbering as the table build above
         if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
-        const bool all_in = x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1;
+        const bool all_in = (x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1) ||
+                            (x0 >= L.jx0 && x0 + CT_W <= L.jx1 && y0 >= L.jy0 && y0 + CT_H <= L.jy1);
         if (all_in && (L.fast & FAST_CONST)) {  // opaque colour interior: the layer leaves constant bytes
             const uchar4 cb = *reinterpret_cast<const uchar4 *>(&L.const_bytes);
 #pragma unroll
             for (int j = 0; j < CT_H; j++)
 #pragma unroll
                 for (int i = 0; i < CT_W; i++) px[j][i] = cb;
+            continue;
+        }
+        if (all_in && lut_i < MAX_LUT) {  // translucent colour interior: four byte lookups per pixel
+            const uchar4 *lut = s_lut[lut_i];
+#pragma unroll
+            for (int j = 0; j < CT_H; j++)
+#pragma unroll
+                for (int i = 0; i < CT_W; i++) {
+                    const uchar4 p = px[j][i];
+                    px[j][i] = make_uchar4(lut[p.x].x, lut[p.y].y, lut[p.z].z, lut[p.w].w);
+                }
             continue;
         }
         if (all_in && (L.fast & FAST_IDENT)) {  // 1:1 texture interior: exact texel per pixel

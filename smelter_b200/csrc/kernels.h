@@ -52,12 +52,14 @@ struct alignas(16) LayerDev {
     int32_t mask_begin, mask_count;
     // host-proved fast region: for pixels in [ix0,ix1)x[iy0,iy1) the rounded-rect / border / mask factors are
     // all exactly 1 (>= 2 px inside every edge and radius), so the fragment is the bare colour or sample
-    int32_t ix0, ix1, iy0, iy1;
+    int32_t ix0, ix1, iy0, iy1;   // the full-height bar: core x range, y up to the straight edges
+    int32_t jx0, jx1, jy0, jy1;   // the full-width bar (the two bars form a plus that leaves out the corner squares)
     int32_t fast;                    // FAST_* bits
     int32_t tx_off, ty_off;          // FAST_IDENT: texel = (px + tx_off, py + ty_off)
     uint32_t const_bytes;            // FAST_CONST: bytes an opaque colour leaves in the target (RGBA little endian)
 };
-enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2 };
+// FAST_LUT: translucent bare colour -- inside the bars the blend is a per-channel function of the target byte
+enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2, FAST_LUT = 4 };
 
 struct CompositeJob {
     int32_t width, height;           // render target (root node texture) size

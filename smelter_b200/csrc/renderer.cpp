@@ -651,29 +651,41 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
     }
     // ---- fast interior (see LayerDev): only where every alpha factor of fs_main is provably exactly 1 ----
     d.ix0 = d.ix1 = d.iy0 = d.iy1 = 0;
+    d.jx0 = d.jx1 = d.jy0 = d.jy1 = 0;
     if (!d.rotated && l.kind != RenderLayout::BoxShadow) {
+        // Every rounded rect k (the layer itself and each mask) has alpha exactly 1 at least e_k inside its
+        // straight edges and outside its four corner squares of side r_k + 2 (rect_alpha_one in kernels.cu).
+        // The intersection of those regions contains two bars: core x range x edge y range, and the transpose.
         const float m = 2.0f;
         float rmax = std::fmax(std::fmax(l.border_radius.top_left, l.border_radius.top_right),
                                std::fmax(l.border_radius.bottom_left, l.border_radius.bottom_right));
-        float shrink = (l.border_width >= 1.0f ? l.border_width + 1.0f : 0.0f) + std::fmax(rmax, 0.0f) + m;
-        float lo_x = l.left + shrink, hi_x = l.left + l.width - shrink;
-        float lo_y = l.top + shrink, hi_y = l.top + l.height - shrink;
+        float edge = m + (l.border_width >= 1.0f ? l.border_width + 1.0f : 0.0f);
+        float core = edge + std::fmax(rmax, 0.0f);
+        float cx0 = l.left + core, cx1 = l.left + l.width - core, cy0 = l.top + core, cy1 = l.top + l.height - core;
+        float ex0 = l.left + edge, ex1 = l.left + l.width - edge, ey0 = l.top + edge, ey1 = l.top + l.height - edge;
         size_t nm = std::min<size_t>(l.masks.size(), SMR_MAX_MASKS);
         for (size_t i = 0; i < nm; i++) {
             const Mask &k = l.masks[i];
             float mr = std::fmax(std::fmax(k.radius.top_left, k.radius.top_right),
                                  std::fmax(k.radius.bottom_left, k.radius.bottom_right));
             float ms = std::fmax(mr, 0.0f) + m;
-            lo_x = std::fmax(lo_x, k.left + ms); hi_x = std::fmin(hi_x, k.left + k.width - ms);
-            lo_y = std::fmax(lo_y, k.top + ms); hi_y = std::fmin(hi_y, k.top + k.height - ms);
+            cx0 = std::fmax(cx0, k.left + ms); cx1 = std::fmin(cx1, k.left + k.width - ms);
+            cy0 = std::fmax(cy0, k.top + ms); cy1 = std::fmin(cy1, k.top + k.height - ms);
+            ex0 = std::fmax(ex0, k.left + m); ex1 = std::fmin(ex1, k.left + k.width - m);
+            ey0 = std::fmax(ey0, k.top + m); ey1 = std::fmin(ey1, k.top + k.height - m);
         }
-        if (lo_x == lo_x && hi_x == hi_x && lo_y == lo_y && hi_y == hi_y && lo_x < hi_x && lo_y < hi_y) {
-            // pixel X is inside iff lo <= X + .5 <= hi
-            d.ix0 = std::max((int)std::ceil(lo_x - 0.5f), d.px0); d.ix1 = std::min((int)std::floor(hi_x - 0.5f) + 1, d.px1);
-            d.iy0 = std::max((int)std::ceil(lo_y - 0.5f), d.py0); d.iy1 = std::min((int)std::floor(hi_y - 0.5f) + 1, d.py1);
-            if (d.ix0 >= d.ix1 || d.iy0 >= d.iy1) d.ix0 = d.ix1 = d.iy0 = d.iy1 = 0;
-        }
-        if (d.ix0 < d.ix1) {
+        // pixel X is inside iff lo <= X + .5 <= hi
+        auto bar = [&](float lx, float hx, float ly, float hy, int32_t &x0, int32_t &x1, int32_t &y0, int32_t &y1) {
+            x0 = x1 = y0 = y1 = 0;
+            if (!(lx == lx && hx == hx && ly == ly && hy == hy && lx < hx && ly < hy)) return;
+            int ax0 = std::max((int)std::ceil(lx - 0.5f), d.px0), ax1 = std::min((int)std::floor(hx - 0.5f) + 1, d.px1);
+            int ay0 = std::max((int)std::ceil(ly - 0.5f), d.py0), ay1 = std::min((int)std::floor(hy - 0.5f) + 1, d.py1);
+            if (ax0 >= ax1 || ay0 >= ay1) return;
+            x0 = ax0; x1 = ax1; y0 = ay0; y1 = ay1;
+        };
+        bar(cx0, cx1, ey0, ey1, d.ix0, d.ix1, d.iy0, d.iy1);
+        bar(ex0, ex1, cy0, cy1, d.jx0, d.jx1, d.jy0, d.jy1);
+        if (d.ix0 < d.ix1 || d.jx0 < d.jx1) {
             if (l.kind == RenderLayout::Color && l.color.a == 255) {
                 // opaque colour: fma(dst, 0, src) == src, so the target bytes are a constant of the layer
                 d.fast |= dev::FAST_CONST;
@@ -682,6 +694,8 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
                     b[c] = opts_.rendering_mode == SMR_MODE_GPU_OPTIMIZED ? srgb_encode_host(d.color[c]) : unorm8_host(d.color[c]);
                 b[3] = 255;
                 memcpy(&d.const_bytes, b, 4);
+            } else if (l.kind == RenderLayout::Color) {
+                d.fast |= dev::FAST_LUT;
             }
             auto integral = [](float v) { return v == std::rint(v) && std::fabs(v) <= 4096.0f; };
             if (l.kind == RenderLayout::ChildNode && tex_index >= 0 && tex_w <= 4096 && tex_h <= 4096 &&

@@ -151,6 +151,20 @@ def test_semi_transparent_overlay_and_zorder():
     check(V(children=kids + [over, over2], background_color=BG), inputs(2))
 
 
+@pytest.mark.parametrize("mode", [s.RenderingMode.GpuOptimized, s.RenderingMode.CpuOptimized])
+def test_stacked_translucent_colour_layers(mode):
+    """six overlapping translucent colour views (more than the per-tile blend tables of k_composite) with and
+    without radius / border over a video: table path, its overflow to the general path, and both blend modes"""
+    kids = [s.RescalerComponent(child=streams(1)[0])]
+    for k in range(6):
+        kids.append(V(position=s.Position.Absolute(width=360.0 - 30 * k, height=200.0 - 12 * k, left=40.0 + 37 * k,
+                                                   top=20.0 + 21 * k),
+                      background_color=s.RGBAColor(40 * k, 255 - 35 * k, 90 + 20 * k, 60 + 30 * k),
+                      border_radius=s.BorderRadius.new_with_radius(0.0 if k % 2 else 18.0 + k),
+                      border_width=3.0 if k == 2 else 0.0, border_color=s.RGBAColor(255, 255, 255, 128)))
+    check(V(children=kids, background_color=BG), inputs(1), mode=mode)
+
+
 @pytest.mark.parametrize("mode_fit", [s.RescaleMode.Fit, s.RescaleMode.Fill])
 def test_rescaler_modes_and_alignment(mode_fit):
     """rescaler.rs fit/fill with alignment, border, radius, shadow"""
