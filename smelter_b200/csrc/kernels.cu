@@ -32,6 +32,9 @@ namespace dev {
 __device__ float c_u8n[256];
 __device__ float c_dec[256];
 __device__ float c_thr[256];  // 255 used
+#define ENC_KEY0 ((127 - 13) << 5)   // srgb_encode buckets: from x = 2^-13 (< thr[0]) ...
+#define ENC_KEYS ((13 << 5) + 1)     // ... up to x = 1.0
+__device__ unsigned char c_enc0[420];
 __device__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
 
 static char g_err[256] = {0};
@@ -59,6 +62,16 @@ void upload_tables(const float *u8n, const float *dec, const float *thr) {
         yl[i] = m < 0.0f ? 0.0f : (m > 1.0f ? 1.0f : m);
     }
     cudaMemcpyToSymbol(c_yl, yl, sizeof(float) * 256);
+    unsigned char enc0[420] = {0};
+    for (int k = 0; k < ENC_KEYS; k++) {
+        const uint32_t bits = (uint32_t)(k + ENC_KEY0) << 18;   // lower edge of the bucket
+        float lo;
+        memcpy(&lo, &bits, 4);
+        int e = 0;
+        while (e < 255 && lo >= t[e]) e++;
+        enc0[k] = (unsigned char)e;
+    }
+    cudaMemcpyToSymbol(c_enc0, enc0, sizeof(enc0));
 }
 
 struct Tables {  // per-block shared-memory copies (divergent indices would serialise in constant memory)
@@ -66,6 +79,7 @@ struct Tables {  // per-block shared-memory copies (divergent indices would seri
     float dec[256];
     float thr[256];
     float yl[256];
+    unsigned char enc0[420];
 };
 
 __device__ __forceinline__ void load_tables(Tables &t) {
@@ -74,6 +88,8 @@ __device__ __forceinline__ void load_tables(Tables &t) {
         t.dec[i] = c_dec[i];
         t.thr[i] = c_thr[i];
         t.yl[i] = c_yl[i];
+        t.enc0[i] = c_enc0[i];
+        if (i + 256 < 420) t.enc0[i + 256] = c_enc0[i + 256];
     }
     __syncthreads();
 }
@@ -82,13 +98,16 @@ __device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }  //
 
 __device__ __forceinline__ int unorm8(float x) { return __float2int_rn(clamp01(x) * 255.0f); }  // NC-2
 
-__device__ __forceinline__ int srgb_encode(const Tables &t, float lin) {  // NC-4
-    float x = clamp01(lin);
-    float g = x <= 0.0031308f ? 12.92f * x : 1.055f * __powf(x, 0.41666666f) - 0.055f;
-    int e = __float2int_rn(g * 255.0f);
-    e = min(max(e, 0), 255);
-    while (e < 255 && x >= t.thr[e]) e++;       // exact: count of thresholds <= x
-    while (e > 0 && x < t.thr[e - 1]) e--;
+// NC-4: the encoded byte is the number of decision thresholds <= x (thr[] ascending, thr[255] is a sentinel).
+// enc0[] holds that count at the lower edge of each bucket of the float's (exponent, top 5 mantissa bits), so the
+// scan from there passes the few thresholds inside the bucket (at most 2: the curve is steepest, 0.8 codes per
+// bucket, just above the linear segment) instead of evaluating pow().
+__device__ __forceinline__ int srgb_encode(const Tables &t, float lin) {
+    const float x = clamp01(lin);                                  // NaN -> 0
+    const int k = (__float_as_int(x) >> 18) - ENC_KEY0;
+    if (k < 0) return 0;
+    int e = t.enc0[k];
+    while (x >= t.thr[e]) e++;
     return e;
 }
 
@@ -480,7 +499,9 @@ struct W64 {
         __half2 ring[W64_RING][3][W64_TW / 2];
         float4 srow[W64_WARPS][ROWLEN];                                // decoded source row, (r, g, b, -) per pixel
     };
-    static __device__ __forceinline__ int pos(int i) { return i + i / (2 * SS); }
+    // slot of pixel i in a source row: integer ratios pad one slot per 2*S so that the lanes' windows (stride 2*S
+    // pixels) start 2*S+1 float4 apart -- conflict-free LDS.128; any-ratio rows are stored densely
+    static __device__ __forceinline__ int pos(int i) { return S == 0 ? i : i + i / (2 * SS); }
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -646,8 +667,10 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                 if constexpr (S == 0) {
                     const float *w0 = J.w_h + (size_t)oc0 * th, *w1 = J.w_h + (size_t)oc1 * th;  // L1-resident
                     const int win = th + gD;  // union of the two columns' windows (first is non-decreasing)
+                    const float4 *sp = row + gi0;
+#pragma unroll 4
                     for (int j = 0; j < win; j++) {
-                        const float4 v = row[K::pos(gi0 + j)];
+                        const float4 v = sp[j];
                         if (j < th) { const float w = __ldg(w0 + j); r0 = fmaf(v.x, w, r0); g0 = fmaf(v.y, w, g0); b0 = fmaf(v.z, w, b0); }
                         if (j >= gD) { const float w = __ldg(w1 + j - gD); r1 = fmaf(v.x, w, r1); g1 = fmaf(v.y, w, g1); b1 = fmaf(v.z, w, b1); }
                     }
@@ -1068,6 +1091,9 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     // FAST_LUT layers of this tile: blend() of the layer's constant source over each possible target byte, one
     // entry per thread (the four channels of blend() are independent, so one call fills all four maps)
     __shared__ uchar4 s_lut[MAX_LUT][CB_X * CB_Y];
+    __shared__ uchar4 s_px[CB_Y][CB_X * CT_W * CT_H];          // per-warp scratch of the cooperative general path
+    __shared__ unsigned char s_items[CB_Y][CB_X * CT_W * CT_H];
+    static_assert(CB_X == 32 && CB_X * CT_W * CT_H <= 256, "one warp per tile row, items fit a byte");
     static_assert(CB_X * CB_Y == 256, "one table entry per thread");
     {
         const int tid = threadIdx.y * CB_X + threadIdx.x;
@@ -1092,78 +1118,185 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
         for (int i = 0; i < CT_W; i++) px[j][i] = make_uchar4(0, 0, 0, 0);  // LoadOp::Clear(TRANSPARENT)
 
     const int n = s_count;
+    // occlusion: the last layer that replaces this thread's whole 4x2 block makes everything painted before it
+    // invisible -- start there (exact: those layers' bytes do not depend on the target)
+    int first = 0;
+    for (int li = n - 1; li > 0; li--) {
+        const LayerDev &L = PARAM ? LAYERS[s_list[li]] : (li < SM_LAYERS ? s_layers[li] : LAYERS[s_list[li]]);
+        if (!(L.fast & FAST_OPAQUE)) continue;
+        if ((x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1) ||
+            (x0 >= L.jx0 && x0 + CT_W <= L.jx1 && y0 >= L.jy0 && y0 + CT_H <= L.jy1)) { first = li; break; }
+    }
     int lut_next = 0;
     for (int li = 0; li < n; li++) {
         const LayerDev &L = PARAM ? LAYERS[s_list[li]] : (li < SM_LAYERS ? s_layers[li] : LAYERS[s_list[li]]);
         const int lut_i = (L.fast & FAST_LUT) ? lut_next++ : MAX_LUT;   // same numbering as the table build above
-        if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) continue;
-        const bool all_in = (x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1) ||
-                            (x0 >= L.jx0 && x0 + CT_W <= L.jx1 && y0 >= L.jy0 && y0 + CT_H <= L.jy1);
-        if (all_in && (L.fast & FAST_CONST)) {  // opaque colour interior: the layer leaves constant bytes
-            const uchar4 cb = *reinterpret_cast<const uchar4 *>(&L.const_bytes);
-#pragma unroll
-            for (int j = 0; j < CT_H; j++)
-#pragma unroll
-                for (int i = 0; i < CT_W; i++) px[j][i] = cb;
-            continue;
-        }
-        if (all_in && lut_i < MAX_LUT) {  // translucent colour interior: four byte lookups per pixel
-            const uchar4 *lut = s_lut[lut_i];
-#pragma unroll
-            for (int j = 0; j < CT_H; j++)
+        // fast classes first (per thread); `general` survives for blocks that need the full fragment path
+        bool general = false;
+        do {
+            if (li < first) break;
+            if (L.px0 >= x0 + CT_W || L.px1 <= x0 || L.py0 >= y0 + CT_H || L.py1 <= y0) break;
+            const bool all_in = (x0 >= L.ix0 && x0 + CT_W <= L.ix1 && y0 >= L.iy0 && y0 + CT_H <= L.iy1) ||
+                                (x0 >= L.jx0 && x0 + CT_W <= L.jx1 && y0 >= L.jy0 && y0 + CT_H <= L.jy1);
+            if (all_in && (L.fast & FAST_CONST)) {  // opaque colour interior: the layer leaves constant bytes
+                const uchar4 cb = *reinterpret_cast<const uchar4 *>(&L.const_bytes);
+    #pragma unroll
+                for (int j = 0; j < CT_H; j++)
+    #pragma unroll
+                    for (int i = 0; i < CT_W; i++) px[j][i] = cb;
+                break;
+            }
+            if (all_in && lut_i < MAX_LUT) {  // translucent colour interior: four byte lookups per pixel
+                const uchar4 *lut = s_lut[lut_i];
+    #pragma unroll
+                for (int j = 0; j < CT_H; j++)
+    #pragma unroll
+                    for (int i = 0; i < CT_W; i++) {
+                        const uchar4 p = px[j][i];
+                        px[j][i] = make_uchar4(lut[p.x].x, lut[p.y].y, lut[p.z].z, lut[p.w].w);
+                    }
+                break;
+            }
+            if (all_in && (L.fast & FAST_SAMPLE)) {
+                // opaque RGBA8 child sampled at a fractional position / size, axis-aligned: the taps depend on the
+                // column (x) and the row (y) alone, and with alpha exactly 1 blend() ignores the target
+                const Tex &S = J.textures[L.tex];
+                LinTap ax[CT_W], ay[CT_H];
 #pragma unroll
                 for (int i = 0; i < CT_W; i++) {
-                    const uchar4 p = px[j][i];
-                    px[j][i] = make_uchar4(lut[p.x].x, lut[p.y].y, lut[p.z].z, lut[p.w].w);
+                    const float u = (((float)(x0 + i) + 0.5f) - L.left) / L.width;
+                    ax[i] = linear_tap(u * L.crop_sx + L.crop_ox, S.width);
+                    if (ax[i].f == 1.0f) { ax[i].i0 = ax[i].i1; ax[i].f = 0.0f; }
                 }
-            continue;
-        }
-        if (all_in && (L.fast & FAST_IDENT)) {  // 1:1 texture interior: exact texel per pixel
-            const Tex &S = J.textures[L.tex];
-            const int sx = x0 + L.tx_off, sy = y0 + L.ty_off;
-            if (yuv_quad_ok(S, sx, sy) && yuv_quad_ok(S, sx + 2, sy)) {  // YUV source: two chroma-aligned quads
-                yuv_quad(T, S, sx, sy, px[0][0], px[0][1], px[1][0], px[1][1]);       // alpha is 255: bytes pass through
-                yuv_quad(T, S, sx + 2, sy, px[0][2], px[0][3], px[1][2], px[1][3]);
-                continue;
-            }
-            if (S.kind == TEX_RGBA8 && (sx & 3) == 0 && (S.pitch0 & 15) == 0 && ((size_t)S.p0 & 15) == 0) {
-                // RGBA8 source (e.g. a resampled child): one 16-byte load per row
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)sy * S.pitch0) + (sx >> 2));
-                const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)(sy + 1) * S.pitch0) + (sx >> 2));
-                if ((r0.x & r0.y & r0.z & r0.w & r1.x & r1.y & r1.z & r1.w) >= 0xff000000u) {  // all 8 alphas are 255
-                    *reinterpret_cast<unsigned int *>(&px[0][0]) = r0.x; *reinterpret_cast<unsigned int *>(&px[0][1]) = r0.y;
-                    *reinterpret_cast<unsigned int *>(&px[0][2]) = r0.z; *reinterpret_cast<unsigned int *>(&px[0][3]) = r0.w;
-                    *reinterpret_cast<unsigned int *>(&px[1][0]) = r1.x; *reinterpret_cast<unsigned int *>(&px[1][1]) = r1.y;
-                    *reinterpret_cast<unsigned int *>(&px[1][2]) = r1.z; *reinterpret_cast<unsigned int *>(&px[1][3]) = r1.w;
-                    continue;
+#pragma unroll
+                for (int j = 0; j < CT_H; j++) {
+                    const float v = (((float)(y0 + j) + 0.5f) - L.top) / L.height;
+                    ay[j] = linear_tap(v * L.crop_sy + L.crop_oy, S.height);
+                    if (ay[j].f == 1.0f) { ay[j].i0 = ay[j].i1; ay[j].f = 0.0f; }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < CT_H; j++)
+                for (int j = 0; j < CT_H; j++) {
+                    const uchar4 *r0 = reinterpret_cast<const uchar4 *>(S.p0 + (size_t)ay[j].i0 * S.pitch0);
+                    const uchar4 *r1 = reinterpret_cast<const uchar4 *>(S.p0 + (size_t)ay[j].i1 * S.pitch0);
+                    const float fy = ay[j].f;
 #pragma unroll
-                for (int i = 0; i < CT_W; i++) {
-                    uchar4 t = node_texel(T, S, x0 + i + L.tx_off, y0 + j + L.ty_off);
-                    if (t.w == 255) px[j][i] = t;  // encode(decode(b)) == b
-                    else {
-                        const float *lut = J.mode == 0 ? T.dec : T.u8n;
-                        px[j][i] = blend(T, J.mode, px[j][i], make_float4(lut[t.x], lut[t.y], lut[t.z], T.u8n[t.w]));
+                    for (int i = 0; i < CT_W; i++) {
+                        const float fx = ax[i].f;
+                        const uchar4 p00 = __ldg(r0 + ax[i].i0);
+                        if (fx == 0.0f && fy == 0.0f) { px[j][i] = p00; continue; }   // exact texel, alpha 255
+                        const uchar4 p10 = fx != 0.0f ? __ldg(r0 + ax[i].i1) : p00;
+                        const uchar4 p01 = fy != 0.0f ? __ldg(r1 + ax[i].i0) : p00;
+                        const uchar4 p11 = (fx != 0.0f && fy != 0.0f) ? __ldg(r1 + ax[i].i1) : (fx != 0.0f ? p10 : p01);
+                        uchar4 o;
+                        if (J.mode != 0) {
+                            o.x = (unsigned char)unorm8(filter_u8(p00.x, p10.x, p01.x, p11.x, fx, fy));
+                            o.y = (unsigned char)unorm8(filter_u8(p00.y, p10.y, p01.y, p11.y, fx, fy));
+                            o.z = (unsigned char)unorm8(filter_u8(p00.z, p10.z, p01.z, p11.z, fx, fy));
+                        } else {
+                            o.x = (unsigned char)srgb_encode(T, bilerp(T.dec[p00.x], T.dec[p10.x], T.dec[p01.x], T.dec[p11.x], fx, fy));
+                            o.y = (unsigned char)srgb_encode(T, bilerp(T.dec[p00.y], T.dec[p10.y], T.dec[p01.y], T.dec[p11.y], fx, fy));
+                            o.z = (unsigned char)srgb_encode(T, bilerp(T.dec[p00.z], T.dec[p10.z], T.dec[p01.z], T.dec[p11.z], fx, fy));
+                        }
+                        o.w = 255;
+                        px[j][i] = o;
                     }
                 }
-            continue;
+                break;
+            }
+            if (all_in && (L.fast & FAST_IDENT)) {  // 1:1 texture interior: exact texel per pixel
+                const Tex &S = J.textures[L.tex];
+                const int sx = x0 + L.tx_off, sy = y0 + L.ty_off;
+                if (yuv_quad_ok(S, sx, sy) && yuv_quad_ok(S, sx + 2, sy)) {  // YUV source: two chroma-aligned quads
+                    yuv_quad(T, S, sx, sy, px[0][0], px[0][1], px[1][0], px[1][1]);       // alpha is 255: bytes pass through
+                    yuv_quad(T, S, sx + 2, sy, px[0][2], px[0][3], px[1][2], px[1][3]);
+                    break;
+                }
+                if (S.kind == TEX_RGBA8 && (sx & 3) == 0 && (S.pitch0 & 15) == 0 && ((size_t)S.p0 & 15) == 0) {
+                    // RGBA8 source (e.g. a resampled child): one 16-byte load per row
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)sy * S.pitch0) + (sx >> 2));
+                    const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(S.p0 + (size_t)(sy + 1) * S.pitch0) + (sx >> 2));
+                    if ((r0.x & r0.y & r0.z & r0.w & r1.x & r1.y & r1.z & r1.w) >= 0xff000000u) {  // all 8 alphas are 255
+                        *reinterpret_cast<unsigned int *>(&px[0][0]) = r0.x; *reinterpret_cast<unsigned int *>(&px[0][1]) = r0.y;
+                        *reinterpret_cast<unsigned int *>(&px[0][2]) = r0.z; *reinterpret_cast<unsigned int *>(&px[0][3]) = r0.w;
+                        *reinterpret_cast<unsigned int *>(&px[1][0]) = r1.x; *reinterpret_cast<unsigned int *>(&px[1][1]) = r1.y;
+                        *reinterpret_cast<unsigned int *>(&px[1][2]) = r1.z; *reinterpret_cast<unsigned int *>(&px[1][3]) = r1.w;
+                        break;
+                    }
+                }
+    #pragma unroll
+                for (int j = 0; j < CT_H; j++)
+    #pragma unroll
+                    for (int i = 0; i < CT_W; i++) {
+                        uchar4 t = node_texel(T, S, x0 + i + L.tx_off, y0 + j + L.ty_off);
+                        if (t.w == 255) px[j][i] = t;  // encode(decode(b)) == b
+                        else {
+                            const float *lut = J.mode == 0 ? T.dec : T.u8n;
+                            px[j][i] = blend(T, J.mode, px[j][i], make_float4(lut[t.x], lut[t.y], lut[t.z], T.u8n[t.w]));
+                        }
+                    }
+                break;
+            }
+            general = true;
+        } while (0);
+        // general path, warp-cooperative: the pixels that need the full fragment shader + blend are usually a thin
+        // band (anti-aliased edges, corner squares), a few lanes' worth per warp.  They are gathered into a
+        // per-warp list and shaded 32 at a time instead of 8 rounds with most lanes idle.
+        unsigned need = 0;
+        if (general) {
+#pragma unroll 1
+            for (int k = 0; k < CT_W * CT_H; k++) {
+                const int X = x0 + (k & (CT_W - 1)), Y = y0 + k / CT_W;
+                if (X < J.width && Y < J.height && quad_covers(L, X, Y)) need |= 1u << k;
+            }
         }
-        for (int k = 0; k < CT_W * CT_H; k++) {  // general path, deliberately not unrolled (code size)
-            const int i = k & (CT_W - 1), j = k / CT_W;
-            const int X = x0 + i, Y = y0 + j;
-            if (X < J.width && Y < J.height && quad_covers(L, X, Y)) {
+        if (__ballot_sync(0xffffffffu, need != 0) == 0) continue;   // warp-uniform
+        const int lane = threadIdx.x;
+        const int cnt = __popc(need);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > 5 * 32) {   // dense (e.g. a resampled layer at a fractional position): every lane shades its own pixels
+            for (int k = 0; k < CT_W * CT_H; k++) {  // deliberately not unrolled (code size)
+                if (!((need >> k) & 1u)) continue;
+                const int i = k & (CT_W - 1), j = k / CT_W;
                 uchar4 cur = j == 0 ? (i == 0 ? px[0][0] : i == 1 ? px[0][1] : i == 2 ? px[0][2] : px[0][3])
                                     : (i == 0 ? px[1][0] : i == 1 ? px[1][1] : i == 2 ? px[1][2] : px[1][3]);
-                uchar4 res = shade_blend(T, J, L, X, Y, cur);
+                uchar4 res = shade_blend(T, J, L, x0 + i, y0 + j, cur);
 #pragma unroll
                 for (int jj = 0; jj < CT_H; jj++)
 #pragma unroll
                     for (int ii = 0; ii < CT_W; ii++)
                         if (jj == j && ii == i) px[jj][ii] = res;
             }
+            continue;
+        }
+        unsigned char *items = s_items[threadIdx.y];
+        uchar4 *spx = s_px[threadIdx.y];
+        if (need) {
+            int o = incl - cnt;
+#pragma unroll
+            for (int k = 0; k < CT_W * CT_H; k++) {
+                spx[lane * (CT_W * CT_H) + k] = px[k / CT_W][k & (CT_W - 1)];
+                if ((need >> k) & 1u) items[o++] = (unsigned char)(lane * (CT_W * CT_H) + k);
+            }
+        }
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            if (idx < total) {
+                const int item = items[idx], k = item & (CT_W * CT_H - 1);
+                const int X = tile_x0 + (item / (CT_W * CT_H)) * CT_W + (k & (CT_W - 1)), Y = y0 + k / CT_W;
+                spx[item] = shade_blend(T, J, L, X, Y, spx[item]);
+            }
+        }
+        __syncwarp();
+        if (need) {
+#pragma unroll
+            for (int k = 0; k < CT_W * CT_H; k++) px[k / CT_W][k & (CT_W - 1)] = spx[lane * (CT_W * CT_H) + k];
         }
     }
 
@@ -1232,8 +1365,8 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     }  // it
 }
 
-__global__ void __launch_bounds__(CB_X *CB_Y) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
-__global__ void __launch_bounds__(CB_X *CB_Y) k_composite_p(const __grid_constant__ CompositeParams P) {
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_p(const __grid_constant__ CompositeParams P) {
     composite_body<true>(P.job, P.layers);
 }
 

@@ -59,7 +59,11 @@ struct alignas(16) LayerDev {
     uint32_t const_bytes;            // FAST_CONST: bytes an opaque colour leaves in the target (RGBA little endian)
 };
 // FAST_LUT: translucent bare colour -- inside the bars the blend is a per-channel function of the target byte
-enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2, FAST_LUT = 4 };
+// FAST_OPAQUE: inside the bars the layer REPLACES the target bytes (opaque constant, or 1:1 texels of a texture
+// whose alpha is 255 everywhere) -- earlier layers cannot show through there
+// FAST_SAMPLE: axis-aligned opaque RGBA8 child that is NOT 1:1 -- inside the bars each pixel is the filtered,
+// re-encoded sample alone (source alpha exactly 1)
+enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2, FAST_LUT = 4, FAST_OPAQUE = 8, FAST_SAMPLE = 16 };
 
 struct CompositeJob {
     int32_t width, height;           // render target (root node texture) size

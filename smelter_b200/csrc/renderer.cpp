@@ -250,6 +250,7 @@ class Renderer {
     struct PendingComposite { dev::CompositeJob job; size_t layers_off, masks_off; };
     struct PendingCopy { void *dst; size_t dpitch; const void *src; size_t spitch; size_t width, height; };
     std::vector<dev::Tex> tex_table_;
+    std::vector<uint8_t> tex_opaque_;  // per table entry: every texel's alpha is 255 by construction
     std::vector<size_t> tex_frame_off_;       // for textures living in the frame arena: offset of p0 (else SIZE_MAX)
     std::vector<dev::ResampleJob> stage_jobs_[3];
     std::vector<std::pair<size_t, size_t>> stage_frame_off_[3];  // (src offset or SIZE_MAX, dst offset)
@@ -492,6 +493,7 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
         I.has_frame = true;
         I.raw_tex = (int)tex_table_.size();
         tex_table_.push_back(t);
+        tex_opaque_.push_back(t.kind == dev::TEX_YUV420 || t.kind == dev::TEX_NV12);
         tex_frame_off_.push_back(SIZE_MAX);
     }
     return SMR_OK;
@@ -509,6 +511,7 @@ int Renderer::materialised_input(Input &in) {
     t.pitch0 = (int)pitch;
     in.node_tex = (int)tex_table_.size();
     tex_table_.push_back(t);
+    tex_opaque_.push_back(in.tex.kind == dev::TEX_YUV420 || in.tex.kind == dev::TEX_NV12);
     tex_frame_off_.push_back(off);
     convert_jobs_.push_back({in.raw_tex, off});
     return in.node_tex;
@@ -552,6 +555,7 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     out.kind = dev::TEX_RGBA8; out.width = dw; out.height = dh; out.pitch0 = dw * 4;
     int idx = (int)tex_table_.size();
     tex_table_.push_back(out);
+    tex_opaque_.push_back(1);   // the fused kernel reads YUV and writes alpha 255
     tex_frame_off_.push_back(dst_off);
     return idx;
 }
@@ -688,7 +692,7 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
         if (d.ix0 < d.ix1 || d.jx0 < d.jx1) {
             if (l.kind == RenderLayout::Color && l.color.a == 255) {
                 // opaque colour: fma(dst, 0, src) == src, so the target bytes are a constant of the layer
-                d.fast |= dev::FAST_CONST;
+                d.fast |= dev::FAST_CONST | dev::FAST_OPAQUE;
                 uint8_t b[4];
                 for (int c = 0; c < 3; c++)
                     b[c] = opts_.rendering_mode == SMR_MODE_GPU_OPTIMIZED ? srgb_encode_host(d.color[c]) : unorm8_host(d.color[c]);
@@ -705,7 +709,12 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
                 // 1:1 mapping on whole texels: the NC-6 tap is texel (px - left, py - top) with weight exactly 1
                 // (|coordinate error| < 1e-3 << 1/512, the 8-bit weight rounds to 0 or 1)
                 d.fast |= dev::FAST_IDENT;
+                if (tex_opaque_[tex_index]) d.fast |= dev::FAST_OPAQUE;
                 d.tx_off = -(int)l.left; d.ty_off = -(int)l.top;
+            } else if (l.kind == RenderLayout::ChildNode && tex_index >= 0 && tex_opaque_[tex_index] &&
+                       tex_table_[tex_index].kind == dev::TEX_RGBA8 && l.width > 0.0f && l.height > 0.0f) {
+                // opaque resampled child at a fractional position / size: filtered sample alone, target ignored
+                d.fast |= dev::FAST_SAMPLE | dev::FAST_OPAQUE;
             }
         }
     }
@@ -943,6 +952,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
                             t.kind = dev::TEX_RGBA8; t.width = dw; t.height = dh; t.pitch0 = dw * 4;
                             tex_index = (int)tex_table_.size();
                             tex_table_.push_back(t);
+                            tex_opaque_.push_back(0);
                             tex_frame_off_.push_back(dst_off);
                             resample_cache_[key] = tex_index;
                         }
@@ -999,6 +1009,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
         t.kind = dev::TEX_RGBA8; t.width = W; t.height = H; t.pitch0 = W * 4;
         int ti = (int)tex_table_.size();
         tex_table_.push_back(t);
+        tex_opaque_.push_back(0);
         tex_frame_off_.push_back(off);
         push_output_job(ti, 0);
     }
@@ -1022,7 +1033,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         inflight_.pop_front();
     }
     uploaded_ = false;
-    tex_table_.clear(); tex_frame_off_.clear();
+    tex_table_.clear(); tex_opaque_.clear(); tex_frame_off_.clear();
     for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
     fused_jobs_.clear(); fused_src_dst_.clear();
     weight_jobs_.clear(); convert_jobs_.clear(); composites_.clear(); output_jobs_.clear(); output_src_tex_.clear();
