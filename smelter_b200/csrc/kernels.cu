@@ -493,11 +493,12 @@ struct W64 {
     static constexpr int SS = S == 0 ? 4 : S;                           // sizing ratio
     static constexpr int TAPS = 6 * SS + 1;
     static constexpr int SPAN = (W64_TW - 1) * SS + TAPS + 3;          // + chroma alignment / ceil slack
-    static constexpr int ROWLEN = ((SPAN + SPAN / (2 * SS) + 2) + 7) & ~7;
+    static constexpr int ROWLEN = S == 0 ? ((SPAN + 2 + 7) & ~7) : (((SPAN + SPAN / (2 * SS) + 2) + 7) & ~7);
     struct Smem {
         Tables T;
         __half2 ring[W64_RING][3][W64_TW / 2];
         float4 srow[W64_WARPS][ROWLEN];                                // decoded source row, (r, g, b, -) per pixel
+        float hw[S == 0 ? TAPS * W64_TW : 1];                          // any-ratio: the strip's weights, [tap][column]
     };
     // slot of pixel i in a source row: integer ratios pad one slot per 2*S so that the lanes' windows (stride 2*S
     // pixels) start 2*S+1 float4 apart -- conflict-free LDS.128; any-ratio rows are stored densely
@@ -540,6 +541,11 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
         inv0 = __ldg(J.inv_h + oc0); inv1 = __ldg(J.inv_h + oc1);
         const int o_last = min(ox0 + W64_TW - 1, J.dst_w - 1);
         npairs_g = (min(__ldg(J.first_h + o_last) + th - xa_e, K::SPAN) + 1) >> 1;
+        for (int t = warp; t < th; t += W64_WARPS) {   // [tap][column]: conflict-free reads in A2
+            M.hw[t * W64_TW + 2 * lane] = __ldg(J.w_h + (size_t)oc0 * th + t);
+            M.hw[t * W64_TW + 2 * lane + 1] = __ldg(J.w_h + (size_t)oc1 * th + t);
+        }
+        __syncthreads();
     } else {
         inv0 = inv1 = c_winv[S];
     }
@@ -665,14 +671,14 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                 __half2 *ringrow = &M.ring[r & (W64_RING - 1)][0][0];
                 float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
                 if constexpr (S == 0) {
-                    const float *w0 = J.w_h + (size_t)oc0 * th, *w1 = J.w_h + (size_t)oc1 * th;  // L1-resident
+                    const float *w0 = M.hw + 2 * lane, *w1 = M.hw + 2 * lane + 1 - gD * W64_TW;
                     const int win = th + gD;  // union of the two columns' windows (first is non-decreasing)
                     const float4 *sp = row + gi0;
 #pragma unroll 4
                     for (int j = 0; j < win; j++) {
                         const float4 v = sp[j];
-                        if (j < th) { const float w = __ldg(w0 + j); r0 = fmaf(v.x, w, r0); g0 = fmaf(v.y, w, g0); b0 = fmaf(v.z, w, b0); }
-                        if (j >= gD) { const float w = __ldg(w1 + j - gD); r1 = fmaf(v.x, w, r1); g1 = fmaf(v.y, w, g1); b1 = fmaf(v.z, w, b1); }
+                        if (j < th) { const float w = w0[j * W64_TW]; r0 = fmaf(v.x, w, r0); g0 = fmaf(v.y, w, g0); b0 = fmaf(v.z, w, b0); }
+                        if (j >= gD) { const float w = w1[j * W64_TW]; r1 = fmaf(v.x, w, r1); g1 = fmaf(v.y, w, g1); b1 = fmaf(v.z, w, b1); }
                     }
                 } else {
                     const float4 *sp = row + (2 * S + 1) * lane;   // pos(2*S*lane + j) = (2*S+1)*lane + pos(j)
