@@ -129,7 +129,11 @@ typedef enum {
     SMR_FRAME_NV12 = 2,            /* FrameData::Nv12: planes y, uv */
     SMR_FRAME_BGRA = 3,            /* FrameData::Bgra */
     SMR_FRAME_ARGB = 4,            /* FrameData::Argb */
-    SMR_FRAME_RGBA8 = 5            /* FrameData::Rgba8UnormWgpuTexture analogue: premultiplied RGBA8 */
+    SMR_FRAME_RGBA8 = 5,           /* FrameData::Rgba8UnormWgpuTexture analogue: premultiplied RGBA8 */
+    SMR_FRAME_PLANAR_YUV422 = 6,   /* FrameData::PlanarYuv422: planes y (w x h), u, v (w/2 x h) */
+    SMR_FRAME_PLANAR_YUV444 = 7,   /* FrameData::PlanarYuv444: planes y, u, v (w x h) */
+    SMR_FRAME_UYVY422 = 8,         /* FrameData::InterleavedUyvy422: one plane, rows of (w/2) x {U,Y0,V,Y1} */
+    SMR_FRAME_YUYV422 = 9          /* FrameData::InterleavedYuyv422: one plane, rows of (w/2) x {Y0,U,Y1,V} */
 } smr_frame_format;
 
 typedef enum { SMR_MEM_HOST = 0, SMR_MEM_DEVICE = 1 } smr_mem_kind;
@@ -146,6 +150,8 @@ typedef struct {                   /* one entry of FrameSet<InputId> */
 
 typedef enum {                     /* OutputFrameFormat, types.rs:187-194 */
     SMR_OUT_PLANAR_YUV420 = 0,     /* PlanarYuv420Bytes */
+    SMR_OUT_PLANAR_YUV422 = 1,     /* PlanarYuv422Bytes: u, v planes (w/2) x h */
+    SMR_OUT_PLANAR_YUV444 = 2,     /* PlanarYuv444Bytes: u, v planes w x h */
     SMR_OUT_RGBA8 = 3,             /* RgbaWgpuTexture analogue */
     SMR_OUT_NV12 = 4               /* Nv12WgpuTexture analogue */
 } smr_output_format;

@@ -92,6 +92,23 @@ def yuv420_to_rgba(y, u, v, w, h, full_range=False):
     return out
 
 
+def yuv_planar_to_rgba(y, u, v, w, h, cw, ch, full_range=False):
+    """planar 4:2:0 / 4:2:2 / 4:4:4 by chroma plane size (texture/planar_yuv.rs:64-83)"""
+    y, u, v = _u8(y), _u8(u), _u8(v)
+    out = np.empty((h, w, 4), np.uint8)
+    lib().orc_yuv_planar_to_rgba(_p(y), _p(u), _p(v), w, h, cw, ch, int(full_range), _p(out))
+    return out
+
+
+def interleaved422_to_rgba(data, w, h, yuyv):
+    """K3: UYVY (yuyv=False) / YUYV (yuyv=True), h rows of 2*(w//2)*2 bytes"""
+    data = _u8(data)
+    assert data.size >= (w // 2) * 4 * h
+    out = np.empty((h, w, 4), np.uint8)
+    lib().orc_interleaved422_to_rgba(_p(data), w, h, int(bool(yuyv)), _p(out))
+    return out
+
+
 def nv12_to_rgba(y, uv, w, h):
     y, uv = _u8(y), _u8(uv)
     out = np.empty((h, w, 4), np.uint8)
@@ -139,6 +156,16 @@ def rgba_to_yuv420_scaled(rgba, w, h):
     u = np.empty((h // 2, w // 2), np.uint8)
     v = np.empty((h // 2, w // 2), np.uint8)
     lib().orc_rgba_to_yuv420_scaled(_p(rgba), sw, sh, w, h, _p(y), _p(u), _p(v))
+    return y, u, v
+
+
+def rgba_to_yuv_planar_scaled(rgba, w, h, cw, ch):
+    rgba = _u8(rgba)
+    sh, sw = rgba.shape[:2]
+    y = np.empty((h, w), np.uint8)
+    u = np.empty((ch, cw), np.uint8)
+    v = np.empty((ch, cw), np.uint8)
+    lib().orc_rgba_to_yuv_planar_scaled(_p(rgba), sw, sh, w, h, cw, ch, _p(y), _p(u), _p(v))
     return y, u, v
 
 

@@ -178,9 +178,11 @@ static inline void yuv_to_rgba_px(float y, float u, float v, int full_range, uin
     out[0] = orc_unorm8(r); out[1] = orc_unorm8(g); out[2] = orc_unorm8(b); out[3] = 255;
 }
 
-void orc_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h,
-                        int full_range, uint8_t *rgba) {
-    int cw = w / 2, ch = h / 2; /* texture/planar_yuv.rs:66-71 */
+/* any planar variant: the chroma planes are cw x ch (420: w/2 x h/2, 422: w/2 x h, 444: w x h;
+ * texture/planar_yuv.rs:64-83) and all three planes are sampled at the SAME normalised coordinate
+ * (planar_yuv_to_rgba.wgsl:37-39) */
+void orc_yuv_planar_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h, int cw, int ch,
+                            int full_range, uint8_t *rgba) {
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < h; py++) {
         float ty = ((float)py + 0.5f) / (float)h;
@@ -190,6 +192,37 @@ void orc_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, in
             float uu = sample_u8_plane(u, cw, ch, cw, 1, 0, tx, ty);
             float vv = sample_u8_plane(v, cw, ch, cw, 1, 0, tx, ty);
             yuv_to_rgba_px(yy, uu, vv, full_range, rgba + ((size_t)py * w + px) * 4);
+        }
+    }
+}
+
+void orc_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h,
+                        int full_range, uint8_t *rgba) {
+    orc_yuv_planar_to_rgba(y, u, v, w, h, w / 2, h / 2, full_range, rgba); /* texture/planar_yuv.rs:66-71 */
+}
+
+/* K3: interleaved 4:2:2 (interleaved_uyvy_to_rgba.wgsl:24-61, interleaved_yuyv_to_rgba.wgsl:24-61).  The frame is
+ * uploaded as an Rgba8Unorm texture of (w/2) x h texels, one texel = two pixels (texture/interleaved_yuv422.rs:12-36);
+ * the fragment shader turns its interpolated coordinate back into a column index, fetches the texel at its centre
+ * (NC-6: the residual bilinear weight rounds to 0) and picks the first or second luma.  Always limited range. */
+void orc_interleaved422_to_rgba(const uint8_t *data, int w, int h, int yuyv, uint8_t *rgba) {
+    int dimx = w / 2;
+    if (dimx < 1) return;
+    const float eps = 0.0001f, half_pixel_width = 0.5f / (float)dimx;
+#pragma omp parallel for schedule(static)
+    for (int py = 0; py < h; py++) {
+        float ty = ((float)py + 0.5f) / (float)h;
+        for (int px = 0; px < w; px++) {
+            float tx = ((float)px + 0.5f) / (float)w;
+            float xf = ((tx * (float)dimx - half_pixel_width) + eps) * 2.0f;
+            uint32_t x_pos = xf >= 4294967296.0f ? 0xffffffffu : (xf > 0.0f ? (uint32_t)xf : 0u); /* u32(): saturating */
+            float tcx = (float)(x_pos / 2u) / (float)dimx + half_pixel_width;
+            float t[4];
+            for (int c = 0; c < 4; c++) t[c] = sample_u8_plane(data, dimx, h, dimx, 4, c, tcx, ty);
+            float uu, vv, yy;
+            if (yuyv) { yy = (x_pos & 1u) ? t[2] : t[0]; uu = t[1]; vv = t[3]; }
+            else { yy = (x_pos & 1u) ? t[3] : t[1]; uu = t[0]; vv = t[2]; }
+            yuv_to_rgba_px(yy, uu, vv, 0, rgba + ((size_t)py * w + px) * 4);
         }
     }
 }
@@ -256,9 +289,10 @@ static void rgba_to_y_plane(const uint8_t *rgba, int sw, int sh, int w, int h, u
         }
 }
 
-void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *u,
-                               uint8_t *v) {
-    int cw = w / 2, ch = h / 2;
+/* planar 420 / 422 / 444 outputs differ only in the chroma plane size cw x ch (texture/planar_yuv.rs:64-83);
+ * every plane is a full-target draw sampling the source at its own pixel centres (rgba_to_yuv.rs:67-116) */
+void orc_rgba_to_yuv_planar_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, int cw, int ch, uint8_t *y,
+                                   uint8_t *u, uint8_t *v) {
     rgba_to_y_plane(rgba, sw, sh, w, h, y);
 #pragma omp parallel for schedule(static)
     for (int py = 0; py < ch; py++)
@@ -268,6 +302,11 @@ void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h
             u[(size_t)py * cw + px] = orc_unorm8(to_u(c));
             v[(size_t)py * cw + px] = orc_unorm8(to_v(c));
         }
+}
+
+void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *u,
+                               uint8_t *v) {
+    orc_rgba_to_yuv_planar_scaled(rgba, sw, sh, w, h, w / 2, h / 2, y, u, v);
 }
 
 void orc_rgba_to_nv12_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *uv) {

@@ -73,6 +73,11 @@ void orc_init(void);
 void orc_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h,
                         int full_range, uint8_t *rgba);
 void orc_nv12_to_rgba(const uint8_t *y, const uint8_t *uv, int w, int h, uint8_t *rgba);
+/* planar 4:2:0 / 4:2:2 / 4:4:4 by chroma plane size (texture/planar_yuv.rs:64-83) */
+void orc_yuv_planar_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h, int cw, int ch,
+                            int full_range, uint8_t *rgba);
+/* K3 interleaved_{uyvy,yuyv}_to_rgba.wgsl; yuyv = 0: U Y0 V Y1, 1: Y0 U Y1 V */
+void orc_interleaved422_to_rgba(const uint8_t *data, int w, int h, int yuyv, uint8_t *rgba);
 /* K4 (bgra_to_rgba.wgsl / argb_to_rgba.wgsl): pure swizzles */
 void orc_bgra_to_rgba(const uint8_t *bgra, int w, int h, uint8_t *rgba);
 void orc_argb_to_rgba(const uint8_t *argb, int w, int h, uint8_t *rgba);
@@ -83,6 +88,8 @@ void orc_rgba_to_nv12(const uint8_t *rgba, int w, int h, uint8_t *y, uint8_t *uv
 /* same converters when the root texture (sw x sh) is not the output size (w x h) */
 void orc_rgba_to_yuv420_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *u,
                                uint8_t *v);
+void orc_rgba_to_yuv_planar_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, int cw, int ch, uint8_t *y,
+                                   uint8_t *u, uint8_t *v);
 void orc_rgba_to_nv12_scaled(const uint8_t *rgba, int sw, int sh, int w, int h, uint8_t *y, uint8_t *uv);
 /* RGBColor::to_yuv (scene/types.rs:28-42) stored through an R8Unorm target; black-frame fill
  * of render_loop.rs:127-139 */

@@ -14,8 +14,9 @@ MODE_GPU_OPTIMIZED, MODE_CPU_OPTIMIZED = 0, 1
 COMPONENT_INPUT_STREAM, COMPONENT_VIEW, COMPONENT_TILES, COMPONENT_RESCALER = 0, 1, 2, 3
 COMPONENT_SHADER, COMPONENT_WEB_VIEW, COMPONENT_IMAGE, COMPONENT_TEXT = 4, 5, 6, 7
 FRAME_PLANAR_YUV420, FRAME_PLANAR_YUVJ420, FRAME_NV12, FRAME_BGRA, FRAME_ARGB, FRAME_RGBA8 = 0, 1, 2, 3, 4, 5
+FRAME_PLANAR_YUV422, FRAME_PLANAR_YUV444, FRAME_UYVY422, FRAME_YUYV422 = 6, 7, 8, 9
 MEM_HOST, MEM_DEVICE = 0, 1
-OUT_PLANAR_YUV420, OUT_RGBA8, OUT_NV12 = 0, 3, 4
+OUT_PLANAR_YUV420, OUT_PLANAR_YUV422, OUT_PLANAR_YUV444, OUT_RGBA8, OUT_NV12 = 0, 1, 2, 3, 4
 MAX_MASKS = 20
 
 

@@ -260,6 +260,33 @@ __device__ __forceinline__ uchar4 node_texel(const Tables &T, const Tex &s, int 
             }
             return yuv_to_rgba8(yy, uu, vv, s.full_range);
         }
+        case TEX_YUV422:
+        case TEX_YUV444: {   // the three planes are sampled at the same normalised coordinate (NC-6)
+            const int cw = s.kind == TEX_YUV444 ? s.width : s.width / 2, ch = s.height;
+            float tx = ((float)x + 0.5f) / (float)s.width, ty = ((float)y + 0.5f) / (float)s.height;
+            LinTap ax = linear_tap(tx, s.width), ay = linear_tap(ty, s.height);
+            LinTap cx = linear_tap(tx, cw), cy = linear_tap(ty, ch);
+            float yy = sample_plane(T, s.p0, s.pitch0, 1, 0, ax, ay);
+            float uu = sample_plane(T, s.p1, s.pitch1, 1, 0, cx, cy);
+            float vv = sample_plane(T, s.p2, s.pitch2, 1, 0, cx, cy);
+            return yuv_to_rgba8(yy, uu, vv, 0);
+        }
+        case TEX_UYVY:
+        case TEX_YUYV: {   // K3 (interleaved_{uyvy,yuyv}_to_rgba.wgsl:24-61): column index back from the coordinate
+            const int dimx = s.width / 2;
+            const float eps = 0.0001f, hpw = 0.5f / (float)dimx;
+            float tx = ((float)x + 0.5f) / (float)s.width, ty = ((float)y + 0.5f) / (float)s.height;
+            float xf = ((tx * (float)dimx - hpw) + eps) * 2.0f;
+            unsigned x_pos = xf >= 4294967296.0f ? 0xffffffffu : (xf > 0.0f ? (unsigned)xf : 0u);
+            float tcx = (float)(x_pos / 2u) / (float)dimx + hpw;
+            LinTap ax = linear_tap(tcx, dimx), ay = linear_tap(ty, s.height);
+            float t[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) t[c] = sample_plane(T, s.p0, s.pitch0, 4, c, ax, ay);
+            const bool second = x_pos & 1u;
+            if (s.kind == TEX_YUYV) return yuv_to_rgba8(second ? t[2] : t[0], t[1], t[3], 0);
+            return yuv_to_rgba8(second ? t[3] : t[1], t[0], t[2], 0);
+        }
         default:
             return make_uchar4(0, 0, 0, 0);
     }
@@ -1416,7 +1443,8 @@ __global__ void __launch_bounds__(256) k_output(OutputJob J) {
     float r, g, b;
     sample_raw_rgb(T, J.src, ((float)x + 0.5f) / (float)J.out_w, ((float)y + 0.5f) / (float)J.out_h, r, g, b);
     J.out0[(size_t)y * J.out_pitch0 + x] = (unsigned char)unorm8(to_y(r, g, b));
-    int cw = J.out_w / 2, ch = J.out_h / 2;
+    int cw, ch;
+    chroma_dims(J.out_format, J.out_w, J.out_h, cw, ch);
     if (x < cw && y < ch) {  // chroma target texel (x, y)
         sample_raw_rgb(T, J.src, ((float)x + 0.5f) / (float)cw, ((float)y + 0.5f) / (float)ch, r, g, b);
         unsigned char u = (unsigned char)unorm8(to_u(r, g, b)), v = (unsigned char)unorm8(to_v(r, g, b));
@@ -1448,7 +1476,9 @@ __global__ void k_fill(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pi
         return;
     }
     p0[(size_t)y * pitch0 + x] = yv;
-    if (x < w / 2 && y < h / 2) {
+    int cw, ch;
+    chroma_dims(fmt, w, h, cw, ch);
+    if (x < cw && y < ch) {
         if (fmt == 4) {
             p1[(size_t)y * pitch1 + 2 * x] = uv;
             p1[(size_t)y * pitch1 + 2 * x + 1] = vv;

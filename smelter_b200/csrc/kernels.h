@@ -18,7 +18,21 @@ enum TexKind : int32_t {
     TEX_F16 = 4,     // Rgba16Float scratch
     TEX_BGRA = 5,
     TEX_ARGB = 6,
+    TEX_YUV422 = 7,  // planar, chroma (w/2) x h
+    TEX_YUV444 = 8,  // planar, chroma w x h
+    TEX_UYVY = 9,    // interleaved 4:2:2, one plane of (w/2) x h texels {U,Y0,V,Y1} (K3)
+    TEX_YUYV = 10,   // ... {Y0,U,Y1,V}
 };
+// output formats follow smr_output_format: 0 = planar 4:2:0, 1 = planar 4:2:2, 2 = planar 4:4:4, 3 = RGBA8, 4 = NV12.
+// Size of one chroma plane (texture/planar_yuv.rs:64-83)
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void chroma_dims(int out_format, int w, int h, int &cw, int &ch) {
+    cw = out_format == 2 ? w : w / 2;
+    ch = (out_format == 1 || out_format == 2) ? h : h / 2;
+}
 
 struct Tex {
     int32_t kind = TEX_NONE;

@@ -389,7 +389,7 @@ smr_status Renderer::unregister_output(const char *id) {
 smr_status Renderer::update_scene(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, const smr_component *root) {
     if (!output_id || !root) return SMR_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(mu_);
-    if (fmt != SMR_OUT_PLANAR_YUV420 && fmt != SMR_OUT_RGBA8 && fmt != SMR_OUT_NV12) {
+    if (fmt < SMR_OUT_PLANAR_YUV420 || fmt > SMR_OUT_NV12) {
         set_error("unsupported output format");
         return SMR_ERR_UNSUPPORTED;
     }
@@ -430,6 +430,17 @@ static bool plane_layout(int fmt, uint32_t w, uint32_t h, int plane, size_t &row
             if (plane == 0) { row_bytes = w; rows = h; return true; }
             if (plane == 1) { row_bytes = (size_t)cw * 2; rows = ch; return true; }
             return false;
+        case SMR_FRAME_PLANAR_YUV422:   // texture/planar_yuv.rs:72-77
+            if (plane == 0) { row_bytes = w; rows = h; return true; }
+            if (plane <= 2) { row_bytes = cw; rows = h; return true; }
+            return false;
+        case SMR_FRAME_PLANAR_YUV444:   // texture/planar_yuv.rs:78-83
+            if (plane <= 2) { row_bytes = w; rows = h; return true; }
+            return false;
+        case SMR_FRAME_UYVY422:
+        case SMR_FRAME_YUYV422:         // texture/interleaved_yuv422.rs:12-36: (w/2) x h texels of 4 bytes
+            if (plane == 0) { row_bytes = (size_t)cw * 4; rows = h; return true; }
+            return false;
         case SMR_FRAME_BGRA:
         case SMR_FRAME_ARGB:
         case SMR_FRAME_RGBA8:
@@ -463,6 +474,10 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
             case SMR_FRAME_BGRA: t.kind = dev::TEX_BGRA; break;
             case SMR_FRAME_ARGB: t.kind = dev::TEX_ARGB; break;
             case SMR_FRAME_RGBA8: t.kind = dev::TEX_RGBA8; break;
+            case SMR_FRAME_PLANAR_YUV422: t.kind = dev::TEX_YUV422; break;
+            case SMR_FRAME_PLANAR_YUV444: t.kind = dev::TEX_YUV444; break;
+            case SMR_FRAME_UYVY422: t.kind = dev::TEX_UYVY; break;
+            case SMR_FRAME_YUYV422: t.kind = dev::TEX_YUYV; break;
             default: set_error("unsupported input frame format"); return SMR_ERR_UNSUPPORTED;
         }
         t.width = (int)f->width; t.height = (int)f->height;
@@ -478,8 +493,12 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
                 pitches[p] = (int)spitch;
             } else {
                 CUDA_OK(I.planes[slot_][p].ensure(row_bytes * rows));
-                CUDA_OK(cudaMemcpy2DAsync(I.planes[slot_][p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
-                                          cudaMemcpyHostToDevice, copy_stream_));
+                if (spitch == row_bytes)   // tightly packed (the reference's bytes::Bytes planes): one linear DMA
+                    CUDA_OK(cudaMemcpyAsync(I.planes[slot_][p].p, f->planes[p], row_bytes * rows, cudaMemcpyHostToDevice,
+                                            copy_stream_));
+                else
+                    CUDA_OK(cudaMemcpy2DAsync(I.planes[slot_][p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
+                                              cudaMemcpyHostToDevice, copy_stream_));
                 uploaded_ = true;
                 stats_.h2d_bytes += row_bytes * rows;
                 ptrs[p] = I.planes[slot_][p].p;
@@ -493,7 +512,7 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
         I.has_frame = true;
         I.raw_tex = (int)tex_table_.size();
         tex_table_.push_back(t);
-        tex_opaque_.push_back(t.kind == dev::TEX_YUV420 || t.kind == dev::TEX_NV12);
+        tex_opaque_.push_back(t.kind == dev::TEX_YUV420 || t.kind == dev::TEX_NV12 || t.kind >= dev::TEX_YUV422);
         tex_frame_off_.push_back(SIZE_MAX);
     }
     return SMR_OK;
@@ -511,7 +530,7 @@ int Renderer::materialised_input(Input &in) {
     t.pitch0 = (int)pitch;
     in.node_tex = (int)tex_table_.size();
     tex_table_.push_back(t);
-    tex_opaque_.push_back(in.tex.kind == dev::TEX_YUV420 || in.tex.kind == dev::TEX_NV12);
+    tex_opaque_.push_back(in.tex.kind == dev::TEX_YUV420 || in.tex.kind == dev::TEX_NV12 || in.tex.kind >= dev::TEX_YUV422);
     tex_frame_off_.push_back(off);
     convert_jobs_.push_back({in.raw_tex, off});
     return in.node_tex;
@@ -768,7 +787,9 @@ static void black_yuv(uint8_t out[3]) {  // RGBColor::BLACK.to_yuv() through an 
 
 static void out_plane_layout(int fmt, uint32_t w, uint32_t h, size_t row_bytes[3], size_t rows[3]) {
     for (int i = 0; i < 3; i++) row_bytes[i] = rows[i] = 0;
-    uint32_t cw = w / 2, ch = h / 2;
+    int icw, ich;
+    dev::chroma_dims(fmt, (int)w, (int)h, icw, ich);
+    uint32_t cw = (uint32_t)icw, ch = (uint32_t)ich;
     if (fmt == SMR_OUT_RGBA8) { row_bytes[0] = (size_t)w * 4; rows[0] = h; }
     else if (fmt == SMR_OUT_NV12) { row_bytes[0] = w; rows[0] = h; row_bytes[1] = (size_t)cw * 2; rows[1] = ch; }
     else { row_bytes[0] = w; rows[0] = h; row_bytes[1] = row_bytes[2] = cw; rows[1] = rows[2] = ch; }
@@ -828,7 +849,8 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
             return SMR_ERR_UNSUPPORTED;
         }
         const bool same = in.res.width == o.res.width && in.res.height == o.res.height;
-        if (same && (o.format == SMR_OUT_RGBA8 || ((of.width % 2 == 0) && (of.height % 2 == 0)))) {
+        const bool fused_fmt = o.format == SMR_OUT_PLANAR_YUV420 || o.format == SMR_OUT_NV12;   // K10/K11 in the composite
+        if (same && (o.format == SMR_OUT_RGBA8 || (fused_fmt && (of.width % 2 == 0) && (of.height % 2 == 0)))) {
             // Same size: K1 -> K10 runs as ONE composite launch with a single full-frame texture layer; an
             // unmodified opaque texel passes through the sRGB target byte-exactly, so the bytes K10 sees
             // are the node texture's.
@@ -991,7 +1013,8 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
     if (!masks.empty()) memcpy(param_host_.data() + pc.masks_off, masks.data(), sizeof(dev::MaskDev) * masks.size());
 
     bool same_size = (size_t)W == o.res.width && (size_t)H == o.res.height;
-    bool fusable = same_size && (o.format == SMR_OUT_RGBA8 || ((W % 2 == 0) && (H % 2 == 0)));
+    bool fused_fmt = o.format == SMR_OUT_PLANAR_YUV420 || o.format == SMR_OUT_NV12;
+    bool fusable = same_size && (o.format == SMR_OUT_RGBA8 || (fused_fmt && (W % 2 == 0) && (H % 2 == 0)));
     if (fusable) {
         pc.job.out_format = o.format;
         pc.job.out0 = dst[0]; pc.job.out1 = dst[1]; pc.job.out2 = dst[2];
@@ -1192,7 +1215,10 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         prof_mark(SMR_KERNEL_FILL);
     }
     for (PendingCopy &c : d2h_)
-        CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, stream_));
+        if (c.dpitch == c.width && c.spitch == c.width)
+            CUDA_OK(cudaMemcpyAsync(c.dst, c.src, c.width * c.height, cudaMemcpyDeviceToHost, stream_));
+        else
+            CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, stream_));
     stats_.kernel_launches += launches;
     stats_.last_render_kernel_launches = launches;
     stats_.frames_rendered += n_out;
@@ -1461,7 +1487,7 @@ const char *smr_version(void) { return "smelter_b200 0.1 (sm_100a)"; }
 
 smr_status smr_output_plane_sizes(uint32_t w, uint32_t h, int32_t fmt, size_t sizes[3]) {
     if (!sizes) return SMR_ERR_INVALID_ARGUMENT;
-    if (fmt != SMR_OUT_PLANAR_YUV420 && fmt != SMR_OUT_RGBA8 && fmt != SMR_OUT_NV12) return SMR_ERR_UNSUPPORTED;
+    if (fmt < SMR_OUT_PLANAR_YUV420 || fmt > SMR_OUT_NV12) return SMR_ERR_UNSUPPORTED;
     size_t rb[3], rows[3];
     smr::out_plane_layout(fmt, w, h, rb, rows);
     for (int i = 0; i < 3; i++) sizes[i] = rb[i] * rows[i];

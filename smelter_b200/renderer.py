@@ -39,6 +39,8 @@ class RenderingMode:
 
 class OutputFrameFormat:
     PlanarYuv420Bytes = F.OUT_PLANAR_YUV420
+    PlanarYuv422Bytes = F.OUT_PLANAR_YUV422
+    PlanarYuv444Bytes = F.OUT_PLANAR_YUV444
     RgbaWgpuTexture = F.OUT_RGBA8   # RGBA8 premultiplied texture (device or host buffer here)
     Nv12WgpuTexture = F.OUT_NV12
 
@@ -64,7 +66,8 @@ class NvPlanes:
 
 @dataclass
 class FrameData:
-    """FrameData enum: kind in {PlanarYuv420, PlanarYuvJ420, Nv12, Bgra, Argb, Rgba8}.
+    """FrameData enum: kind in {PlanarYuv420, PlanarYuv422, PlanarYuv444, PlanarYuvJ420, InterleavedUyvy422,
+    InterleavedYuyv422, Nv12, Bgra, Argb, Rgba8}.
     `planes` are numpy arrays (host) or integer device pointers (device=True)."""
     kind: str
     planes: tuple
@@ -73,6 +76,22 @@ class FrameData:
     @staticmethod
     def PlanarYuv420(p: YuvPlanes):
         return FrameData("PlanarYuv420", (p.y_plane, p.u_plane, p.v_plane))
+
+    @staticmethod
+    def PlanarYuv422(p: YuvPlanes):
+        return FrameData("PlanarYuv422", (p.y_plane, p.u_plane, p.v_plane))
+
+    @staticmethod
+    def PlanarYuv444(p: YuvPlanes):
+        return FrameData("PlanarYuv444", (p.y_plane, p.u_plane, p.v_plane))
+
+    @staticmethod
+    def InterleavedUyvy422(data):
+        return FrameData("InterleavedUyvy422", (data,))
+
+    @staticmethod
+    def InterleavedYuyv422(data):
+        return FrameData("InterleavedYuyv422", (data,))
 
     @staticmethod
     def PlanarYuvJ420(p: YuvPlanes):
@@ -96,7 +115,9 @@ class FrameData:
 
 
 _FRAME_KIND = {"PlanarYuv420": F.FRAME_PLANAR_YUV420, "PlanarYuvJ420": F.FRAME_PLANAR_YUVJ420,
-               "Nv12": F.FRAME_NV12, "Bgra": F.FRAME_BGRA, "Argb": F.FRAME_ARGB, "Rgba8": F.FRAME_RGBA8}
+               "Nv12": F.FRAME_NV12, "Bgra": F.FRAME_BGRA, "Argb": F.FRAME_ARGB, "Rgba8": F.FRAME_RGBA8,
+               "PlanarYuv422": F.FRAME_PLANAR_YUV422, "PlanarYuv444": F.FRAME_PLANAR_YUV444,
+               "InterleavedUyvy422": F.FRAME_UYVY422, "InterleavedYuyv422": F.FRAME_YUYV422}
 
 
 @dataclass
@@ -488,6 +509,11 @@ class Renderer:
             if fmt == F.OUT_PLANAR_YUV420:
                 data = FrameData.PlanarYuv420(YuvPlanes(pl[0].reshape(h, w), pl[1].reshape(h // 2, w // 2),
                                                         pl[2].reshape(h // 2, w // 2)))
+            elif fmt == F.OUT_PLANAR_YUV422:
+                data = FrameData.PlanarYuv422(YuvPlanes(pl[0].reshape(h, w), pl[1].reshape(h, w // 2),
+                                                        pl[2].reshape(h, w // 2)))
+            elif fmt == F.OUT_PLANAR_YUV444:
+                data = FrameData.PlanarYuv444(YuvPlanes(pl[0].reshape(h, w), pl[1].reshape(h, w), pl[2].reshape(h, w)))
             elif fmt == F.OUT_NV12:
                 data = FrameData.Nv12(NvPlanes(pl[0].reshape(h, w), pl[1].reshape(h // 2, w // 2, 2)))
             else:

@@ -38,6 +38,12 @@ def node_texture(frame: s.Frame):
         return orc.yuv420_to_rgba(*d.planes, w, h)
     if d.kind == "PlanarYuvJ420":
         return orc.yuv420_to_rgba(*d.planes, w, h, full_range=True)
+    if d.kind == "PlanarYuv422":
+        return orc.yuv_planar_to_rgba(*d.planes, w, h, w // 2, h)
+    if d.kind == "PlanarYuv444":
+        return orc.yuv_planar_to_rgba(*d.planes, w, h, w, h)
+    if d.kind in ("InterleavedUyvy422", "InterleavedYuyv422"):
+        return orc.interleaved422_to_rgba(d.planes[0], w, h, d.kind == "InterleavedYuyv422")
     if d.kind == "Nv12":
         return orc.nv12_to_rgba(d.planes[0], d.planes[1], w, h)
     if d.kind == "Bgra":
@@ -70,7 +76,17 @@ def oracle_output(renderer, scene, frames, resolution, out_format, mode, pts, li
         return (rgba,)
     if out_format == s.OutputFrameFormat.Nv12WgpuTexture:
         return orc.rgba_to_nv12_scaled(rgba, W, H)
-    return orc.rgba_to_yuv420_scaled(rgba, W, H)
+    cw, ch = chroma_size(out_format, W, H)
+    return orc.rgba_to_yuv_planar_scaled(rgba, W, H, cw, ch)
+
+
+def chroma_size(out_format, W, H):
+    """texture/planar_yuv.rs:64-83"""
+    if out_format == s.OutputFrameFormat.PlanarYuv422Bytes:
+        return W // 2, H
+    if out_format == s.OutputFrameFormat.PlanarYuv444Bytes:
+        return W, H
+    return W // 2, H // 2
 
 
 def black(resolution, out_format):
@@ -82,7 +98,8 @@ def black(resolution, out_format):
         uv = np.empty((H // 2, W // 2, 2), np.uint8)
         uv[..., 0], uv[..., 1] = u, v
         return (np.full((H, W), y, np.uint8), uv)
-    return (np.full((H, W), y, np.uint8), np.full((H // 2, W // 2), u, np.uint8), np.full((H // 2, W // 2), v, np.uint8))
+    cw, ch = chroma_size(out_format, W, H)
+    return (np.full((H, W), y, np.uint8), np.full((ch, cw), u, np.uint8), np.full((ch, cw), v, np.uint8))
 
 
 def product_planes(frame: s.Frame):
@@ -126,3 +143,27 @@ def nv12_frame(planes, w, h, pts=0.0):
     y, u, v = planes
     uv = np.stack([u, v], axis=-1)
     return s.Frame(s.FrameData.Nv12(s.NvPlanes(y, uv)), s.Resolution(w, h), pts)
+
+
+def wide_chroma_frame(kind, seed, w, h, pts=0.0):
+    """seeded frame in one of the non-4:2:0 input formats (FrameData::{PlanarYuv422, PlanarYuv444,
+    InterleavedUyvy422, InterleavedYuyv422}); smooth luma ramp + noise so that scaling has something to filter"""
+    rng = np.random.default_rng(seed)
+    xx, yy = np.meshgrid(np.arange(w), np.arange(h))
+    y = (16 + ((xx * 3 + yy * 5 + seed * 7) % 200) * 0.9 + rng.integers(0, 20, (h, w))).astype(np.uint8)
+    cw = w if kind == "PlanarYuv444" else w // 2
+    u = rng.integers(16, 241, (h, cw), dtype=np.uint8)
+    v = rng.integers(16, 241, (h, cw), dtype=np.uint8)
+    if kind == "PlanarYuv422":
+        d = s.FrameData.PlanarYuv422(s.YuvPlanes(y, u, v))
+    elif kind == "PlanarYuv444":
+        d = s.FrameData.PlanarYuv444(s.YuvPlanes(y, u, v))
+    else:
+        t = np.empty((h, w // 2, 4), np.uint8)
+        if kind == "InterleavedUyvy422":
+            t[..., 0], t[..., 1], t[..., 2], t[..., 3] = u, y[:, 0::2], v, y[:, 1::2]
+            d = s.FrameData.InterleavedUyvy422(t)
+        else:
+            t[..., 0], t[..., 1], t[..., 2], t[..., 3] = y[:, 0::2], u, y[:, 1::2], v
+            d = s.FrameData.InterleavedYuyv422(t)
+    return s.Frame(d, s.Resolution(w, h), pts)

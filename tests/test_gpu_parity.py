@@ -7,7 +7,7 @@ import pytest
 
 import smelter_b200 as s
 from tests import harness
-from tests.parity import OUTPUT_ID, assert_identical, nv12_frame, run_case, yuv_frame
+from tests.parity import OUTPUT_ID, assert_identical, nv12_frame, run_case, wide_chroma_frame, yuv_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -398,3 +398,48 @@ def test_two_ticks_in_flight_give_the_same_frames():
     r.wait()
     for got, exp in zip(outs[-1], expected[-1]):
         assert np.array_equal(got, exp.reshape(-1))
+
+
+WIDE_KINDS = ["PlanarYuv422", "PlanarYuv444", "InterleavedUyvy422", "InterleavedYuyv422"]
+
+
+@pytest.mark.parametrize("kind", WIDE_KINDS)
+def test_wide_chroma_input_formats(kind):
+    """SURVEY 8f-3: FrameData::{PlanarYuv422, PlanarYuv444, InterleavedUyvy422, InterleavedYuyv422} inputs
+    (input_texture.rs:86-150, interleaved_{uyvy,yuyv}_to_rgba.wgsl) -- 1:1 pass-through root, a Lanczos-scaled
+    tile next to a 4:2:0 one with rounded corners, and the CpuOptimized bilinear path"""
+    fr = wide_chroma_frame(kind, 11, 640, 360)
+    check(s.InputStreamComponent(input_id="input_1"), {"input_1": fr})
+    both = {"input_1": fr, "input_2": inputs(2)["input_2"]}
+    kids = [s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(20.0)) for c in streams(2)]
+    check(s.TilesComponent(children=kids, background_color=BG), both, out_format=NV12)
+    check(s.TilesComponent(children=streams(2), background_color=BG), both, mode=s.RenderingMode.CpuOptimized)
+
+
+@pytest.mark.parametrize("kind", ["InterleavedUyvy422", "PlanarYuv422"])
+def test_wide_chroma_input_odd_sizes(kind):
+    """odd width / height: the interleaved texture is floor(w/2) texels wide (texture/interleaved_yuv422.rs:18-22)
+    and the sampler clamps at its edge; planar 4:2:2 chroma is floor(w/2) wide"""
+    w, h = 321, 181
+    rng = np.random.default_rng(9)
+    if kind == "PlanarYuv422":
+        d = s.FrameData.PlanarYuv422(s.YuvPlanes(rng.integers(16, 236, (h, w), dtype=np.uint8),
+                                                 rng.integers(16, 241, (h, w // 2), dtype=np.uint8),
+                                                 rng.integers(16, 241, (h, w // 2), dtype=np.uint8)))
+    else:
+        d = s.FrameData.InterleavedUyvy422(rng.integers(16, 236, (h, w // 2, 4), dtype=np.uint8))
+    fr = s.Frame(d, s.Resolution(w, h))
+    check(V(children=[s.RescalerComponent(child=streams(1)[0])], background_color=BG), {"input_1": fr})
+    check(s.InputStreamComponent(input_id="input_1"), {"input_1": fr}, resolution=s.Resolution(w, h), out_format=RGBA)
+
+
+@pytest.mark.parametrize("fmt", [s.OutputFrameFormat.PlanarYuv422Bytes, s.OutputFrameFormat.PlanarYuv444Bytes])
+def test_planar_422_444_outputs(fmt):
+    """OutputFrameFormat::{PlanarYuv422Bytes, PlanarYuv444Bytes} (texture/planar_yuv.rs:72-83, rgba_to_yuv.rs:67-116):
+    tiles scene, pass-through root (same size and rescaled), missing input (black fill), odd output size"""
+    check(s.TilesComponent(children=streams(3), background_color=BG), inputs(3), out_format=fmt)
+    check(s.InputStreamComponent(input_id="input_1"), inputs(1), out_format=fmt)
+    check(s.InputStreamComponent(input_id="input_1"), inputs(1), out_format=fmt, resolution=s.Resolution(400, 300))
+    check(s.InputStreamComponent(input_id="input_1"), {}, out_format=fmt)
+    check(s.TilesComponent(children=streams(2), background_color=BG), inputs(2), out_format=fmt,
+          resolution=s.Resolution(501, 283))

@@ -182,3 +182,33 @@ def test_even_size_sampler_phases_exhaustive():
     L = orc.lib()
     L.orc_check_even_size_phases.restype = C.c_long
     assert L.orc_check_even_size_phases(8192) == 0
+
+
+def test_wide_chroma_restatements_are_consistent():
+    """No reference KAT exists for 4:2:2 / 4:4:4 / interleaved frames (parity for them is pinned only through the
+    arithmetic they share with the KAT-pinned 4:2:0 path).  Internal consistency of the restatement:
+    UYVY == YUYV of the same samples; interleaved (texel-centre chroma) == planar 4:4:4 with the chroma columns
+    duplicated; the general planar converter with (w/2, h/2) chroma == the 4:2:0 one; 4:4:4 / 4:2:2 outputs of a
+    flat colour == the 4:2:0 bytes."""
+    rng = np.random.default_rng(3)
+    w, h = 24, 10
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    u = rng.integers(16, 241, (h, w // 2), dtype=np.uint8)
+    v = rng.integers(16, 241, (h, w // 2), dtype=np.uint8)
+    uy = np.empty((h, w // 2, 4), np.uint8)
+    uy[..., 0], uy[..., 1], uy[..., 2], uy[..., 3] = u, y[:, 0::2], v, y[:, 1::2]
+    yu = np.empty((h, w // 2, 4), np.uint8)
+    yu[..., 0], yu[..., 1], yu[..., 2], yu[..., 3] = y[:, 0::2], u, y[:, 1::2], v
+    a = orc.interleaved422_to_rgba(uy, w, h, False)
+    assert np.array_equal(a, orc.interleaved422_to_rgba(yu, w, h, True))
+    assert np.array_equal(a, orc.yuv_planar_to_rgba(y, np.repeat(u, 2, 1), np.repeat(v, 2, 1), w, h, w, h))
+    assert np.array_equal(orc.yuv_planar_to_rgba(y, u[::2], v[::2], w, h, w // 2, h // 2),
+                          orc.yuv420_to_rgba(y, u[::2], v[::2], w, h))
+    # 4:2:2 input: chroma rows are exact, columns interpolate like 4:2:0 -> equals 4:2:0 applied to row-duplicated luma
+    flat = np.empty((h, w, 4), np.uint8)
+    flat[...] = (200, 40, 90, 255)
+    y0, u0, v0 = orc.rgba_to_yuv420_scaled(flat, w, h)
+    for cw, ch in ((w // 2, h), (w, h)):
+        y1, u1, v1 = orc.rgba_to_yuv_planar_scaled(flat, w, h, cw, ch)
+        assert np.array_equal(y0, y1) and u1.shape == (ch, cw)
+        assert len(np.unique(u1)) == 1 and u1[0, 0] == u0[0, 0] and v1[0, 0] == v0[0, 0]
