@@ -443,3 +443,45 @@ def test_planar_422_444_outputs(fmt):
     check(s.InputStreamComponent(input_id="input_1"), {}, out_format=fmt)
     check(s.TilesComponent(children=streams(2), background_color=BG), inputs(2), out_format=fmt,
           resolution=s.Resolution(501, 283))
+
+
+def test_strided_host_planes_in_and_out():
+    """SURVEY 8f-1 (ingest / egress glue): an AVFrame's planes carry a linesize larger than the row
+    (copy_plane_from_av, decoder/ffmpeg_utils.rs:67-79; write_plane_to_av_frame, encoder/ffmpeg_utils.rs:77-84).
+    The C ABI takes the pitch directly, so the repacking copy on both sides disappears: padded planes in and padded
+    planes out must give exactly the bytes of the packed call."""
+    from smelter_b200 import _ffi as F
+    w, h = 640, 360
+    fr = inputs(2)
+    scene = s.TilesComponent(children=streams(2), background_color=BG)
+    r = s.Renderer()
+    for i in fr:
+        r.register_input(i)
+    r.update_scene(OUTPUT_ID, s.Resolution(w, h), YUV, scene)
+    packed = [np.asarray(p) for p in r.render(s.FrameSet(frames=fr, pts=0.0)).frames[OUTPUT_ID].data.planes]
+
+    keep, arr = [], (F.InputFrame * 2)()
+    for k, (iid, f) in enumerate(fr.items()):
+        arr[k].input_id = iid.encode()
+        arr[k].format = F.FRAME_PLANAR_YUV420
+        arr[k].width, arr[k].height, arr[k].pts_ns, arr[k].mem_kind = w, h, 0, F.MEM_HOST
+        for p, pl in enumerate(f.data.planes):
+            pl = np.asarray(pl)
+            pitch = pl.shape[1] + 64 + 32 * p                       # linesize > width, different per plane
+            buf = np.full((pl.shape[0], pitch), 0xAB, np.uint8)
+            buf[:, :pl.shape[1]] = pl
+            keep.append(buf)
+            arr[k].planes[p], arr[k].pitch[p] = buf.ctypes.data, pitch
+    out = (F.OutputFrame * 1)()
+    out[0].output_id, out[0].mem_kind = OUTPUT_ID.encode(), F.MEM_HOST
+    obufs = []
+    for p, (rows, cols) in enumerate(((h, w), (h // 2, w // 2), (h // 2, w // 2))):
+        pitch = cols + 48
+        b = np.full((rows, pitch), 0xCD, np.uint8)
+        obufs.append(b)
+        out[0].planes[p], out[0].pitch[p] = b.ctypes.data, pitch
+    r.render_raw(0, arr, 2, out, 1, wait=True)
+    for p, b in enumerate(obufs):
+        cols = packed[p].shape[1]
+        assert np.array_equal(b[:, :cols], packed[p]), f"plane {p}"
+        assert np.all(b[:, cols:] == 0xCD), "padding bytes must stay untouched"
