@@ -392,7 +392,7 @@ def main():
                 arr[k].mem_kind = F.MEM_HOST
                 arr[k].planes[0], arr[k].planes[1] = hys[b][k].data_ptr(), huvs[b][k].data_ptr()
             host_out.append(arr)
-        ke = max(5, min(args.steps, 30))
+        ke = max(5, min(args.steps, 200))   # enough ticks that one host hiccup cannot dominate sub-ms ticks
         for k in range(3):
             r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=True)
         barrier()

@@ -534,9 +534,12 @@ struct W64 {
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int S, bool NV12>
+// SRC: 0 planar 4:2:0 (K1), 1 NV12 (K2), 2 UYVY, 3 YUYV (K3: texel-centre chroma, no interpolation -- for even
+// widths >= 8 the shader's coordinate round trip lands on pixel x's own texel (x >> 1) with weight exactly 1)
+template <int S, int SRC>
 __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const FusedJob *jobs, const FusedPiece *pieces,
                                                                             const int *piece_begin) {
+    constexpr bool NV12 = SRC == 1, IL = SRC >= 2;
     using K = W64<S>;
     constexpr int TAPS = K::TAPS;  // S > 0: exact tap count; S == 0: upper bound (the job's taps_h is used)
     constexpr int WIN = S + TAPS;  // S > 0: window feeding 2 adjacent output columns
@@ -582,7 +585,9 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
     const int full_range = src.full_range;
     const float *ytab = full_range ? M.T.u8n : M.T.yl;
     // pairs whose pixels and chroma taps need no clamping: x = xa_e + 2p >= 2 and x + 3 <= W - 1
-    const int p_in_lo = xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1, p_in_hi = (W - 4 - xa_e) >> 1;
+    // (interleaved sources have no chroma neighbours: x >= 0 and x + 1 <= W - 1)
+    const int p_in_lo = IL ? (xa_e >= 0 ? 0 : (1 - xa_e) >> 1) : (xa_e >= 2 ? 0 : (2 - xa_e + 1) >> 1);
+    const int p_in_hi = IL ? (W - 2 - xa_e) >> 1 : (W - 4 - xa_e) >> 1;
     const int p_hi = min(p_in_hi, npairs - 1);   // last pair of the strip on the unclamped path
     // S > 0: pixel x is stored at slot x - xa so that lane l's window starts at slot 2*S*l (compile-time offsets)
     const int dsh = S == 0 ? 0 : d0;
@@ -598,7 +603,8 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
             const int nr = need_hi + 1 + (tid >> 3), part = tid & 7;  // 32 luma rows x (3 luma + 3 chroma lines)
             if (nr < H && part < 6) {
                 const int xb = min(max(xa_e, 0), W - 1);
-                if (part < 3) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(xb + part * 128, W - 1));
+                if (IL) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(2 * xb + part * 128, 2 * W - 1));
+                else if (part < 3) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(xb + part * 128, W - 1));
                 else if ((nr & 1) == 0) {
                     const int cyn = min(nr >> 1, chei - 1);
                     if (NV12) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + min(xb + (part - 3) * 128, W - 2));
@@ -613,15 +619,19 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
             {
                 const uint8_t *yrow = src.p0 + (size_t)r * src.pitch0;
                 const int cy0 = (r & 1) ? (r >> 1) : max((r >> 1) - 1, 0), cy1 = (r & 1) ? min((r >> 1) + 1, chei - 1) : (r >> 1);
-                const uint8_t *c0a = src.p1 + (size_t)cy0 * src.pitch1, *c1a = src.p1 + (size_t)cy1 * src.pitch1;
-                const uint8_t *c0b = NV12 ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
-                const uint8_t *c1b = NV12 ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
+                const uint8_t *c0a = IL ? nullptr : src.p1 + (size_t)cy0 * src.pitch1, *c1a = IL ? nullptr : src.p1 + (size_t)cy1 * src.pitch1;
+                const uint8_t *c0b = (NV12 || IL) ? nullptr : src.p2 + (size_t)cy0 * src.pitch2;
+                const uint8_t *c1b = (NV12 || IL) ? nullptr : src.p2 + (size_t)cy1 * src.pitch2;
                 const bool odd = r & 1;
                 // raw bytes of one pixel pair, each in a full register: luma pair (y0 | y1 << 8) and the three chroma
                 // taps of both chroma rows (NV12: u | v << 8 as loaded; planar: u | v << 16)
                 struct Raw { unsigned y, a0, b0, d0, a1, b1, d1; };
                 auto load_raw = [&](int pp, Raw &R) {
                     const int x = xa_e + 2 * pp, cx = x >> 1;
+                    if (IL) {   // one texel = the pixel pair: {U,Y0,V,Y1} or {Y0,U,Y1,V}
+                        R.y = __ldg(reinterpret_cast<const unsigned int *>(yrow) + cx);
+                        return;
+                    }
                     if (NV12) {
                         const unsigned short *r0 = reinterpret_cast<const unsigned short *>(c0a) + cx;
                         const unsigned short *r1 = reinterpret_cast<const unsigned short *>(c1a) + cx;
@@ -642,6 +652,19 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                     row[K::pos(i)] = make_float4(M.T.dec[r8], M.T.dec[g8], M.T.dec[b8], 0.0f);
                 };
                 auto convert_store = [&](const Raw &R, int p) {
+                    if constexpr (IL) {
+                        const unsigned t = R.y;
+                        const unsigned ub = SRC == 2 ? (t & 0xffu) : ((t >> 8) & 0xffu), vb = SRC == 2 ? ((t >> 16) & 0xffu) : (t >> 24);
+                        const unsigned y0 = SRC == 2 ? ((t >> 8) & 0xffu) : (t & 0xffu), y1 = SRC == 2 ? (t >> 24) : ((t >> 16) & 0xffu);
+                        const float u = M.T.u8n[ub], v = M.T.u8n[vb];   // texel hit: exactly b / 255 (NC-1)
+                        const int i = 2 * p - dsh;
+                        int r8, g8, b8;
+                        yuv_to_rgb8n(M.T.yl[y0], u, v, 0, r8, g8, b8);
+                        if (i >= 0) put(i, r8, g8, b8);
+                        yuv_to_rgb8n(M.T.yl[y1], u, v, 0, r8, g8, b8);
+                        put(i + 1, r8, g8, b8);
+                        return;
+                    }
                     // NC-6u chroma: u in bits 0..15, v in bits 16..31 of one register (max 4080 < 65536)
                     const unsigned a0 = spread(R.a0), b0 = 3u * spread(R.b0), e0 = spread(R.d0);
                     const unsigned a1 = spread(R.a1), b1 = 3u * spread(R.b1), e1 = spread(R.d1);
@@ -762,33 +785,41 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
     }  // pieces
 }
 
-template <int S, bool NV12>
+template <int S, int SRC>
 static bool launch_fused_int(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks,
                              cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_resample_fused_int<S, NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_resample_fused_int<S, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(typename W64<S>::Smem));
         attr_set = true;
     }
-    k_resample_fused_int<S, NV12><<<nblocks, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev, pieces, piece_begin);
+    k_resample_fused_int<S, SRC><<<nblocks, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev, pieces, piece_begin);
     return check_launch("k_resample_fused_int");
 }
 
-int launch_resample_fused(int variant, bool nv12, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
+template <int S>
+static bool launch_fused_src(int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev, const int *piece_begin_dev,
+                             int nblocks, cudaStream_t st) {
+    switch (src) {
+        case 0: return launch_fused_int<S, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st);
+        case 1: return launch_fused_int<S, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st);
+        case 2: return launch_fused_int<S, 2>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st);
+        default: return launch_fused_int<S, 3>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st);
+    }
+}
+
+// src: 0 planar 4:2:0, 1 NV12, 2 UYVY, 3 YUYV (fused_source_class)
+int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
                           const int *piece_begin_dev, int nblocks, Stream s) {
     if (nblocks <= 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
     bool ok = false;
     switch (variant) {
-        case 2: ok = nv12 ? launch_fused_int<2, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
-                          : launch_fused_int<2, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
-        case 3: ok = nv12 ? launch_fused_int<3, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
-                          : launch_fused_int<3, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
-        case 4: ok = nv12 ? launch_fused_int<4, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
-                          : launch_fused_int<4, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
-        default: ok = nv12 ? launch_fused_int<0, true>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
-                           : launch_fused_int<0, false>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 2: ok = launch_fused_src<2>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 3: ok = launch_fused_src<3>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 4: ok = launch_fused_src<4>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        default: ok = launch_fused_src<0>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
     }
     return ok ? 1 : -1;
 }

@@ -155,7 +155,11 @@ typedef void *Stream;  // cudaStream_t
 int launch_convert_to_rgba(const Tex &src, uint8_t *dst, int dst_pitch, Stream s);
 int launch_weights(const WeightJob *jobs_dev, const WeightJob *jobs_host, int n_jobs, Stream s);
 int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, int n_jobs, Stream s);
-int launch_resample_fused(int variant, bool nv12, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
+// source class of the fused kernel's template: 0 planar 4:2:0, 1 NV12, 2 UYVY, 3 YUYV; -1 not supported
+inline int fused_source_class(int tex_kind) {
+    return tex_kind == TEX_YUV420 ? 0 : tex_kind == TEX_NV12 ? 1 : tex_kind == TEX_UYVY ? 2 : tex_kind == TEX_YUYV ? 3 : -1;
+}
+int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
                           const int *piece_begin_dev, int nblocks, Stream s);
 // integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping
 void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s);

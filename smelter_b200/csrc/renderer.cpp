@@ -541,8 +541,11 @@ int Renderer::materialised_input(Input &in) {
 // (the generic multi-pass path is used), -2 on error.
 int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMapping &vm, int dw, int dh) {
     const dev::Tex &t = in.tex;
-    if (t.kind != dev::TEX_YUV420 && t.kind != dev::TEX_NV12) return -1;
-    if ((t.width | t.height) & 1) return -1;
+    const int src_class = dev::fused_source_class(t.kind);
+    if (src_class < 0) return -1;
+    if (src_class < 2 && ((t.width | t.height) & 1)) return -1;
+    // interleaved 4:2:2: texel-centre fast form holds for even widths >= 8 and 4-byte aligned rows
+    if (src_class >= 2 && ((t.width & 1) || t.width < 8 || (t.pitch0 & 3) || ((uintptr_t)t.p0 & 3))) return -1;
     if (hm.predecimate_levels() != 0 || vm.predecimate_levels() != 0) return -1;
     KernelPass passes[2];
     if (plan_passes(hm, vm, passes) != 2 || passes[0].mapping.axis != 0) return -1;
@@ -1113,18 +1116,18 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     wj_off = param_alloc(sizeof(dev::WeightJob) * std::max<size_t>(weight_jobs_.size(), 1));
     size_t fj_off = param_alloc(sizeof(dev::FusedJob) * std::max<size_t>(fused_jobs_.size(), 1));
     // partition the fused resamples of the tick over a persistent grid, one launch per kernel variant
-    struct FusedLaunch { int variant; bool nv12; size_t pieces_off, begin_off; int nblocks; };
+    struct FusedLaunch { int variant; int src; size_t pieces_off, begin_off; int nblocks; };
     std::vector<FusedLaunch> fused_launches;
     {
-        std::vector<std::pair<int, bool>> variants;
+        std::vector<std::pair<int, int>> variants;
         for (const dev::FusedJob &j : fused_jobs_) {
-            std::pair<int, bool> v{j.variant, j.src.kind == dev::TEX_NV12};
+            std::pair<int, int> v{j.variant, dev::fused_source_class(j.src.kind)};
             if (std::find(variants.begin(), variants.end(), v) == variants.end()) variants.push_back(v);
         }
         for (auto &v : variants) {
             long long total = 0;
             for (const dev::FusedJob &j : fused_jobs_)
-                if (j.variant == v.first && (j.src.kind == dev::TEX_NV12) == v.second)
+                if (j.variant == v.first && dev::fused_source_class(j.src.kind) == v.second)
                     total += (long long)((j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols) * j.dst_h;
             if (total <= 0) continue;
             int nblocks = (int)std::min<long long>((long long)sm_count_ * 3, (total + 7) / 8);
@@ -1134,7 +1137,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             long long room = per_block;
             for (size_t ji = 0; ji < fused_jobs_.size(); ji++) {
                 const dev::FusedJob &j = fused_jobs_[ji];
-                if (j.variant != v.first || (j.src.kind == dev::TEX_NV12) != v.second) continue;
+                if (j.variant != v.first || dev::fused_source_class(j.src.kind) != v.second) continue;
                 int strips = (j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols;
                 for (int st = 0; st < strips; st++) {
                     int y = 0;
@@ -1148,7 +1151,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             }
             if (begin.back() != (int)pieces.size()) begin.push_back((int)pieces.size());
             FusedLaunch fl;
-            fl.variant = v.first; fl.nv12 = v.second; fl.nblocks = (int)begin.size() - 1;
+            fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
             fl.pieces_off = param_alloc(sizeof(dev::FusedPiece) * pieces.size());
             fl.begin_off = param_alloc(sizeof(int) * begin.size());
             if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
@@ -1183,7 +1186,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     for (auto &pw : pending_int_weights_) dev::set_int_weights(pw.first, pw.second.weights, pw.second.inv, pw.second.taps, stream_);
     pending_int_weights_.clear();
     for (const FusedLaunch &fl : fused_launches) {
-        if (!launched(dev::launch_resample_fused(fl.variant, fl.nv12, (const dev::FusedJob *)(pd + fj_off),
+        if (!launched(dev::launch_resample_fused(fl.variant, fl.src, (const dev::FusedJob *)(pd + fj_off),
                                                  (const dev::FusedPiece *)(pd + fl.pieces_off), (const int *)(pd + fl.begin_off),
                                                  fl.nblocks, stream_))) goto fail;
         prof_mark(SMR_KERNEL_RESAMPLE_FUSED);

@@ -485,3 +485,18 @@ def test_strided_host_planes_in_and_out():
         cols = packed[p].shape[1]
         assert np.array_equal(b[:, :cols], packed[p]), f"plane {p}"
         assert np.all(b[:, cols:] == 0xCD), "padding bytes must stay untouched"
+
+
+@pytest.mark.parametrize("kind", ["InterleavedUyvy422", "InterleavedYuyv422"])
+def test_interleaved_inputs_through_fused_resampler(kind):
+    """capture-card frames (UYVY / YUYV) through the fused convert+Lanczos kernel: exact 4:1 (25 taps), 3:1 and a
+    fractional ratio, including the clamped strips at both image edges"""
+    big = {f"input_{i}": wide_chroma_frame(kind, 20 + i, 1280, 720) for i in range(1, 5)}
+    check(s.TilesComponent(children=streams(4), background_color=BG), big, out_format=NV12)           # 4:1
+    one = {"input_1": wide_chroma_frame(kind, 31, 960, 540)}
+    check(V(children=[s.RescalerComponent(child=streams(1)[0],
+                                          position=s.Position.Absolute(width=320.0, height=180.0, left=40.0, top=30.0))],
+            background_color=BG), one)                                                                  # 3:1
+    check(V(children=[s.RescalerComponent(child=streams(1)[0],
+                                          position=s.Position.Absolute(width=417.0, height=233.0, left=11.0, top=7.0))],
+            background_color=BG), one)                                                                  # fractional
