@@ -236,6 +236,13 @@ smr_status smr_render_begin(smr_renderer *r, uint64_t pts_ns, const smr_input_fr
                             smr_output_frame *outputs, uint32_t n_outputs);
 smr_status smr_render_end(smr_renderer *r);
 
+/* FramePreProcessor::process_to_bytes (state/frame_pre_processor.rs:81-100): one frame in any input format ->
+ * RGBA8 bytes of its node texture (sRGB-encoded in GpuOptimized), optionally rescaled with the linear sampler
+ * (rgba_rescale.wgsl) to out_width x out_height; 0 x 0 keeps the source resolution.  Blocking, like the reference.
+ * `rgba` has out_height rows of `pitch` bytes (0 = tightly packed), host or device memory per `mem_kind`. */
+smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *frame, uint32_t out_width, uint32_t out_height,
+                                void *rgba, uint32_t pitch, int32_t mem_kind);
+
 /* byte sizes of the planes smr_render writes for an output (0 for unused planes) */
 smr_status smr_output_plane_sizes(uint32_t width, uint32_t height, int32_t output_format, size_t sizes[3]);
 

@@ -169,6 +169,15 @@ def rgba_to_yuv_planar_scaled(rgba, w, h, cw, ch):
     return y, u, v
 
 
+def rescale_rgba(rgba, ow, oh, mode=0):
+    """FramePreProcessor rescale: bilinear (NC-6) sample of the node texture, stored through the target format"""
+    rgba = _u8(rgba)
+    sh, sw = rgba.shape[:2]
+    out = np.empty((oh, ow, 4), np.uint8)
+    lib().orc_rescale_rgba(_p(rgba), sw, sh, ow, oh, int(mode), _p(out))
+    return out
+
+
 def rgba_to_nv12_scaled(rgba, w, h):
     rgba = _u8(rgba)
     sh, sw = rgba.shape[:2]

@@ -662,6 +662,23 @@ static inline void sample_node(const orc_texture *t, int mode, float tx, float t
     }
 }
 
+/* FramePreProcessor::rescale_node_texture (state/frame_pre_processor.rs:117-132) with rgba_rescale.wgsl:24-27:
+ * one full-target draw, `blend: None` (rgba_rescale.rs:38-42): each target pixel is the linear-filtered sample of
+ * the node texture at its centre, stored through the target format (sRGB encode in GpuOptimized, plain UNORM8 in
+ * CpuOptimized; RescaleTexture::new :199-206). */
+void orc_rescale_rgba(const uint8_t *rgba, int sw, int sh, int ow, int oh, int mode, uint8_t *out) {
+    orc_texture t = {sw, sh, rgba};
+#pragma omp parallel for schedule(static)
+    for (int py = 0; py < oh; py++)
+        for (int px = 0; px < ow; px++) {
+            float sm[4];
+            sample_node(&t, mode, ((float)px + 0.5f) / (float)ow, ((float)py + 0.5f) / (float)oh, sm);
+            uint8_t *o = out + ((size_t)py * ow + px) * 4;
+            for (int c = 0; c < 3; c++) o[c] = mode == ORC_MODE_GPU_OPTIMIZED ? orc_srgb_encode_u8(sm[c]) : orc_unorm8(sm[c]);
+            o[3] = orc_unorm8(sm[3]);
+        }
+}
+
 /* PREMULTIPLIED_ALPHA_BLENDING through the node texture's view (common_pipeline.rs:125) */
 static inline void blend_store(uint8_t *dst, const float src_in[4], int mode) {
     float s[4];

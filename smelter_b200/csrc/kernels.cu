@@ -1496,6 +1496,34 @@ int launch_output(const OutputJob &job, Stream s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// FramePreProcessor (state/frame_pre_processor.rs): K1..K4 to RGBA8, optional rescale (rgba_rescale.wgsl, blend: None)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_preprocess(Tex src, int mode, int rescale, uint8_t *out, int out_pitch, int ow, int oh) {
+    __shared__ Tables T;
+    load_tables(T);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ow || y >= oh) return;
+    uchar4 o;
+    if (!rescale) {
+        o = node_texel(T, src, x, y);
+    } else {
+        bool exact;
+        uchar4 texel;
+        const float4 sm = sample_node(T, &src, mode, ((float)x + 0.5f) / (float)ow, ((float)y + 0.5f) / (float)oh, exact, texel);
+        if (exact) o = texel;   // encode(decode(b)) == b, unorm8(b / 255) == b
+        else if (mode == 0) o = make_uchar4(srgb_encode(T, sm.x), srgb_encode(T, sm.y), srgb_encode(T, sm.z), unorm8(sm.w));
+        else o = make_uchar4(unorm8(sm.x), unorm8(sm.y), unorm8(sm.z), unorm8(sm.w));
+    }
+    reinterpret_cast<uchar4 *>(out + (size_t)y * out_pitch)[x] = o;
+}
+
+int launch_preprocess(const Tex &src, int mode, int rescale, uint8_t *out, int out_pitch, int out_w, int out_h, Stream s) {
+    dim3 b(32, 8), g((out_w + 31) / 32, (out_h + 7) / 8);
+    k_preprocess<<<g, b, 0, (cudaStream_t)s>>>(src, mode, rescale, out, out_pitch, out_w, out_h);
+    return check_launch("k_preprocess") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: black frame (render_loop.rs:127-173)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,

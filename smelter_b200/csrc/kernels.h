@@ -159,6 +159,8 @@ int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, i
 inline int fused_source_class(int tex_kind) {
     return tex_kind == TEX_YUV420 ? 0 : tex_kind == TEX_NV12 ? 1 : tex_kind == TEX_UYVY ? 2 : tex_kind == TEX_YUYV ? 3 : -1;
 }
+// FramePreProcessor: node texture of `src` (rescale = 0) or its linear-filtered rescale to out_w x out_h
+int launch_preprocess(const Tex &src, int mode, int rescale, uint8_t *out, int out_pitch, int out_w, int out_h, Stream s);
 int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
                           const int *piece_begin_dev, int nblocks, Stream s);
 // integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping

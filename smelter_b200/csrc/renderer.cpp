@@ -179,6 +179,7 @@ class Renderer {
     smr_status unregister_output(const char *id);
     smr_status render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out, uint32_t n_out);
     smr_status render_end();
+    smr_status preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch, int32_t mem_kind);
     smr_status debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
     smr_status debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap, uint32_t *n,
                              uint32_t *rw, uint32_t *rh);
@@ -291,6 +292,7 @@ class Renderer {
     }
     void fold_profile();
     bool host_only_ = false;
+    DevBuf pre_planes_[3], pre_out_;   // FramePreProcessor scratch (input_texture / rescale_texture / download_buffer)
     // optional per-kernel-class device timing (cudaEvents on the launching stream)
     void prof_mark(int kernel_class);
     bool profiling_ = false;
@@ -450,6 +452,22 @@ static bool plane_layout(int fmt, uint32_t w, uint32_t h, int plane, size_t &row
     }
 }
 
+static bool tex_kind_of_format(int fmt, dev::Tex &t) {   // FrameData variant -> texture kind (input_texture.rs:69-150)
+    switch (fmt) {
+        case SMR_FRAME_PLANAR_YUV420: t.kind = dev::TEX_YUV420; return true;
+        case SMR_FRAME_PLANAR_YUVJ420: t.kind = dev::TEX_YUV420; t.full_range = 1; return true;
+        case SMR_FRAME_NV12: t.kind = dev::TEX_NV12; return true;
+        case SMR_FRAME_BGRA: t.kind = dev::TEX_BGRA; return true;
+        case SMR_FRAME_ARGB: t.kind = dev::TEX_ARGB; return true;
+        case SMR_FRAME_RGBA8: t.kind = dev::TEX_RGBA8; return true;
+        case SMR_FRAME_PLANAR_YUV422: t.kind = dev::TEX_YUV422; return true;
+        case SMR_FRAME_PLANAR_YUV444: t.kind = dev::TEX_YUV444; return true;
+        case SMR_FRAME_UYVY422: t.kind = dev::TEX_UYVY; return true;
+        case SMR_FRAME_YUYV422: t.kind = dev::TEX_YUYV; return true;
+        default: return false;
+    }
+}
+
 smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in) {
     for (auto &kv : inputs_) {
         Input &I = kv.second;
@@ -467,19 +485,7 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
             return SMR_ERR_INVALID_ARGUMENT;
         }
         dev::Tex t;
-        switch (f->format) {
-            case SMR_FRAME_PLANAR_YUV420: t.kind = dev::TEX_YUV420; break;
-            case SMR_FRAME_PLANAR_YUVJ420: t.kind = dev::TEX_YUV420; t.full_range = 1; break;
-            case SMR_FRAME_NV12: t.kind = dev::TEX_NV12; break;
-            case SMR_FRAME_BGRA: t.kind = dev::TEX_BGRA; break;
-            case SMR_FRAME_ARGB: t.kind = dev::TEX_ARGB; break;
-            case SMR_FRAME_RGBA8: t.kind = dev::TEX_RGBA8; break;
-            case SMR_FRAME_PLANAR_YUV422: t.kind = dev::TEX_YUV422; break;
-            case SMR_FRAME_PLANAR_YUV444: t.kind = dev::TEX_YUV444; break;
-            case SMR_FRAME_UYVY422: t.kind = dev::TEX_UYVY; break;
-            case SMR_FRAME_YUYV422: t.kind = dev::TEX_YUYV; break;
-            default: set_error("unsupported input frame format"); return SMR_ERR_UNSUPPORTED;
-        }
+        if (!tex_kind_of_format(f->format, t)) { set_error("unsupported input frame format"); return SMR_ERR_UNSUPPORTED; }
         t.width = (int)f->width; t.height = (int)f->height;
         const uint8_t *ptrs[3] = {nullptr, nullptr, nullptr};
         int pitches[3] = {0, 0, 0};
@@ -741,6 +747,67 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
         }
     }
     skip = false;
+}
+
+// FramePreProcessor::process_to_bytes / process_to_texture (state/frame_pre_processor.rs:60-100)
+smr_status Renderer::preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch,
+                                      int32_t mem_kind) {
+    if (!f || !rgba) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (host_only_) { set_error("host-only handle (cuda_device = -1) has no device: no CPU fallback"); return SMR_ERR_CUDA; }
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    if (f->width < 2 || f->height < 2 || f->width > 16384 || f->height > 16384) {
+        set_error("input frame resolution out of range");
+        return SMR_ERR_INVALID_ARGUMENT;
+    }
+    const bool rescale = ow != 0 || oh != 0;
+    if (!rescale) { ow = f->width; oh = f->height; }
+    if (ow == 0 || oh == 0 || ow > 16384 || oh > 16384) { set_error("output resolution out of range"); return SMR_ERR_INVALID_ARGUMENT; }
+    dev::Tex t;
+    if (!tex_kind_of_format(f->format, t)) { set_error("unsupported input frame format"); return SMR_ERR_UNSUPPORTED; }
+    t.width = (int)f->width; t.height = (int)f->height;
+    const uint8_t *ptrs[3] = {nullptr, nullptr, nullptr};
+    int pitches[3] = {0, 0, 0};
+    for (int p = 0; p < 3; p++) {
+        size_t row_bytes = 0, rows = 0;
+        if (!plane_layout(f->format, f->width, f->height, p, row_bytes, rows)) continue;
+        if (!f->planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
+        size_t spitch = f->pitch[p] ? f->pitch[p] : row_bytes;
+        if (f->mem_kind == SMR_MEM_DEVICE) {
+            ptrs[p] = (const uint8_t *)f->planes[p];
+            pitches[p] = (int)spitch;
+        } else {
+            if (row_bytes * rows > pre_planes_[p].cap) CUDA_OK(cudaStreamSynchronize(stream_));
+            CUDA_OK(pre_planes_[p].ensure(row_bytes * rows));
+            CUDA_OK(cudaMemcpy2DAsync(pre_planes_[p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
+                                      cudaMemcpyHostToDevice, stream_));
+            stats_.h2d_bytes += row_bytes * rows;
+            ptrs[p] = pre_planes_[p].p;
+            pitches[p] = (int)row_bytes;
+        }
+    }
+    t.p0 = ptrs[0]; t.p1 = ptrs[1]; t.p2 = ptrs[2];
+    t.pitch0 = pitches[0]; t.pitch1 = pitches[1]; t.pitch2 = pitches[2];
+    const size_t row = (size_t)ow * 4, user_pitch = pitch ? pitch : row;
+    if (user_pitch < row) { set_error("output pitch smaller than a row"); return SMR_ERR_BUFFER_TOO_SMALL; }
+    uint8_t *dst = (uint8_t *)rgba;
+    size_t dpitch = user_pitch;
+    if (mem_kind != SMR_MEM_DEVICE) {
+        if (row * oh > pre_out_.cap) CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(pre_out_.ensure(row * oh));
+        dst = pre_out_.p; dpitch = row;
+    }
+    if (dev::launch_preprocess(t, opts_.rendering_mode, rescale ? 1 : 0, dst, (int)dpitch, (int)ow, (int)oh, stream_) < 0) {
+        set_error(dev::last_launch_error());
+        return SMR_ERR_CUDA;
+    }
+    stats_.kernel_launches++;
+    if (mem_kind != SMR_MEM_DEVICE) {
+        CUDA_OK(cudaMemcpy2DAsync(rgba, user_pitch, dst, dpitch, row, oh, cudaMemcpyDeviceToHost, stream_));
+        stats_.d2h_bytes += row * oh;
+    }
+    CUDA_OK(cudaStreamSynchronize(stream_));   // the reference blocks in device.poll (frame_pre_processor.rs:171-176)
+    return SMR_OK;
 }
 
 smr_status Renderer::get_weights(const KernelPass &p, WeightEntry &out) {
@@ -1451,6 +1518,8 @@ smr_status smr_unregister_output(smr_renderer *r, const char *id) { SMR_GUARD(r-
 smr_status smr_render_begin(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in,
                             smr_output_frame *out, uint32_t n_out) { SMR_GUARD(r->impl.render_begin(pts, in, n_in, out, n_out)) }
 smr_status smr_render_end(smr_renderer *r) { SMR_GUARD(r->impl.render_end()) }
+smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch,
+                                int32_t mem_kind) { SMR_GUARD(r->impl.preprocess_frame(f, ow, oh, rgba, pitch, mem_kind)) }
 smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,
                       uint32_t n_out) {
     if (!r) return SMR_ERR_INVALID_ARGUMENT;

@@ -133,6 +133,16 @@ class FrameSet:
     pts: float = 0.0
 
 
+class FramePreProcessor:
+    """smelter_render::FramePreProcessor (state/frame_pre_processor.rs:33-116) over a Renderer handle."""
+
+    def __init__(self, renderer):
+        self._r = renderer
+
+    def process_to_bytes(self, frame: "Frame", resolution: Optional["Resolution"] = None) -> np.ndarray:
+        return self._r.preprocess_frame(frame, resolution)
+
+
 # ------------------------------------------------------------------------------------------------
 # scene types (scene/types.rs, scene/components.rs) -- same field names and defaults
 # ------------------------------------------------------------------------------------------------
@@ -520,6 +530,17 @@ class Renderer:
                 data = FrameData.Rgba8(pl[0].reshape(h, w, 4))
             result.frames[oid] = Frame(data, Resolution(w, h), input.pts)
         return result
+
+    def preprocess_frame(self, frame: Frame, resolution: Optional[Resolution] = None) -> np.ndarray:
+        """FramePreProcessor::process_to_bytes (state/frame_pre_processor.rs:81-100): one frame -> RGBA8 bytes of
+        its node texture, optionally rescaled (linear sampler) to `resolution`.  Returns an (h, w, 4) uint8 array."""
+        keep = []
+        arr = self._input_frames(FrameSet(frames={"_": frame}), keep)
+        ow, oh = (resolution.width, resolution.height) if resolution else (0, 0)
+        w, h = (ow, oh) if resolution else (frame.resolution.width, frame.resolution.height)
+        out = np.empty((h, w, 4), np.uint8)
+        self._check(self._lib.smr_preprocess_frame(self._h, arr, ow, oh, out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
+        return out
 
     # -- zero-copy path (device pointers in and out; used by bench.py's `value` leg) ---------------
     def render_raw(self, pts_ns, in_arr, n_in, out_arr, n_out, wait=True):

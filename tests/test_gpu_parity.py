@@ -500,3 +500,27 @@ def test_interleaved_inputs_through_fused_resampler(kind):
     check(V(children=[s.RescalerComponent(child=streams(1)[0],
                                           position=s.Position.Absolute(width=417.0, height=233.0, left=11.0, top=7.0))],
             background_color=BG), one)                                                                  # fractional
+
+
+@pytest.mark.parametrize("mode", [s.RenderingMode.GpuOptimized, s.RenderingMode.CpuOptimized])
+def test_frame_pre_processor(mode):
+    """FramePreProcessor::process_to_bytes (state/frame_pre_processor.rs:81-100, rgba_rescale.wgsl): every input
+    format to RGBA8 at the source resolution, and rescaled down / up (exact 2:1, fractional, odd target) with the
+    linear sampler through the mode's target format; BGRA keeps its alpha"""
+    from tests.parity import node_texture
+    from oracle import oracle as orc
+    r = s.Renderer(s.RendererOptions(rendering_mode=mode))
+    pre = s.FramePreProcessor(r)
+    w, h = 320, 180
+    rng = np.random.default_rng(77)
+    frames = [inputs(1, w, h)["input_1"], nv12_frame(harness.smooth_yuv420(5, w, h), w, h),
+              wide_chroma_frame("InterleavedUyvy422", 3, w, h), wide_chroma_frame("PlanarYuv444", 4, w, h),
+              s.Frame(s.FrameData.Bgra(rng.integers(0, 256, (h, w, 4), dtype=np.uint8)), s.Resolution(w, h))]
+    omode = 0 if mode == s.RenderingMode.GpuOptimized else 1
+    for fr in frames:
+        node = node_texture(fr)
+        assert np.array_equal(pre.process_to_bytes(fr), node), fr.data.kind
+        for ow, oh in ((160, 90), (211, 97), (480, 271)):
+            got = pre.process_to_bytes(fr, s.Resolution(ow, oh))
+            exp = orc.rescale_rgba(node, ow, oh, omode)
+            assert_identical((got,), (exp,), f"{fr.data.kind} -> {ow}x{oh}")
