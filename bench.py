@@ -393,17 +393,21 @@ def main():
                 arr[k].planes[0], arr[k].planes[1] = hys[b][k].data_ptr(), huvs[b][k].data_ptr()
             host_out.append(arr)
         ke = max(5, min(args.steps, 200))   # enough ticks that one host hiccup cannot dominate sub-ms ticks
+        def step_host(k, wait):
+            for a in host_in[k % hv]:
+                a.pts_ns = k * frame_ns          # fresh frames every tick (a frame older than the fallback timeout is dropped)
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=wait)
         for k in range(3):
-            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=True)
+            step_host(k, True)
         barrier()
         st0 = r.stats()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ee0.record(stream)
         acc = 0
-        r.render_raw(0, host_in[0], n, host_out[0], n_out, wait=False)
+        step_host(0, False)
         for k in range(1, ke):
-            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=False)
+            step_host(k, False)
             r.wait()                                   # retires tick k-1
             acc += int(hys[(k - 1) & 1][0][0, 0])      # the step's result is read on the host
         r.wait()
@@ -418,6 +422,8 @@ def main():
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        h2d_expected = n * iw * ih * 3 // 2
+        assert (st1["h2d_bytes"] - st0["h2d_bytes"]) == h2d_expected * ke, "e2e leg: some ticks did not upload their inputs"
         e2e = {"value": world * n_out * ke / e2e_s, "unit": "frames/s", "steps": ke,
                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // ke,
                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // ke}

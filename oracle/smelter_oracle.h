@@ -15,7 +15,9 @@
  *   - smelter-render/src/scene/transition/cubic_bezier.rs tests
  * Beyond those vectors: **parity unpinned** (GPU fixed-function behaviour -- sRGB conversion,
  * UNORM rounding, bilinear weight precision, rasteriser snapping -- is restated from the
- * WebGPU/Vulkan rules, see DESIGN.md "numeric contract").
+ * WebGPU/Vulkan rules, see DESIGN.md "numeric contract").  The planar 4:2:2 / 4:4:4, interleaved
+ * UYVY / YUYV and FramePreProcessor-rescale restatements have NO reference vector at all (the reference
+ * tests them through snapshots only): parity unpinned for them.
  *
  * Every function cites the reference file:line it follows.
  */

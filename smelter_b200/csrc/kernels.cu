@@ -532,7 +532,15 @@ struct W64 {
     static __device__ __forceinline__ int pos(int i) { return S == 0 ? i : i + i / (2 * SS); }
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Pull [p, p + bytes) towards L2, clipped to the plane [lo, hi): one bulk prefetch of exactly the span (16-byte
+// granules) instead of whole 128-byte lines -- neighbouring strips' lines are not dragged in a second time.
+__device__ __forceinline__ void prefetch_l2_span(const uint8_t *p, int bytes, const uint8_t *lo, const uint8_t *hi) {
+    unsigned long long a = (unsigned long long)(p < lo ? lo : p), e = (unsigned long long)(p + bytes < hi ? p + bytes : hi);
+    a = (a + 15ull) & ~15ull;
+    if (e <= a + 16ull) return;
+    const unsigned size = (unsigned)((e - a) & ~15ull);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(size) : "memory");
+}
 
 // SRC: 0 planar 4:2:0 (K1), 1 NV12 (K2), 2 UYVY, 3 YUYV (K3: texel-centre chroma, no interpolation -- for even
 // widths >= 8 the shader's coordinate round trip lands on pixel x's own texel (x >> 1) with weight exactly 1)
@@ -598,17 +606,24 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
         const int need_lo = min(max(__ldg(J.first_v + o0), 0), H - 1);
         const int need_hi = min(max(__ldg(J.first_v + o_l) + tv - 1, 0), H - 1);
         const int start = max(produced_hi + 1, need_lo);
-        {   // pull the NEXT group's source rows towards L2 while this group computes
+        {   // pull the NEXT group's source rows towards L2 while this group computes: 32 rows x (luma, chroma) spans
             const int tid = warp * 32 + lane;
-            const int nr = need_hi + 1 + (tid >> 3), part = tid & 7;  // 32 luma rows x (3 luma + 3 chroma lines)
-            if (nr < H && part < 6) {
-                const int xb = min(max(xa_e, 0), W - 1);
-                if (IL) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(2 * xb + part * 128, 2 * W - 1));
-                else if (part < 3) prefetch_l2(src.p0 + (size_t)nr * src.pitch0 + min(xb + part * 128, W - 1));
-                else if ((nr & 1) == 0) {
+            const int nr = need_hi + 1 + (tid >> 2), part = tid & 3;
+            if (tid < 128 && nr < H) {
+                const int xb = max(xa_e - 2, 0), span = K::SPAN + 4;   // the strip's pixels plus the chroma neighbours
+                if (IL) {
+                    if (part == 0) prefetch_l2_span(src.p0 + (size_t)nr * src.pitch0 + 2 * xb, 2 * span, src.p0, src.p0 + (size_t)H * src.pitch0);
+                } else if (part == 0) {
+                    prefetch_l2_span(src.p0 + (size_t)nr * src.pitch0 + xb, span, src.p0, src.p0 + (size_t)H * src.pitch0);
+                } else if ((nr & 1) == 0) {
                     const int cyn = min(nr >> 1, chei - 1);
-                    if (NV12) prefetch_l2(src.p1 + (size_t)cyn * src.pitch1 + min(xb + (part - 3) * 128, W - 2));
-                    else if (part < 5) prefetch_l2((part == 3 ? src.p1 : src.p2) + (size_t)cyn * (part == 3 ? src.pitch1 : src.pitch2) + (xb >> 1));
+                    if (NV12) {
+                        if (part == 1) prefetch_l2_span(src.p1 + (size_t)cyn * src.pitch1 + xb, span, src.p1, src.p1 + (size_t)chei * src.pitch1);
+                    } else if (part == 1) {
+                        prefetch_l2_span(src.p1 + (size_t)cyn * src.pitch1 + (xb >> 1), span >> 1, src.p1, src.p1 + (size_t)chei * src.pitch1);
+                    } else if (part == 2) {
+                        prefetch_l2_span(src.p2 + (size_t)cyn * src.pitch2 + (xb >> 1), span >> 1, src.p2, src.p2 + (size_t)chei * src.pitch2);
+                    }
                 }
             }
         }

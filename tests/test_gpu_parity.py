@@ -524,3 +524,19 @@ def test_frame_pre_processor(mode):
             got = pre.process_to_bytes(fr, s.Resolution(ow, oh))
             exp = orc.rescale_rgba(node, ow, oh, omode)
             assert_identical((got,), (exp,), f"{fr.data.kind} -> {ow}x{oh}")
+
+
+def test_many_layers_beyond_the_parameter_bank():
+    """150 layers (> the 96 that travel in the kernel parameter bank): the composite reads its layer list from
+    global / shared memory instead; translucent, opaque, rounded and video layers mixed, more than 40 in one tile"""
+    kids = [s.RescalerComponent(child=streams(1)[0])]
+    for i in range(148):
+        kids.append(V(position=s.Position.Absolute(width=60.0 + (i % 7) * 9, height=40.0 + (i % 5) * 11,
+                                                   left=5.0 + (i * 37) % 560, top=4.0 + (i * 53) % 300),
+                      background_color=s.RGBAColor((i * 29) % 256, (i * 71) % 256, (i * 13) % 256, 255 if i % 3 else 120),
+                      border_radius=s.BorderRadius.new_with_radius(float((i % 4) * 6))))
+    # a pile of 45 views on one spot: more than the layers a tile keeps in shared memory
+    for i in range(45):
+        kids.append(V(position=s.Position.Absolute(width=90.0 - i, height=70.0 - i, left=300.0 + i * 0.5, top=150.0 + i * 0.25),
+                      background_color=s.RGBAColor((i * 5) % 256, 200, (i * 17) % 256, 200)))
+    check(V(children=kids, background_color=BG), inputs(1), max_layouts=400)
