@@ -268,7 +268,10 @@ smr_status smr_debug_set_inputs(smr_renderer *r, uint64_t pts_ns, const smr_inpu
  * handle is ordered after it).  The unique id travels over whatever transport the host already has. */
 smr_status smr_comm_get_unique_id(uint8_t id[128]);
 smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, int32_t nranks);
-/* frames[i]: device-resident planes, identical geometry on every rank; root_ranks[i] holds the data */
+/* frames[i]: device-resident planes, identical geometry on every rank; root_ranks[i] holds the data.
+ * Asynchronous: the NCCL group runs on the handle's communication stream, after every tick submitted BEFORE the most
+ * recent smr_render_begin has finished and before the next smr_render_begin's kernels -- i.e. it overlaps the tick in
+ * flight.  The planes must therefore not be the ones the most recently submitted tick reads (alternate two sets). */
 smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n,
                                      const int32_t *root_ranks);
 smr_status smr_comm_destroy(smr_renderer *r);

@@ -280,6 +280,11 @@ class Renderer {
     // up to two ticks in flight: uploads of tick n+1 (copy stream) overlap the kernels of tick n
     cudaStream_t copy_stream_ = nullptr;
     cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, tick_done_[2] = {nullptr, nullptr};
+    // the tick's exchange step overlaps the previous tick's kernels: NCCL runs on its own stream, ordered after
+    // everything submitted BEFORE the most recent tick and before the next one
+    cudaStream_t comm_stream_ = nullptr;
+    cudaEvent_t comm_done_ = nullptr, tick_start_ = nullptr;
+    bool comm_pending_ = false, tick_started_ = false;
     std::deque<int> inflight_;
     int slot_ = 0;
     bool uploaded_ = false;
@@ -287,6 +292,7 @@ class Renderer {
     void drain() {
         if (stream_) cudaStreamSynchronize(stream_);
         if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+        if (comm_stream_) cudaStreamSynchronize(comm_stream_);
         fold_profile();
         inflight_.clear();
     }
@@ -316,6 +322,9 @@ Renderer::~Renderer() {
         cudaSetDevice(opts_.cuda_device);
         cudaStreamSynchronize(stream_);
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+        if (comm_stream_) { cudaStreamSynchronize(comm_stream_); cudaStreamDestroy(comm_stream_); }
+        if (comm_done_) cudaEventDestroy(comm_done_);
+        if (tick_start_) cudaEventDestroy(tick_start_);
         for (int i = 0; i < 2; i++) { if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]); if (tick_done_[i]) cudaEventDestroy(tick_done_[i]); }
         if (nccl_comm_) { g_nccl.CommDestroy(nccl_comm_); nccl_comm_ = nullptr; }
         for (auto &kv : weights_) {
@@ -348,6 +357,9 @@ smr_status Renderer::init() {
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&comm_done_, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&tick_start_, cudaEventDisableTiming));
     CUDA_OK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, opts_.cuda_device));
     for (int i = 0; i < 2; i++) {
         CUDA_OK(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
@@ -1153,6 +1165,14 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         if (st != SMR_OK) return st;
     }
 
+    // everything already on the stream belongs to earlier ticks: a broadcast issued after this call may overwrite any
+    // buffer those ticks read once this event has fired
+    CUDA_OK(cudaEventRecord(tick_start_, stream_));
+    tick_started_ = true;
+    if (comm_pending_) {   // this tick's shared inputs arrive on the communication stream
+        CUDA_OK(cudaStreamWaitEvent(stream_, comm_done_, 0));
+        comm_pending_ = false;
+    }
     // ---- resolve frame-arena addresses --------------------------------------------------------
     if (uploaded_) {   // kernels of this tick start after its uploads; earlier ticks keep running meanwhile
         CUDA_OK(cudaEventRecord(h2d_done_[slot_], copy_stream_));
@@ -1386,6 +1406,9 @@ smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, c
     if (!nccl_comm_) { set_error("smr_comm_init was not called"); return SMR_ERR_INVALID_ARGUMENT; }
     if (n && (!frames || !roots)) return SMR_ERR_INVALID_ARGUMENT;
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    // Runs on its own stream so that it overlaps the kernels of the tick submitted last; it is ordered after every
+    // EARLIER tick (whose buffers the caller may be recycling) and before the next smr_render_begin.
+    if (tick_started_) CUDA_OK(cudaStreamWaitEvent(comm_stream_, tick_start_, 0));
     int rc = g_nccl.GroupStart();
     for (uint32_t i = 0; i < n && rc == 0; i++) {
         const smr_input_frame &f = frames[i];
@@ -1396,12 +1419,14 @@ smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, c
             if (!plane_layout(f.format, f.width, f.height, p, row_bytes, rows)) continue;
             size_t pitch = f.pitch[p] ? f.pitch[p] : row_bytes;
             size_t bytes = pitch * (rows - 1) + row_bytes;
-            rc = g_nccl.Broadcast(f.planes[p], (void *)f.planes[p], bytes, /*ncclUint8*/ 1, roots[i], nccl_comm_, stream_);
+            rc = g_nccl.Broadcast(f.planes[p], (void *)f.planes[p], bytes, /*ncclUint8*/ 1, roots[i], nccl_comm_, comm_stream_);
         }
     }
     int rc2 = g_nccl.GroupEnd();
     if (rc == 0) rc = rc2;
     if (rc != 0) { set_error(std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
+    CUDA_OK(cudaEventRecord(comm_done_, comm_stream_));
+    comm_pending_ = true;
     return SMR_OK;
 }
 
