@@ -281,3 +281,7 @@ def render_layout_node(out_w, out_h, layouts, nodes, mode=MODE_GPU_OPTIMIZED, ma
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))

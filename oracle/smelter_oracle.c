@@ -52,6 +52,14 @@ __attribute__((constructor)) void orc_init(void) {
     g_init_done = 1;
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

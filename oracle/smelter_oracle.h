@@ -142,6 +142,7 @@ uint8_t orc_unorm8(float x);            /* UNORM8 store */
 uint16_t orc_f32_to_f16(float x);
 float orc_f16_to_f32(uint16_t h);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* OpenMP team size of the parallel loops (bench: pick the fastest) */
 
 #ifdef __cplusplus
 }
