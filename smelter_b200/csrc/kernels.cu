@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 
 #include "kernels.h"
@@ -37,7 +38,7 @@ __device__ float c_thr[256];  // 255 used
 __device__ unsigned char c_enc0[420];
 __device__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
 
-static char g_err[256] = {0};
+static thread_local char g_err[256] = {0};   // a launch and the read of its error happen on the same thread
 const char *last_launch_error() { return g_err; }
 static bool check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -803,11 +804,15 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
 template <int S, int SRC>
 static bool launch_fused_int(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks,
                              cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: several handles of one process may drive different GPUs from different threads
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
         cudaFuncSetAttribute(k_resample_fused_int<S, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(typename W64<S>::Smem));
-        attr_set = true;
+        done.fetch_or(bit, std::memory_order_release);
     }
     k_resample_fused_int<S, SRC><<<nblocks, dim3(32, W64_WARPS), sizeof(typename W64<S>::Smem), s>>>(jobs_dev, pieces, piece_begin);
     return check_launch("k_resample_fused_int");
@@ -1449,10 +1454,36 @@ __global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_p(const __grid_cons
     composite_body<true>(P.job, P.layers);
 }
 
+// all outputs of a tick in one launch (blockIdx.z = output): a 1080p frame alone is 2.3 waves of 444 resident
+// blocks, eight of them back to back are 18.4 -- the per-launch tails disappear
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_multi(const CompositeJob *__restrict__ jobs) {
+    __shared__ CompositeJob J;
+    {
+        const int tid = threadIdx.y * CB_X + threadIdx.x;
+        const unsigned int *src = reinterpret_cast<const unsigned int *>(jobs + blockIdx.z);
+        if (tid < (int)(sizeof(CompositeJob) / 4)) reinterpret_cast<unsigned int *>(&J)[tid] = __ldg(src + tid);
+    }
+    __syncthreads();
+    if ((int)blockIdx.x * (CB_X * CT_W) >= J.width || (int)blockIdx.y * (CB_Y * CT_H * CT_ITERS) >= J.height) return;
+    composite_body<false>(J, J.layers);
+}
+
+int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *jobs_host, int n, Stream s) {
+    static_assert(sizeof(CompositeJob) % 4 == 0 && sizeof(CompositeJob) / 4 <= CB_X * CB_Y, "job copied by one block pass");
+    int gx = 0, gy = 0;
+    for (int i = 0; i < n; i++) {
+        gx = max(gx, (jobs_host[i].width + CB_X * CT_W - 1) / (CB_X * CT_W));
+        gy = max(gy, (jobs_host[i].height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
+    }
+    if (n <= 0 || gx == 0 || gy == 0) return 0;
+    k_composite_multi<<<dim3(gx, gy, n), dim3(CB_X, CB_Y), 0, (cudaStream_t)s>>>(jobs_dev);
+    return check_launch("k_composite_multi") ? 1 : -1;
+}
+
 int launch_composite(const CompositeJob &job, Stream s) {
     dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
     if (job.n_layers <= PARAM_LAYERS && job.layers_host != nullptr) {
-        static CompositeParams P;   // launches are serialised by the handle's mutex; the driver copies at launch
+        CompositeParams P;   // ~26 KB on the host stack; the driver copies the parameter block at launch
         P.job = job;
         memcpy(P.layers, job.layers_host, sizeof(LayerDev) * (size_t)job.n_layers);
         k_composite_p<<<g, b, 0, (cudaStream_t)s>>>(P);

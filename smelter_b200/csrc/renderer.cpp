@@ -1254,8 +1254,27 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
     if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
+    // composite jobs: their device pointers are known once the arena is sized; with two or more outputs in the tick
+    // the jobs travel in the arena and run as ONE launch
+    const size_t cj_off = param_alloc(sizeof(dev::CompositeJob) * std::max<size_t>(composites_.size(), 1));
+    if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
     CUDA_OK(param_pinned_[slot_].ensure(param_used_));
     CUDA_OK(param_dev_[slot_].ensure(param_used_));
+    {
+        uint8_t *pd0 = param_dev_[slot_].p;
+        for (size_t i = 0; i < composites_.size(); i++) {
+            PendingComposite &pc = composites_[i];
+            pc.job.layers = (const dev::LayerDev *)(pd0 + pc.layers_off);
+            pc.job.layers_host = (const dev::LayerDev *)(param_host_.data() + pc.layers_off);
+            pc.job.masks = (const dev::MaskDev *)(pd0 + pc.masks_off);
+            pc.job.textures = (const dev::Tex *)(pd0 + tex_off);
+            if (pc.job.out_format == -1 && pc.job.out1 == (uint8_t *)(uintptr_t)1) {
+                pc.job.out0 = fb + (size_t)(uintptr_t)pc.job.out0;
+                pc.job.out1 = nullptr;
+            }
+            memcpy(param_host_.data() + cj_off + i * sizeof(dev::CompositeJob), &pc.job, sizeof(dev::CompositeJob));
+        }
+    }
     memcpy(param_pinned_[slot_].p, param_host_.data(), param_used_);
     CUDA_OK(cudaMemcpyAsync(param_dev_[slot_].p, param_pinned_[slot_].p, param_used_, cudaMemcpyHostToDevice, stream_));
     uint8_t *pd = param_dev_[slot_].p;
@@ -1283,17 +1302,16 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
                                            (int)stage_jobs_[s].size(), stream_))) goto fail;
         if (!stage_jobs_[s].empty()) prof_mark(SMR_KERNEL_RESAMPLE_BOX + s);
     }
-    for (PendingComposite &pc : composites_) {
-        pc.job.layers = (const dev::LayerDev *)(pd + pc.layers_off);
-        pc.job.layers_host = (const dev::LayerDev *)(param_host_.data() + pc.layers_off);
-        pc.job.masks = (const dev::MaskDev *)(pd + pc.masks_off);
-        pc.job.textures = (const dev::Tex *)(pd + tex_off);
-        if (pc.job.out_format == -1 && pc.job.out1 == (uint8_t *)(uintptr_t)1) {
-            pc.job.out0 = fb + (size_t)(uintptr_t)pc.job.out0;
-            pc.job.out1 = nullptr;
-        }
-        if (!launched(dev::launch_composite(pc.job, stream_))) goto fail;
+    if (composites_.size() >= 2) {
+        if (!launched(dev::launch_composite_multi((const dev::CompositeJob *)(pd + cj_off),
+                                                  (const dev::CompositeJob *)(param_host_.data() + cj_off),
+                                                  (int)composites_.size(), stream_))) goto fail;
         prof_mark(SMR_KERNEL_COMPOSITE);
+    } else {
+        for (PendingComposite &pc : composites_) {
+            if (!launched(dev::launch_composite(pc.job, stream_))) goto fail;
+            prof_mark(SMR_KERNEL_COMPOSITE);
+        }
     }
     for (dev::OutputJob &oj : output_jobs_) {
         if (!launched(dev::launch_output(oj, stream_))) goto fail;
