@@ -693,9 +693,15 @@ __global__ void __launch_bounds__(32 * W64_WARPS, 3) k_resample_fused_int(const 
                     const float uo = div255((float)(no & 0xffffu), 0.0625f), vo = div255((float)(no >> 16), 0.0625f);
                     const int i = 2 * p - dsh;
                     int r8, g8, b8;
-                    yuv_to_rgb8n(ytab[R.y & 0xffu], ue, ve, full_range, r8, g8, b8);
+                    // luma by arithmetic, not by table: f32(y/255) exactly (div255), then the same two f32 operations as the
+                    // table entry -- trades one conflict-prone LDS per pixel for three FP32 instructions
+                    auto luma = [&](unsigned yb) {
+                        const float yn = div255((float)yb, 1.0f);
+                        return full_range ? yn : clamp01((yn - K16) * RCP_Y);
+                    };
+                    yuv_to_rgb8n(luma(R.y & 0xffu), ue, ve, full_range, r8, g8, b8);
                     if (i >= 0) put(i, r8, g8, b8);
-                    yuv_to_rgb8n(ytab[R.y >> 8], uo, vo, full_range, r8, g8, b8);
+                    yuv_to_rgb8n(luma(R.y >> 8), uo, vo, full_range, r8, g8, b8);
                     put(i + 1, r8, g8, b8);
                 };
                 auto inside = [&](int pp) { return pp >= p_in_lo && pp <= p_hi; };
