@@ -308,7 +308,32 @@ def main():
             arr[i].planes[0], arr[i].planes[1] = ptr(yv), ptr(uvv)
         return arr
 
+    if roots is not None:
+        # each ingest GPU keeps the frames it owns in one pool: the planes of a root are contiguous, so the library
+        # replicates them with one ncclBroadcast per root instead of one per plane
+        order = sorted(range(n), key=lambda i: (roots[i], i))
+        for v in range(nvar):
+            pool = torch.empty(sum(t.numel() for i in order for t in dev_frames[v][i]), dtype=torch.uint8, device=dev)
+            off, packed = 0, {}
+            for i in order:
+                views = []
+                for t in dev_frames[v][i]:
+                    view = pool[off:off + t.numel()].view(t.shape)
+                    view.copy_(t)
+                    views.append(view)
+                    off += t.numel()
+                packed[i] = tuple(views)
+            dev_frames[v] = [packed[i] for i in range(n)]
     dev_in = [in_array(dev_frames[v], F.MEM_DEVICE, lambda t: t.data_ptr()) for v in range(nvar)]
+    comm_in, comm_roots = None, None
+    if roots is not None:   # the exchange lists the frames root by root, so each root's pool is one contiguous run
+        comm_roots = [roots[i] for i in order]
+        comm_in = []
+        for v in range(nvar):
+            arr = (F.InputFrame * n)()
+            for k, i in enumerate(order):
+                C.memmove(C.byref(arr[k]), C.byref(dev_in[v][i]), C.sizeof(F.InputFrame))
+            comm_in.append(arr)
     dev_out = (F.OutputFrame * n_out)()
     for k in range(n_out):
         dev_out[k].output_id = out_ids[k]
@@ -322,7 +347,7 @@ def main():
         for a in dev_in[k % nvar]:
             a.pts_ns = k * frame_ns
         if roots is not None:   # the tick's exchange step: one NCCL group on the render stream
-            r.comm_broadcast_inputs(dev_in[k % nvar], n, roots)
+            r.comm_broadcast_inputs(comm_in[k % nvar], n, comm_roots)
         r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, n_out, wait=False)
 
     # ---- value: device-resident, device-timed ---------------------------------------------------------

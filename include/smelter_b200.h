@@ -271,7 +271,9 @@ smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, i
 /* frames[i]: device-resident planes, identical geometry on every rank; root_ranks[i] holds the data.
  * Asynchronous: the NCCL group runs on the handle's communication stream, after every tick submitted BEFORE the most
  * recent smr_render_begin has finished and before the next smr_render_begin's kernels -- i.e. it overlaps the tick in
- * flight.  The planes must therefore not be the ones the most recently submitted tick reads (alternate two sets). */
+ * flight.  The planes must therefore not be the ones the most recently submitted tick reads (alternate two sets).
+ * Consecutive planes of the list that share a root and are contiguous in memory are sent as ONE ncclBroadcast, so
+ * every rank must lay its planes out identically (same contiguity) -- e.g. one frame pool per ingest GPU. */
 smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n,
                                      const int32_t *root_ranks);
 smr_status smr_comm_destroy(smr_renderer *r);

@@ -1427,19 +1427,28 @@ smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, c
     // Runs on its own stream so that it overlaps the kernels of the tick submitted last; it is ordered after every
     // EARLIER tick (whose buffers the caller may be recycling) and before the next smr_render_begin.
     if (tick_started_) CUDA_OK(cudaStreamWaitEvent(comm_stream_, tick_start_, 0));
-    int rc = g_nccl.GroupStart();
-    for (uint32_t i = 0; i < n && rc == 0; i++) {
+    // one ncclBroadcast per run of planes that share a root and are contiguous in memory (an ingest GPU's frame pool):
+    // the host cost of the group scales with the number of calls, not with the bytes
+    struct Run { uint8_t *p; size_t bytes; int root; };
+    std::vector<Run> runs;
+    for (uint32_t i = 0; i < n; i++) {
         const smr_input_frame &f = frames[i];
-        if (f.mem_kind != SMR_MEM_DEVICE) { g_nccl.GroupEnd(); set_error("broadcast needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
-        if (roots[i] < 0 || roots[i] >= comm_size_) { g_nccl.GroupEnd(); return SMR_ERR_INVALID_ARGUMENT; }
-        for (int p = 0; p < 3 && rc == 0; p++) {
+        if (f.mem_kind != SMR_MEM_DEVICE) { set_error("broadcast needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (roots[i] < 0 || roots[i] >= comm_size_) return SMR_ERR_INVALID_ARGUMENT;
+        for (int p = 0; p < 3; p++) {
             size_t row_bytes = 0, rows = 0;
             if (!plane_layout(f.format, f.width, f.height, p, row_bytes, rows)) continue;
+            if (!f.planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
             size_t pitch = f.pitch[p] ? f.pitch[p] : row_bytes;
             size_t bytes = pitch * (rows - 1) + row_bytes;
-            rc = g_nccl.Broadcast(f.planes[p], (void *)f.planes[p], bytes, /*ncclUint8*/ 1, roots[i], nccl_comm_, comm_stream_);
+            uint8_t *ptr = (uint8_t *)f.planes[p];
+            if (!runs.empty() && runs.back().root == roots[i] && runs.back().p + runs.back().bytes == ptr) runs.back().bytes += bytes;
+            else runs.push_back({ptr, bytes, roots[i]});
         }
     }
+    int rc = g_nccl.GroupStart();
+    for (size_t i = 0; i < runs.size() && rc == 0; i++)
+        rc = g_nccl.Broadcast(runs[i].p, runs[i].p, runs[i].bytes, /*ncclUint8*/ 1, runs[i].root, nccl_comm_, comm_stream_);
     int rc2 = g_nccl.GroupEnd();
     if (rc == 0) rc = rc2;
     if (rc != 0) { set_error(std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
