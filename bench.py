@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -132,9 +132,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """the timed region starts here: only rows that arrive from now on are reported"""
+        self.i0 = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        i1 = len(self.rows)
+        i0 = min(getattr(self, "i0", 0), max(i1 - 1, 0))   # a region shorter than one sampling period: the latest row
+        self.rows = self.rows[i0:i1] if i1 > i0 else self.rows[-1:]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -351,12 +358,13 @@ def main():
         r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, n_out, wait=False)
 
     # ---- value: device-resident, device-timed ---------------------------------------------------------
+    clocks = ClockSampler(local)      # already streaming when the timed region starts (nvidia-smi takes ~0.2 s to start)
+    clocks.start()
     for k in range(args.warmup):
         step_dev(k)
     r.wait()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.mark()
     launches0 = r.stats()["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
