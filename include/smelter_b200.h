@@ -243,6 +243,13 @@ smr_status smr_render_end(smr_renderer *r);
 smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *frame, uint32_t out_width, uint32_t out_height,
                                 void *rgba, uint32_t pitch, int32_t mem_kind);
 
+/* inspection (no device needed): the balanced row partition the fused resample launch uses for jobs of
+ * dst_w[i] x dst_h[i] output pixels on `max_blocks` resident blocks.  pieces: 4 ints each {job, strip, row_begin,
+ * row_end}; block b owns pieces [begin[b], begin[b + 1]). */
+smr_status smr_debug_partition(const int32_t *dst_w, const int32_t *dst_h, uint32_t n_jobs, uint32_t max_blocks,
+                               int32_t *pieces, uint32_t pieces_cap, uint32_t *n_pieces, int32_t *begin,
+                               uint32_t begin_cap, uint32_t *n_blocks);
+
 /* byte sizes of the planes smr_render writes for an output (0 for unused planes) */
 smr_status smr_output_plane_sizes(uint32_t width, uint32_t height, int32_t output_format, size_t sizes[3]);
 

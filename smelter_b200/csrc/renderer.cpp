@@ -99,6 +99,37 @@ static int resample_taps(float scale) {  // resample.wgsl:43-48
 // ------------------------------------------------------------------------------------------------
 // small RAII helpers
 // ------------------------------------------------------------------------------------------------
+// Balanced partition of a launch of the fused resample kernel (kernels.cu: k_resample_fused_int): the output rows of
+// every (job, 64-column strip) are concatenated and cut into `max_blocks` equal contiguous shares (a multiple of the 8
+// output rows a block produces per step).  Block b owns pieces [begin[b], begin[b+1]); every output row of every
+// strip belongs to exactly one piece.
+void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst_h, int n_jobs, int max_blocks,
+                          std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin) {
+    pieces.clear(); begin.clear();
+    long long total = 0;
+    for (int i = 0; i < n_jobs; i++)
+        if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + dev::kFusedStripCols - 1) / dev::kFusedStripCols) * dst_h[i];
+    if (total <= 0 || max_blocks <= 0) return;
+    const int nblocks = (int)std::min<long long>((long long)max_blocks, (total + 7) / 8);
+    const long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
+    begin.push_back(0);
+    long long room = per_block;
+    for (int i = 0; i < n_jobs; i++) {
+        if (dst_w[i] <= 0 || dst_h[i] <= 0) continue;
+        const int strips = (dst_w[i] + dev::kFusedStripCols - 1) / dev::kFusedStripCols;
+        for (int st = 0; st < strips; st++) {
+            int y = 0;
+            while (y < dst_h[i]) {
+                const int take = (int)std::min<long long>(room, dst_h[i] - y);
+                pieces.push_back({job_index[i], st, y, y + take});
+                y += take; room -= take;
+                if (room == 0) { begin.push_back((int)pieces.size()); room = per_block; }
+            }
+        }
+    }
+    if (begin.back() != (int)pieces.size()) begin.push_back((int)pieces.size());
+}
+
 struct DevBuf {
     uint8_t *p = nullptr;
     size_t cap = 0;
@@ -1212,31 +1243,16 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             if (std::find(variants.begin(), variants.end(), v) == variants.end()) variants.push_back(v);
         }
         for (auto &v : variants) {
-            long long total = 0;
-            for (const dev::FusedJob &j : fused_jobs_)
-                if (j.variant == v.first && dev::fused_source_class(j.src.kind) == v.second)
-                    total += (long long)((j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols) * j.dst_h;
-            if (total <= 0) continue;
-            int nblocks = (int)std::min<long long>((long long)sm_count_ * 3, (total + 7) / 8);
-            long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
-            std::vector<dev::FusedPiece> pieces;
-            std::vector<int> begin{0};
-            long long room = per_block;
+            std::vector<int> idx, widths, heights;
             for (size_t ji = 0; ji < fused_jobs_.size(); ji++) {
                 const dev::FusedJob &j = fused_jobs_[ji];
                 if (j.variant != v.first || dev::fused_source_class(j.src.kind) != v.second) continue;
-                int strips = (j.dst_w + dev::kFusedStripCols - 1) / dev::kFusedStripCols;
-                for (int st = 0; st < strips; st++) {
-                    int y = 0;
-                    while (y < j.dst_h) {
-                        int take = (int)std::min<long long>(room, j.dst_h - y);
-                        pieces.push_back({(int)ji, st, y, y + take});
-                        y += take; room -= take;
-                        if (room == 0) { begin.push_back((int)pieces.size()); room = per_block; }
-                    }
-                }
+                idx.push_back((int)ji); widths.push_back(j.dst_w); heights.push_back(j.dst_h);
             }
-            if (begin.back() != (int)pieces.size()) begin.push_back((int)pieces.size());
+            std::vector<dev::FusedPiece> pieces;
+            std::vector<int> begin;
+            partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(), sm_count_ * 3, pieces, begin);
+            if (pieces.empty()) continue;
             FusedLaunch fl;
             fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
             fl.pieces_off = param_alloc(sizeof(dev::FusedPiece) * pieces.size());
@@ -1570,6 +1586,24 @@ smr_status smr_unregister_output(smr_renderer *r, const char *id) { SMR_GUARD(r-
 smr_status smr_render_begin(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in,
                             smr_output_frame *out, uint32_t n_out) { SMR_GUARD(r->impl.render_begin(pts, in, n_in, out, n_out)) }
 smr_status smr_render_end(smr_renderer *r) { SMR_GUARD(r->impl.render_end()) }
+smr_status smr_debug_partition(const int32_t *dst_w, const int32_t *dst_h, uint32_t n_jobs, uint32_t max_blocks,
+                               int32_t *pieces, uint32_t pieces_cap, uint32_t *n_pieces, int32_t *begin, uint32_t begin_cap,
+                               uint32_t *n_blocks) {
+    if ((n_jobs && (!dst_w || !dst_h)) || !n_pieces || !n_blocks) return SMR_ERR_INVALID_ARGUMENT;
+    std::vector<int> idx(n_jobs);
+    for (uint32_t i = 0; i < n_jobs; i++) idx[i] = (int)i;
+    std::vector<smr::dev::FusedPiece> pc;
+    std::vector<int> bg;
+    smr::partition_fused_rows(idx.data(), dst_w, dst_h, (int)n_jobs, (int)max_blocks, pc, bg);
+    *n_pieces = (uint32_t)pc.size();
+    *n_blocks = bg.empty() ? 0 : (uint32_t)bg.size() - 1;
+    if (pc.size() > pieces_cap || bg.size() > begin_cap) return SMR_ERR_BUFFER_TOO_SMALL;
+    for (size_t i = 0; i < pc.size(); i++) {
+        pieces[4 * i] = pc[i].job; pieces[4 * i + 1] = pc[i].strip; pieces[4 * i + 2] = pc[i].oy_begin; pieces[4 * i + 3] = pc[i].oy_end;
+    }
+    for (size_t i = 0; i < bg.size(); i++) begin[i] = bg[i];
+    return SMR_OK;
+}
 smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch,
                                 int32_t mem_kind) { SMR_GUARD(r->impl.preprocess_frame(f, ow, oh, rgba, pitch, mem_kind)) }
 smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,

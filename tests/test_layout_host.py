@@ -331,3 +331,47 @@ def test_unsupported_component_is_reported():
 def test_max_layouts_and_masks_constants():
     assert F.MAX_MASKS == 20
     assert s.RendererOptions().max_layouts_count == 100
+
+
+def test_fused_resample_row_partition_covers_every_row_once():
+    """host logic of the persistent fused-resample launch (renderer.cpp: partition_fused_rows): the output rows of every
+    (job, 64-column strip) are cut into equal contiguous shares for the resident blocks.  Every row of every strip must
+    belong to exactly one piece, blocks own consecutive pieces, shares are equal up to the 8-row step."""
+    import ctypes as C
+    from smelter_b200 import _ffi as F
+    lib = F.lib()
+
+    def partition(sizes, max_blocks):
+        n = len(sizes)
+        w = (C.c_int32 * n)(*[s[0] for s in sizes])
+        h = (C.c_int32 * n)(*[s[1] for s in sizes])
+        cap = 16384
+        pieces, begin = (C.c_int32 * (4 * cap))(), (C.c_int32 * cap)()
+        npieces, nblocks = C.c_uint32(), C.c_uint32()
+        assert lib.smr_debug_partition(w, h, n, max_blocks, pieces, cap, C.byref(npieces), begin, cap, C.byref(nblocks)) == 0
+        pc = [tuple(pieces[4 * i:4 * i + 4]) for i in range(npieces.value)]
+        return pc, list(begin[:nblocks.value + 1])
+
+    cases = [([(960, 540)] * 16, 444),                       # BASELINE config 3
+             ([(1230, 692)] * 32, 444),                      # config 5: ragged last strip
+             ([(960, 540)] * 8, 444), ([(320, 180), (417, 233), (1, 1), (64, 8)], 444), ([(64, 8)], 444),
+             ([(5, 3)], 12), ([(4096, 4096)], 7), ([(100, 50), (0, 10), (30, 0)], 9)]
+    for sizes, max_blocks in cases:
+        pc, begin = partition(sizes, max_blocks)
+        total = sum(((w + 63) // 64) * h for w, h in sizes if w > 0 and h > 0)
+        assert begin[0] == 0 and begin[-1] == len(pc) and all(a < b for a, b in zip(begin, begin[1:]))
+        assert len(begin) - 1 <= max_blocks
+        covered = {}
+        for job, strip, y0, y1 in pc:
+            w, h = sizes[job]
+            assert 0 <= strip < (w + 63) // 64 and 0 <= y0 < y1 <= h
+            for y in range(y0, y1):
+                assert (job, strip, y) not in covered
+                covered[(job, strip, y)] = True
+        assert len(covered) == total
+        # pieces are in (job, strip, row) order, so a block's pieces are a contiguous run of that order
+        assert pc == sorted(pc)
+        shares = [sum(p[3] - p[2] for p in pc[a:b]) for a, b in zip(begin, begin[1:])]
+        # every block but the last gets the same share, a multiple of the 8 output rows a block produces per step
+        assert len(set(shares[:-1])) <= 1 and all(sh % 8 == 0 for sh in shares[:-1])
+        assert len(shares) == 1 or shares[-1] <= shares[0]
