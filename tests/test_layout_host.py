@@ -375,3 +375,44 @@ def test_fused_resample_row_partition_covers_every_row_once():
         # every block but the last gets the same share, a multiple of the 8 output rows a block produces per step
         assert len(set(shares[:-1])) <= 1 and all(sh % 8 == 0 for sh in shares[:-1])
         assert len(shares) == 1 or shares[-1] <= shares[0]
+
+
+def test_output_plane_sizes_for_every_output_format():
+    """texture/planar_yuv.rs:64-98 (4:2:0 / 4:2:2 / 4:4:4 chroma plane sizes), nv12.rs:77-88, RGBA; odd sizes floor"""
+    import ctypes as C
+    lib = F.lib()
+
+    def sizes(w, h, fmt):
+        out = (C.c_size_t * 3)()
+        st = lib.smr_output_plane_sizes(w, h, fmt, C.byref(out))
+        return st, tuple(out)
+
+    assert sizes(640, 360, F.OUT_PLANAR_YUV420) == (0, (640 * 360, 320 * 180, 320 * 180))
+    assert sizes(640, 360, F.OUT_PLANAR_YUV422) == (0, (640 * 360, 320 * 360, 320 * 360))
+    assert sizes(640, 360, F.OUT_PLANAR_YUV444) == (0, (640 * 360, 640 * 360, 640 * 360))
+    assert sizes(640, 360, F.OUT_NV12) == (0, (640 * 360, 320 * 180 * 2, 0))
+    assert sizes(640, 360, F.OUT_RGBA8) == (0, (640 * 360 * 4, 0, 0))
+    assert sizes(501, 283, F.OUT_PLANAR_YUV422) == (0, (501 * 283, 250 * 283, 250 * 283))
+    assert sizes(501, 283, F.OUT_PLANAR_YUV420) == (0, (501 * 283, 250 * 141, 250 * 141))
+    assert sizes(640, 360, 5)[0] == 5 and sizes(640, 360, -1)[0] == 5      # SMR_ERR_UNSUPPORTED
+
+
+def test_unknown_output_format_is_rejected_and_new_formats_accepted():
+    r = host_renderer()
+    scene = s.ViewComponent(background_color=s.RGBAColor(1, 2, 3, 255))
+    for fmt in (s.OutputFrameFormat.PlanarYuv420Bytes, s.OutputFrameFormat.PlanarYuv422Bytes,
+                s.OutputFrameFormat.PlanarYuv444Bytes, s.OutputFrameFormat.RgbaWgpuTexture,
+                s.OutputFrameFormat.Nv12WgpuTexture):
+        r.update_scene("output_1", RES, fmt, scene)
+    with pytest.raises(s.UpdateSceneError):
+        r.update_scene("output_1", RES, 7, scene)
+
+
+def test_frame_pre_processor_without_gpu_fails_loudly():
+    """no CPU fallback anywhere on the product path: a host-only handle refuses to convert a frame"""
+    import numpy as np
+    r = host_renderer()
+    fr = s.Frame(s.FrameData.InterleavedUyvy422(np.zeros((4, 4, 4), np.uint8)), s.Resolution(8, 4))
+    with pytest.raises(s.RendererError) as e:
+        s.FramePreProcessor(r).process_to_bytes(fr)
+    assert "no CPU fallback" in str(e.value)
