@@ -212,3 +212,67 @@ def test_wide_chroma_restatements_are_consistent():
         y1, u1, v1 = orc.rgba_to_yuv_planar_scaled(flat, w, h, cw, ch)
         assert np.array_equal(y0, y1) and u1.shape == (ch, cw)
         assert len(np.unique(u1)) == 1 and u1[0, 0] == u0[0, 0] and v1[0, 0] == v0[0, 0]
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+def test_interleaved_shader_restated_in_python_floats():
+    """interleaved_uyvy_to_rgba.wgsl:24-61 re-derived step by step with numpy float32 scalars (an implementation
+    independent of the C restatement) on a small frame, including the column-index round trip of the shader and the
+    widths where it degenerates (w = 2: both pixels read the first luma)."""
+    rng = np.random.default_rng(12)
+    for w, h in ((12, 3), (6, 2), (2, 2)):
+        dimx = w // 2
+        data = rng.integers(16, 236, (h, dimx, 4), dtype=np.uint8)
+        got = orc.interleaved422_to_rgba(data, w, h, False)
+        for py in range(h):
+            for px in range(w):
+                tx = _f32(_f32(px + 0.5) / _f32(w))
+                hpw = _f32(_f32(0.5) / _f32(dimx))
+                xf = _f32(_f32(_f32(_f32(tx * _f32(dimx)) - hpw) + _f32(0.0001)) * _f32(2.0))
+                x_pos = int(xf) if xf > 0 else 0
+                tcx = _f32(_f32(_f32(x_pos // 2) / _f32(dimx)) + hpw)
+                c = _f32(_f32(tcx * _f32(dimx)) - _f32(0.5))              # texel-space coordinate of the sample
+                i0 = int(np.floor(c)); frac = _f32(c - _f32(np.floor(c)))
+                wq = int(np.rint(frac * _f32(256.0)))                      # NC-6: 8-bit weight
+                assert wq in (0, 256), "the sample must land on a texel centre"
+                tex = data[py, min(max(i0 + (wq == 256), 0), dimx - 1)]
+                u, y0, v, y1 = [_f32(_f32(t) / _f32(255.0)) for t in tex]
+                y = y1 if x_pos % 2 else y0
+                k16, rcy, rcc = _f32(_f32(16.0) / _f32(255.0)), _f32(_f32(1.0) / _f32(0.85882352941)), _f32(_f32(1.0) / _f32(0.87843137254))
+                cl = lambda t: min(max(t, _f32(0.0)), _f32(1.0))
+                y = cl(_f32(_f32(y - k16) * rcy)); u = cl(_f32(_f32(u - k16) * rcc)); v = cl(_f32(_f32(v - k16) * rcc))
+                um, vm = _f32(u - _f32(0.5)), _f32(v - _f32(0.5))
+                fma = lambda a, b, cc: _f32(np.float64(a) * np.float64(b) + np.float64(cc))   # exact product, one rounding
+                r = fma(_f32(1.5748), vm, y)
+                g = fma(_f32(-0.4681), vm, fma(_f32(-0.1873), um, y))
+                b = fma(_f32(1.8556), um, y)
+                exp = [int(np.rint(cl(t) * _f32(255.0))) for t in (r, g, b)] + [255]
+                assert got[py, px].tolist() == exp, (w, px, py)
+
+
+def test_frame_pre_processor_rescale_restated_in_integers():
+    """rgba_rescale.wgsl through a plain Rgba8Unorm target (CpuOptimized): every output byte is the correctly rounded
+    value of the exact fixed-point bilinear filter (NC-6u) -- re-derived here with Python integers and Fractions."""
+    from fractions import Fraction
+    rng = np.random.default_rng(4)
+    sw, sh, ow, oh = 9, 7, 5, 11
+    src = rng.integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+    got = orc.rescale_rgba(src, ow, oh, mode=1)
+
+    def tap(o, n_out, n_src):
+        c = _f32(_f32(_f32(_f32(o + 0.5) / _f32(n_out)) * _f32(n_src)) - _f32(0.5))
+        fl = int(np.floor(c)); w = int(np.rint(_f32(c - _f32(fl)) * _f32(256.0)))
+        return min(max(fl, 0), n_src - 1), min(max(fl + 1, 0), n_src - 1), w
+
+    for y in range(oh):
+        y0, y1, wy = tap(y, oh, sh)
+        for x in range(ow):
+            x0, x1, wx = tap(x, ow, sw)
+            for c in range(4):
+                n = (int(src[y0, x0, c]) * (256 - wx) + int(src[y0, x1, c]) * wx) * (256 - wy) + \
+                    (int(src[y1, x0, c]) * (256 - wx) + int(src[y1, x1, c]) * wx) * wy
+                v = float(np.float32(Fraction(n, 255 * 65536)))           # one rounding to f32
+                assert got[y, x, c] == int(np.rint(np.float32(v) * np.float32(255.0))), (x, y, c)
