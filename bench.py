@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -358,8 +358,11 @@ def main():
         r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, n_out, wait=False)
 
     # ---- value: device-resident, device-timed ---------------------------------------------------------
-    clocks = ClockSampler(local)      # already streaming when the timed region starts (nvidia-smi takes ~0.2 s to start)
-    clocks.start()
+    # already streaming when the timed region starts (nvidia-smi takes ~0.2 s to start); rank 0 only -- its line is the
+    # one that is printed, and N concurrent nvidia-smi loops would only contend for the driver lock
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for k in range(args.warmup):
         step_dev(k)
     r.wait()
