@@ -97,6 +97,13 @@ def workload(name):
                 tiles=tiles)
 
 
+def cfg4_scene(g, n=8):
+    """scene of global output g of BASELINE config 4: Tiles 2x2 of inputs (g + j) % n, j < 4, from the pool of n"""
+    import smelter_b200 as s
+    kids = [s.InputStreamComponent(input_id=f"input_{(g + j) % n + 1}") for j in range(4)]
+    return s.TilesComponent(children=kids, background_color=s.RGBAColor(*BG))
+
+
 # ------------------------------------------------------------------------------------------------
 def synth_planes_torch(torch, dev, w, h, seed):
     """procedural NV12 frame on the device: smooth blobs + noise, legal range."""
@@ -158,12 +165,26 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle on a bounded sample (1 of n tiles of the workload)
 # ------------------------------------------------------------------------------------------------
-_CPU_TEAM = None
+def metric_name(wl):
+    """one string for both arms (the driver divides the two lines only when the metric strings agree)"""
+    return "4K composited frames/sec (16-input grid) per GPU" if wl["name"] == "cfg3" else "composited output frames/sec"
 
 
-def cpu_sample(wl, repeats=1):
-    """Time the oracle on ONE input of the workload composited into ITS tile-sized output region with the
-    same per-tile layers (K1/K2 -> Lanczos -> K9 -> K11).  Returns (seconds per sample, description)."""
+def cpu_team():
+    """fixed rule, identical in both arms: one OpenMP thread per physical core (half the logical CPUs of the affinity
+    mask on an SMT box; every CPU when there are few)"""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, ncpu // 2) if ncpu >= 8 else max(1, ncpu)
+
+
+CPU_TILES = 4   # distinct tiles per bounded sample
+
+
+def cpu_steps(wl, steps, warmup):
+    """Time the oracle on a BOUNDED SAMPLE of the workload: CPU_TILES distinct inputs, each composited into ITS
+    tile-sized output region with the tile's layers (K1/K2 -> Lanczos -> K9 -> K11).  One step = one pass over the
+    sample; its frame-time estimate = (sum of the tile times) x n_tiles / CPU_TILES.  Returns (list of per-step frame
+    times in seconds, description, threads)."""
     import smelter_b200 as s
     from oracle import oracle as orc
     from tests import harness
@@ -172,8 +193,11 @@ def cpu_sample(wl, repeats=1):
     tw, th = wl["W"] // cols, (wl["W"] // cols) * 9 // 16
     if wl["name"] == "passthrough":
         tw, th = wl["W"], wl["H"]
-    y, u, v = harness.smooth_yuv420(1, iw, ih)
-    uv = np.stack([u, v], axis=-1)
+    k = min(CPU_TILES, n)
+    tiles_in = []
+    for t in range(k):
+        y, u, v = harness.smooth_yuv420(1 + t, iw, ih)
+        tiles_in.append((y, np.stack([u, v], axis=-1)))
     mode = orc.MODE_CPU_OPTIMIZED if wl["mode"] == s.RenderingMode.CpuOptimized else orc.MODE_GPU_OPTIMIZED
     radius = 0.0 if wl["name"] in ("cfg2", "passthrough") else 32.0
     layers = [orc.make_layout(orc.LAYOUT_COLOR, 0, 0, tw, th, color=BG),
@@ -181,55 +205,42 @@ def cpu_sample(wl, repeats=1):
                               masks=[((radius,) * 4, 0, 0, tw, th)] if radius else [])]
     if wl["name"] in ("cfg3", "cfg3b"):  # this tile's share of the alpha overlay
         layers.append(orc.make_layout(orc.LAYOUT_COLOR, th * 0.3, 0, tw, th * 0.5, color=(16, 32, 160, 112)))
-    def once():
+
+    def once(y, uv):
         t0 = time.perf_counter()
         node = orc.nv12_to_rgba(y, uv, iw, ih)
-        if wl["name"] == "passthrough":
-            img = node
-        else:
-            img = orc.render_layout_node(tw, th, layers, [node], mode=mode)
+        img = node if wl["name"] == "passthrough" else orc.render_layout_node(tw, th, layers, [node], mode=mode)
         orc.rgba_to_nv12(img)
         return time.perf_counter() - t0
-    # "all the host threads it can use": the fastest OpenMP team among every logical CPU of the affinity mask, half
-    # of them (physical cores) and a quarter -- SMT / cgroup quotas make the largest team the slowest on some boxes
-    global _CPU_TEAM
-    if _CPU_TEAM is None:
-        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        timed = []
-        for team in sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4)}, reverse=True):
-            orc.set_num_threads(team)
-            once()
-            timed.append((once(), team))
-        _CPU_TEAM = min(timed)[1]
-    orc.set_num_threads(_CPU_TEAM)
-    best = None
-    for _ in range(repeats):
-        dt = once()
-        best = dt if best is None else min(best, dt)
-    desc = (f"1 of {n} tiles: one {iw}x{ih} NV12 input -> {tw}x{th} NV12 region with the tile's layers; "
-            f"frame time = {n} x sample")
-    return best, desc, orc.num_threads()
+
+    orc.set_num_threads(cpu_team())
+    out = []
+    for i in range(warmup + steps):
+        dt = sum(once(y, uv) for (y, uv) in tiles_in) * n / k
+        if i >= warmup:
+            out.append(dt)
+    desc = (f"{k} of {n} tiles per step: each one {iw}x{ih} NV12 input -> {tw}x{th} NV12 region with the tile's layers; "
+            f"frame time = {n}/{k} x the step's tile times; value = 1 / median over the steps; "
+            f"OpenMP team = 1 thread per physical core")
+    return out, desc, orc.num_threads()
 
 
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU path cannot run here (Rust + wgpu, no rustc / Vulkan ICD in
-    the image), so this arm times the CPU oracle -- the restatement of that path -- on all host threads."""
+    the image), so this arm times the CPU oracle -- the restatement of that path -- on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    samples = []
-    desc, cores = "", 1
-    for i in range(args.warmup + args.steps):
-        dt, desc, cores = cpu_sample(wl)
-        if i >= args.warmup:
-            samples.append(dt)
-    per_frame = float(np.mean(samples)) * wl["tiles"]
+    times, desc, cores = cpu_steps(wl, max(args.steps, 5), max(args.warmup, 1))
+    per_frame = float(np.median(times))
     fps = 1.0 / per_frame
-    line = {"impl": "reference", "metric": "composited output frames/sec", "value": fps, "unit": "frames/s",
+    line = {"impl": "reference", "metric": metric_name(wl), "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_frame * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 math on u8 planes (f16 resampler scratch)",
+            "data": "synthetic",
             "config": {"workload": wl["name"], "detail": wl["desc"]},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                             "spread": {"min_ms": float(np.min(times)) * 1e3, "max_ms": float(np.max(times)) * 1e3, "steps": len(times)}},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -283,10 +294,8 @@ def main():
     out_ids = [f"output_{k + 1}".encode() for k in range(n_out)]
     if wl["name"] == "cfg4":
         for k in range(n_out):
-            g = rank * n_out + k   # global output index
-            kids = [s.InputStreamComponent(input_id=f"input_{(g + j) % n + 1}") for j in range(4)]
             r.update_scene(out_ids[k].decode(), s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture,
-                           s.TilesComponent(children=kids, background_color=s.RGBAColor(*BG)))
+                           cfg4_scene(rank * n_out + k, n))
     else:
         r.update_scene("output_1", s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture, wl["scene"])
     # shared-input replication (only cfg4 has inputs referenced from several GPUs)
@@ -484,11 +493,12 @@ def main():
     # ---- cpu baseline (rank 0, N = 1 only) ------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, desc, cores = cpu_sample(wl, repeats=2)
-        cpu = {"value": 1.0 / (dt * wl["tiles"]), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+        times, desc, cores = cpu_steps(wl, 5, 1)   # the same procedure as the --impl reference arm
+        cpu = {"value": 1.0 / float(np.median(times)), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+               "spread": {"min_ms": float(np.min(times)) * 1e3, "max_ms": float(np.max(times)) * 1e3, "steps": len(times)}}
 
     if rank == 0:
-        line = {"metric": "4K composited frames/sec (16-input grid) per GPU" if wl["name"] == "cfg3" else "composited output frames/sec",
+        line = {"metric": metric_name(wl),
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 math on u8 planes (f16 resampler scratch)", "data": "synthetic",

@@ -510,10 +510,20 @@ int launch_resample(const ResampleJob *jobs_dev, const ResampleJob *jobs_host, i
 
 __constant__ float c_wint[5][32];   // [S][tap]
 __constant__ float c_winv[5];       // 1 / weight_sum
+__constant__ float2 c_wpair[5][32]; // [S][tap] = (w[tap], w[tap - S]): the b-channel FFMA2 of two adjacent output columns
 
 void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s) {
     cudaMemcpyToSymbolAsync(c_wint, weights_dev, sizeof(float) * taps, sizeof(float) * 32 * S, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
     cudaMemcpyToSymbolAsync(c_winv, inv_dev, sizeof(float), sizeof(float) * S, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+    // (w[t], w[t - S]) pairs: two strided device-to-device copies into the float2 table (taps below S keep y = 0)
+    float *pair = nullptr;
+    cudaGetSymbolAddress((void **)&pair, c_wpair);
+    pair += 2 * 32 * S;
+    cudaMemsetAsync(pair, 0, sizeof(float2) * 32, (cudaStream_t)s);
+    cudaMemcpy2DAsync(pair, sizeof(float2), weights_dev, sizeof(float), sizeof(float), taps, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+    if (taps > S)
+        cudaMemcpy2DAsync(pair + 2 * S + 1, sizeof(float2), weights_dev, sizeof(float), sizeof(float), taps - S,
+                          cudaMemcpyDeviceToDevice, (cudaStream_t)s);
 }
 
 template <int S>   // S = 0: any ratio <= 4 (weights per column from shared memory)
@@ -835,13 +845,41 @@ static bool launch_fused_src(int src, const FusedJob *jobs_dev, const FusedPiece
     }
 }
 
+}  // namespace dev
+}  // namespace smr
+namespace smr {
+namespace dev {
+#include "resample_tma.cuh"
+
+template <int S, int SRC>
+static bool launch_tma(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks, cudaStream_t s) {
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(v5::k_resample_tma<S, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, v5::Cfg<S>::SMEM);
+        done.fetch_or(bit, std::memory_order_release);
+    }
+    v5::k_resample_tma<S, SRC><<<nblocks, dim3(32, v5::kWarps), v5::Cfg<S>::SMEM, s>>>(jobs_dev, pieces, piece_begin);
+    return check_launch("k_resample_tma");
+}
+
 // src: 0 planar 4:2:0, 1 NV12, 2 UYVY, 3 YUYV (fused_source_class)
 int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
                           const int *piece_begin_dev, int nblocks, Stream s) {
     if (nblocks <= 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
     bool ok = false;
+    static_assert(v5::Cfg<4>::NOUT == kTmaStripCols4 && v5::Cfg<2>::NOUT == kTmaStripCols2, "strip widths");
+    static_assert(v5::Cfg<4>::RROWS == kTmaRing4 && v5::Cfg<2>::RROWS == kTmaRing2, "ring rows");
+    static_assert(v5::kLumaBox == 2 * kTmaLumaBoxW && v5::kChunkRows == kTmaLumaBoxH && v5::kNv12Box == 2 * kTmaNv12BoxW &&
+                  v5::kPlanarBox == kTmaPlanarBoxW && v5::kChromaRows == kTmaChromaBoxH, "TMA boxes");
     switch (variant) {
+        case 12: ok = src == 1 ? launch_tma<2, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                               : launch_tma<2, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 14: ok = src == 1 ? launch_tma<4, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                               : launch_tma<4, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         case 2: ok = launch_fused_src<2>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         case 3: ok = launch_fused_src<3>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         case 4: ok = launch_fused_src<4>(src, jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;

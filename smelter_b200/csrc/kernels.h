@@ -120,7 +120,10 @@ struct FusedJob {
     const int32_t *first_h;
     const float *w_v, *inv_v;
     const int32_t *first_v;
-    int32_t variant;        // 0: any ratio (weights from smem); 2,3,4: integer horizontal ratio (constant-bank weights)
+    int32_t variant;        // 0: any ratio (weights from smem); 2,3,4: integer horizontal ratio (constant-bank weights);
+                            // 12, 14: integer ratio 2 / 4 on the TMA-staged kernel (k_resample_tma, resample_tma.cuh)
+    // TMA variants: device copies of the CUtensorMap of each source plane (luma; NV12 chroma as u16 texels, or U; V)
+    const void *tm0, *tm1, *tm2;
 };
 // a contiguous run of output rows of one 64-column strip of one job; each block of the persistent grid gets an
 // equal share of the launch's rows as a short list of pieces (renderer.cpp: partition_fused)
@@ -129,6 +132,12 @@ struct FusedPiece {
 };
 // limits the host checks before choosing the fused kernel (mirrors FS_* in kernels.cu)
 constexpr int kFusedStripCols = 64, kFusedWarps = 8, kFusedRing = 64, kFusedSpan = 280, kFusedMaxTaps = 25;
+// TMA-staged variants: output columns per strip, ring rows (>= taps_v + ceil(7 * vertical scale)), box sizes of the
+// tensor maps the host encodes (bytes x rows; NV12 chroma in u16 texels)
+constexpr int kTmaStripCols4 = 58, kTmaStripCols2 = 122, kTmaRing4 = 54, kTmaRing2 = 28;
+// luma and NV12 chroma are addressed in 2-byte elements (a box may be at most 256 elements wide), planar chroma in bytes
+constexpr int kTmaLumaBoxW = 136, kTmaLumaBoxH = 32, kTmaNv12BoxW = 144, kTmaPlanarBoxW = 160, kTmaChromaBoxH = 18;
+inline int fused_strip_cols(int variant) { return variant == 14 ? kTmaStripCols4 : variant == 12 ? kTmaStripCols2 : kFusedStripCols; }
 
 struct WeightJob {          // resample.wgsl:42-86 evaluated once per output coordinate
     float scale, offset;

@@ -10,6 +10,7 @@
 // stream: [convert inputs that feed a Lanczos pass] -> [weights for new mappings] -> [box passes] ->
 // [first passes] -> [last passes] -> one composite(+YUV writeback) launch per output.  All transient
 // textures live in a frame arena in HBM that is recycled every tick.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -104,11 +105,11 @@ static int resample_taps(float scale) {  // resample.wgsl:43-48
 // output rows a block produces per step).  Block b owns pieces [begin[b], begin[b+1]); every output row of every
 // strip belongs to exactly one piece.
 void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst_h, int n_jobs, int max_blocks,
-                          std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin) {
+                          std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin, int strip_cols = dev::kFusedStripCols) {
     pieces.clear(); begin.clear();
     long long total = 0;
     for (int i = 0; i < n_jobs; i++)
-        if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + dev::kFusedStripCols - 1) / dev::kFusedStripCols) * dst_h[i];
+        if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + strip_cols - 1) / strip_cols) * dst_h[i];
     if (total <= 0 || max_blocks <= 0) return;
     const int nblocks = (int)std::min<long long>((long long)max_blocks, (total + 7) / 8);
     const long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
@@ -116,7 +117,7 @@ void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst
     long long room = per_block;
     for (int i = 0; i < n_jobs; i++) {
         if (dst_w[i] <= 0 || dst_h[i] <= 0) continue;
-        const int strips = (dst_w[i] + dev::kFusedStripCols - 1) / dev::kFusedStripCols;
+        const int strips = (dst_w[i] + strip_cols - 1) / strip_cols;
         for (int st = 0; st < strips; st++) {
             int y = 0;
             while (y < dst_h[i]) {
@@ -195,6 +196,39 @@ static bool nccl_load(std::string &err) {
         !g_nccl.GroupEnd) { err = "libnccl lacks required symbols"; return false; }
     g_nccl.lib = h;
     return true;
+}
+
+// TMA descriptors of the input planes (k_resample_tma): cuTensorMapEncodeTiled through the runtime's driver entry
+// point, so libcuda is not a link-time dependency.  2-D, no swizzle, zero fill outside the plane.
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static std::once_flag once;
+    static tmap_encode_fn fn = nullptr;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)p;
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+// elem_bytes 1 (u8 planes) or 2 (the NV12 chroma plane as (u, v) texels); width in elements
+static bool encode_plane_tmap(const uint8_t *p, int pitch, int width_elems, int rows, int elem_bytes, int box_w, int box_h,
+                              CUtensorMap *out) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc || ((uintptr_t)p & 15) || (pitch & 15) || width_elems <= 0 || rows <= 0) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)width_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)p, dims, strides, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,6 +323,18 @@ class Renderer {
     std::vector<int> stage_src_tex_[3];       // texture-table index of the source, or -1 when src is a frame-arena f16
     bool int_weights_set_[5] = {false, false, false, false, false};
     std::vector<std::pair<int, WeightEntry>> pending_int_weights_;
+    std::vector<WeightKey> new_weight_keys_;   // cache entries whose k_weights launch is not enqueued yet
+    void rollback_weights();                   // a tick that fails before that launch must not leave them behind
+    // TMA variants of the fused resample: descriptors of the source planes, cached per (pointer, pitch, size, kind)
+    struct TmapKey {
+        uintptr_t p; int pitch, w, h, kind;
+        bool operator<(const TmapKey &o) const { return std::tie(p, pitch, w, h, kind) < std::tie(o.p, o.pitch, o.w, o.h, o.kind); }
+    };
+    std::map<TmapKey, CUtensorMap> tmap_cache_;
+    bool plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, CUtensorMap *out);
+    std::vector<CUtensorMap> tick_tmaps_;      // three per TMA job
+    std::vector<int> fused_tmap_idx_;          // per fused job: first of its three entries in tick_tmaps_, or -1
+    bool disable_tma_ = false;                 // SMR_DISABLE_TMA=1: A/B switch back to the LDG-staged kernels
     std::vector<dev::FusedJob> fused_jobs_;
     std::vector<std::pair<int, size_t>> fused_src_dst_;   // (raw tex index, frame offset of dst)
     std::vector<dev::WeightJob> weight_jobs_;
@@ -375,6 +421,7 @@ smr_status Renderer::init() {
     if (opts_.max_layouts_count == 0) opts_.max_layouts_count = 100;  // DEFAULT_MAX_LAYOUTS_COUNT
     if (opts_.max_layouts_count > 1024) opts_.max_layouts_count = 1024;
     if (opts_.cuda_device == -1) { host_only_ = true; return SMR_OK; }  // scene/layout inspection only
+    if (const char *e = getenv("SMR_DISABLE_TMA")) disable_tma_ = e[0] == '1';
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
@@ -613,14 +660,33 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     j.w_h = wh.weights; j.inv_h = wh.inv; j.first_h = wh.first;
     j.w_v = wv.weights; j.inv_v = wv.inv; j.first_v = wv.first;
     j.variant = 0;
+    int tmap_idx = -1;
     if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) {
         j.variant = (int)sh;
         if (!int_weights_set_[j.variant]) {   // enqueued after k_weights of this tick (same stream)
             int_weights_set_[j.variant] = true;
             pending_int_weights_.push_back({j.variant, wh});
         }
+        // TMA-staged kernel: ratio 2 or 4, planar 4:2:0 / NV12 planes a descriptor can address (16-byte aligned rows),
+        // even target width, the vertical footprint of 8 output rows inside the ring
+        const int ring = j.variant == 4 ? dev::kTmaRing4 : dev::kTmaRing2;
+        if (!disable_tma_ && (j.variant == 2 || j.variant == 4) && src_class < 2 && (dw & 1) == 0 &&
+            (int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 1 <= ring) {
+            CUtensorMap m[3];
+            memset(m, 0, sizeof(m));
+            bool ok = plane_tmap(t.p0, t.pitch0, t.width, t.height, 0, &m[0]);
+            if (src_class == 1) ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 1, &m[1]);
+            else ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 2, &m[1]) &&
+                      plane_tmap(t.p2, t.pitch2, t.width / 2, t.height / 2, 2, &m[2]);
+            if (ok) {
+                tmap_idx = (int)tick_tmaps_.size();
+                tick_tmaps_.insert(tick_tmaps_.end(), m, m + 3);
+                j.variant += 10;
+            }
+        }
     }
     fused_jobs_.push_back(j);
+    fused_tmap_idx_.push_back(tmap_idx);
     fused_src_dst_.push_back({in.raw_tex, dst_off});
     dev::Tex out;
     out.kind = dev::TEX_RGBA8; out.width = dw; out.height = dh; out.pitch0 = dw * 4;
@@ -629,6 +695,34 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     tex_opaque_.push_back(1);   // the fused kernel reads YUV and writes alpha 255
     tex_frame_off_.push_back(dst_off);
     return idx;
+}
+
+bool Renderer::plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, CUtensorMap *out) {
+    TmapKey key{(uintptr_t)p, pitch, w, h, kind};
+    auto it = tmap_cache_.find(key);
+    if (it != tmap_cache_.end()) { *out = it->second; return true; }
+    bool ok = kind == 0   ? encode_plane_tmap(p, pitch, w / 2, h, 2, dev::kTmaLumaBoxW, dev::kTmaLumaBoxH, out)
+              : kind == 1 ? encode_plane_tmap(p, pitch, w, h, 2, dev::kTmaNv12BoxW, dev::kTmaChromaBoxH, out)
+                          : encode_plane_tmap(p, pitch, w, h, 1, dev::kTmaPlanarBoxW, dev::kTmaChromaBoxH, out);
+    if (!ok) return false;
+    if (tmap_cache_.size() > 2048) tmap_cache_.clear();
+    tmap_cache_[key] = *out;
+    return true;
+}
+
+// Weight tables created by a tick whose k_weights launch was never enqueued hold uninitialised memory: drop them
+// (and the constant-bank flags that tick set) so that the next tick computes them.
+void Renderer::rollback_weights() {
+    for (const WeightKey &k : new_weight_keys_) {
+        auto it = weights_.find(k);
+        if (it == weights_.end()) continue;
+        cudaFree(it->second.weights); cudaFree(it->second.inv); cudaFree(it->second.first);
+        weights_.erase(it);
+    }
+    new_weight_keys_.clear();
+    for (auto &pw : pending_int_weights_) int_weights_set_[pw.first] = false;
+    pending_int_weights_.clear();
+    weight_jobs_.clear();
 }
 
 void Renderer::shader_color(const RGBA &c, float out[4]) const {  // wgpu/utils.rs:51-71 + params.rs:353-361
@@ -878,9 +972,15 @@ smr_status Renderer::get_weights(const KernelPass &p, WeightEntry &out) {
     e.taps = resample_taps(scale);
     if (e.taps < 1 || e.taps > 4096) { set_error("resampler tap count out of range"); return SMR_ERR_INVALID_ARGUMENT; }
     e.last_used = tick_;
-    CUDA_OK(cudaMalloc(&e.weights, sizeof(float) * (size_t)e.taps * key.n_out));
-    CUDA_OK(cudaMalloc(&e.inv, sizeof(float) * key.n_out));
-    CUDA_OK(cudaMalloc(&e.first, sizeof(int32_t) * key.n_out));
+    if (cudaMalloc(&e.weights, sizeof(float) * (size_t)e.taps * key.n_out) != cudaSuccess ||
+        cudaMalloc(&e.inv, sizeof(float) * key.n_out) != cudaSuccess ||
+        cudaMalloc(&e.first, sizeof(int32_t) * key.n_out) != cudaSuccess) {
+        cudaFree(e.weights); cudaFree(e.inv); cudaFree(e.first);
+        cudaGetLastError();
+        set_error("out of device memory for resampler weight tables");
+        return SMR_ERR_CUDA;
+    }
+    new_weight_keys_.push_back(key);
     dev::WeightJob j;
     j.scale = scale; j.offset = offset; j.n_out = key.n_out; j.taps = e.taps;
     j.weights = e.weights; j.inv_wsum = e.inv; j.first = e.first;
@@ -1171,7 +1271,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     uploaded_ = false;
     tex_table_.clear(); tex_opaque_.clear(); tex_frame_off_.clear();
     for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
-    fused_jobs_.clear(); fused_src_dst_.clear();
+    fused_jobs_.clear(); fused_src_dst_.clear(); fused_tmap_idx_.clear(); tick_tmaps_.clear();
+    rollback_weights();   // leftovers of a tick that failed before its weight launch (normally empty)
     weight_jobs_.clear(); convert_jobs_.clear(); composites_.clear(); output_jobs_.clear(); output_src_tex_.clear();
     fills_.clear(); d2h_.clear(); resample_cache_.clear();
     param_used_ = 0; frame_used_ = 0;
@@ -1183,6 +1284,10 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         if (in[i].input_id) res_map[in[i].input_id] = {in[i].width, in[i].height};
     scene_.register_render_event(pts, std::move(res_map));
 
+    struct WeightGuard {   // any return before the k_weights launch is enqueued drops this tick's new cache entries
+        Renderer *r; bool armed = true;
+        ~WeightGuard() { if (armed) r->rollback_weights(); }
+    } weight_guard{this};
     smr_status st = populate_inputs(pts, in, n_in);
     if (st != SMR_OK) return st;
     for (uint32_t i = 0; i < n_out; i++) {
@@ -1233,6 +1338,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     for (int s = 0; s < 3; s++) stage_off[s] = param_alloc(sizeof(dev::ResampleJob) * std::max<size_t>(stage_jobs_[s].size(), 1));
     wj_off = param_alloc(sizeof(dev::WeightJob) * std::max<size_t>(weight_jobs_.size(), 1));
     size_t fj_off = param_alloc(sizeof(dev::FusedJob) * std::max<size_t>(fused_jobs_.size(), 1));
+    const size_t tm_off = param_alloc(sizeof(CUtensorMap) * std::max<size_t>(tick_tmaps_.size(), 1));   // 256-byte aligned
     // partition the fused resamples of the tick over a persistent grid, one launch per kernel variant
     struct FusedLaunch { int variant; int src; size_t pieces_off, begin_off; int nblocks; };
     std::vector<FusedLaunch> fused_launches;
@@ -1251,7 +1357,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             }
             std::vector<dev::FusedPiece> pieces;
             std::vector<int> begin;
-            partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(), sm_count_ * 3, pieces, begin);
+            partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(), sm_count_ * 3, pieces, begin,
+                                 dev::fused_strip_cols(v.first));
             if (pieces.empty()) continue;
             FusedLaunch fl;
             fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
@@ -1269,13 +1376,19 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         if (!stage_jobs_[s].empty())
             memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
-    if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
+    if (!tick_tmaps_.empty()) memcpy(param_host_.data() + tm_off, tick_tmaps_.data(), sizeof(CUtensorMap) * tick_tmaps_.size());
     // composite jobs: their device pointers are known once the arena is sized; with two or more outputs in the tick
     // the jobs travel in the arena and run as ONE launch
     const size_t cj_off = param_alloc(sizeof(dev::CompositeJob) * std::max<size_t>(composites_.size(), 1));
     if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
     CUDA_OK(param_pinned_[slot_].ensure(param_used_));
     CUDA_OK(param_dev_[slot_].ensure(param_used_));
+    for (size_t i = 0; i < fused_jobs_.size(); i++)
+        if (fused_tmap_idx_[i] >= 0) {
+            const uint8_t *m = param_dev_[slot_].p + tm_off + sizeof(CUtensorMap) * (size_t)fused_tmap_idx_[i];
+            fused_jobs_[i].tm0 = m; fused_jobs_[i].tm1 = m + sizeof(CUtensorMap); fused_jobs_[i].tm2 = m + 2 * sizeof(CUtensorMap);
+        }
+    if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
     {
         uint8_t *pd0 = param_dev_[slot_].p;
         for (size_t i = 0; i < composites_.size(); i++) {
@@ -1307,6 +1420,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     if (!weight_jobs_.empty()) prof_mark(SMR_KERNEL_WEIGHTS);
     for (auto &pw : pending_int_weights_) dev::set_int_weights(pw.first, pw.second.weights, pw.second.inv, pw.second.taps, stream_);
     pending_int_weights_.clear();
+    new_weight_keys_.clear();
+    weight_guard.armed = false;   // the tables are being computed on the stream: the cache entries are good
     for (const FusedLaunch &fl : fused_launches) {
         if (!launched(dev::launch_resample_fused(fl.variant, fl.src, (const dev::FusedJob *)(pd + fj_off),
                                                  (const dev::FusedPiece *)(pd + fl.pieces_off), (const int *)(pd + fl.begin_off),

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes tens of seconds on the GPU box (still part of -m gpu)")
 
 
 def pytest_collection_modifyitems(config, items):
