@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <cstring>
 
@@ -37,6 +38,11 @@ __device__ float c_thr[256];  // 255 used
 #define ENC_KEYS ((13 << 5) + 1)     // ... up to x = 1.0
 __device__ unsigned char c_enc0[420];
 __device__ float c_yl[256];   // limited-range luma, already expanded: clamp01((n/255 - 16/255) * RCP_Y)
+// finer buckets (exponent + top 8 mantissa bits): every bucket holds AT MOST ONE threshold, so the encode is the
+// bucket's count plus one comparison -- no search loop (checked on the host when the table is built)
+#define ENC1_KEY0 ((127 - 13) << 8)
+#define ENC1_KEYS ((13 << 8) + 1)
+__device__ unsigned char c_enc1[ENC1_KEYS + 3];
 
 static thread_local char g_err[256] = {0};   // a launch and the read of its error happen on the same thread
 const char *last_launch_error() { return g_err; }
@@ -73,6 +79,20 @@ void upload_tables(const float *u8n, const float *dec, const float *thr) {
         enc0[k] = (unsigned char)e;
     }
     cudaMemcpyToSymbol(c_enc0, enc0, sizeof(enc0));
+    static unsigned char enc1[ENC1_KEYS + 3];
+    for (int k = 0; k < ENC1_KEYS; k++) {
+        const uint32_t bits = (uint32_t)(k + ENC1_KEY0) << 15;
+        float lo;
+        memcpy(&lo, &bits, 4);
+        int e = 0;
+        while (e < 255 && lo >= t[e]) e++;
+        enc1[k] = (unsigned char)e;
+        if (k > 0 && enc1[k] - enc1[k - 1] > 1) {   // two thresholds inside one bucket: the one-compare encode would be wrong
+            fprintf(stderr, "smelter_b200: sRGB encode bucket table is too coarse at key %d\n", k);
+            abort();
+        }
+    }
+    cudaMemcpyToSymbol(c_enc1, enc1, sizeof(enc1));
 }
 
 struct Tables {  // per-block shared-memory copies (divergent indices would serialise in constant memory)

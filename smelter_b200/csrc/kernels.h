@@ -124,6 +124,7 @@ struct FusedJob {
                             // 12, 14: integer ratio 2 / 4 on the TMA-staged kernel (k_resample_tma, resample_tma.cuh)
     // TMA variants: device copies of the CUtensorMap of each source plane (luma; NV12 chroma as u16 texels, or U; V)
     const void *tm0, *tm1, *tm2;
+    int32_t v_same;         // TMA variants: the vertical mapping is the same integer ratio with zero offset (weights = c_wint[S])
 };
 // a contiguous run of output rows of one 64-column strip of one job; each block of the persistent grid gets an
 // equal share of the launch's rows as a short list of pieces (renderer.cpp: partition_fused)

@@ -681,6 +681,7 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
             if (ok) {
                 tmap_idx = (int)tick_tmaps_.size();
                 tick_tmaps_.insert(tick_tmaps_.end(), m, m + 3);
+                j.v_same = vm.crop_offset == 0.0f && sv == sh && tv == th;
                 j.variant += 10;
             }
         }

@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
 
     for (int i = tid; i < kDecN; i += 32 * kWarps) s_dec[i] = c_dec[min(max(i - kDecLo, 0), 255)];
     for (int i = tid; i < 256; i += 32 * kWarps) s_thr[i] = c_thr[i];
-    for (int i = tid; i < 420; i += 32 * kWarps) s_enc0[i] = c_enc0[i];
     if (tid == 0) {
         // table address such that entry i = [(float bits of (i + 1.5 * 2^23)) << 2 + kaddr]  (mod 2^32); it takes a
         // round trip through shared memory so that it stays ONE register and the lookup address ONE LEA
@@ -475,11 +474,23 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
                 for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = make_float2(0.f, 0.f);
                 const bool inside = fv >= 0 && fv + tv - 1 <= H - 1;
                 const float *lbase = ring + lane * 3 * OUT;
-                if (inside) {
+                constexpr int ROWF = K::RROW_BYTES / 4;
+                if (inside && J.v_same) {
+                    // same integer ratio vertically: the weights are the constant-bank row, the tap loop unrolls; the ring
+                    // wraps at most once inside the window (warp-uniform tap index)
+                    const int slot0 = fv % K::RROWS, nwrap = K::RROWS - slot0;
+                    const float *p0 = lbase + slot0 * ROWF;
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++) {
+                        const float *p = p0 + (t >= nwrap ? (t - K::RROWS) * ROWF : t * ROWF);
+#pragma unroll
+                        for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = fma2(*reinterpret_cast<const float2 *>(p + 2 * k), splat(c_wint[S][t]), acc[k]);
+                    }
+                } else if (inside) {
                     int slot = fv % K::RROWS;
                     for (int t = 0; t < tv; t++) {
                         const float wt = __ldg(wv + t);
-                        const float *p = lbase + slot * (K::RROW_BYTES / 4);
+                        const float *p = lbase + slot * ROWF;
 #pragma unroll
                         for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = fma2(*reinterpret_cast<const float2 *>(p + 2 * k), splat(wt), acc[k]);
                         slot = slot + 1 == K::RROWS ? 0 : slot + 1;
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
                     for (int t = 0; t < tv; t++) {
                         const float wt = __ldg(wv + t);
                         const int row = min(max(fv + t, 0), H - 1);
-                        const float *p = lbase + (row % K::RROWS) * (K::RROW_BYTES / 4);
+                        const float *p = lbase + (row % K::RROWS) * ROWF;
 #pragma unroll
                         for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = fma2(*reinterpret_cast<const float2 *>(p + 2 * k), splat(wt), acc[k]);
                     }
@@ -501,13 +512,11 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
                     const float rv = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
                     const float gv = (j & 1) ? acc[(OUT + j) / 2].y : acc[(OUT + j) / 2].x;
                     const float bv = (j & 1) ? acc[(2 * OUT + j) / 2].y : acc[(2 * OUT + j) / 2].x;
-                    auto enc = [&](float lin) -> uint32_t {   // NC-4, same search as srgb_encode()
+                    auto enc = [&](float lin) -> uint32_t {   // NC-4: count of thresholds <= x = bucket count + one comparison
                         const float x = clamp01(lin);
-                        const int k = (__float_as_int(x) >> 18) - ENC_KEY0;
-                        if (k < 0) return 0u;
-                        int e = s_enc0[k];
-                        while (x >= s_thr[e]) e++;
-                        return (uint32_t)e;
+                        const int k = max((__float_as_int(x) >> 15) - ENC1_KEY0, 0);
+                        const uint32_t e = __ldg(c_enc1 + k);
+                        return e + (x >= s_thr[e] ? 1u : 0u);
                     };
                     px[j] = enc(rv * inv_v) | (enc(gv * inv_v) << 8) | (enc(bv * inv_v) << 16) | 0xff000000u;
                 }

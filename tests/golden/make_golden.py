@@ -10,13 +10,13 @@ import os
 
 import smelter_b200 as s
 from tests.golden.cases import CASES, digest
-from tests.parity import OUTPUT_ID, oracle_output
+from tests.parity import OUTPUT_ID, TrackedRenderer, oracle_output
 
 
 def expected_planes(name):
     scene_f, frames_f, res, fmt, mode, pts = CASES[name]
     scene, frames = scene_f(), frames_f()
-    r = s.Renderer(s.RendererOptions(rendering_mode=mode, cuda_device=-1))
+    r = TrackedRenderer(s.RendererOptions(rendering_mode=mode, cuda_device=-1))   # layouts from the independent engine
     for iid in frames:
         r.register_input(iid)
     r.update_scene(OUTPUT_ID, res, fmt, scene)

@@ -4,6 +4,7 @@ import numpy as np
 
 import smelter_b200 as s
 from oracle import oracle as orc
+from tests import layout_ref as LR
 
 OUTPUT_ID = "output_1"
 
@@ -28,6 +29,61 @@ def to_oracle_layout(l):
                            (l.border_color.r, l.border_color.g, l.border_color.b, l.border_color.a),
                            l.border_width, l.blur_radius, l.child_index,
                            (l.crop_top, l.crop_left, l.crop_width, l.crop_height), masks)
+
+
+class TrackedRenderer(s.Renderer):
+    """A Renderer whose scene updates are mirrored into the INDEPENDENT layout engine (tests/layout_ref.py), so that the
+    oracle is fed layouts the product did not compute (and the product's own are checked against them)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.ref_scenes = {}
+
+    def update_scene(self, output_id, resolution, out_format, scene):
+        super().update_scene(output_id, resolution, out_format, scene)
+        st = self.ref_scenes.get(output_id)
+        if st is None or (st.out_w, st.out_h) != (resolution.width, resolution.height):
+            st = self.ref_scenes[output_id] = LR.StatefulScene(resolution.width, resolution.height)
+        st.update_scene(scene)
+
+
+def from_ref_layout(l):
+    kind = {"child": orc.LAYOUT_TEXTURE, "color": orc.LAYOUT_COLOR, "shadow": orc.LAYOUT_BOX_SHADOW}[l.kind]
+    masks = [(tuple(float(x) for x in m.radius.tup()), float(m.top), float(m.left), float(m.width), float(m.height)) for m in l.masks]
+    crop = (0, 0, 0, 0) if l.crop is None else (float(l.crop.top), float(l.crop.left), float(l.crop.width), float(l.crop.height))
+    return orc.make_layout(kind, float(l.top), float(l.left), float(l.width), float(l.height), float(l.rotation),
+                           tuple(float(x) for x in l.border_radius.tup()), l.color, l.border_color, float(l.border_width),
+                           float(l.blur_radius), max(l.index, 0), crop, masks)
+
+
+def layouts_equal(prod, ref):
+    """field-for-field, bit-for-bit as f32, of the product's flattened layouts and the independent ones"""
+    import numpy as np
+    if len(prod) != len(ref):
+        return f"{len(prod)} layouts, independent engine has {len(ref)}"
+    kinds = {0: "child", 1: "color", 2: "shadow"}
+    eq = lambda a, b: np.float32(a) == np.float32(b) or (np.isnan(np.float32(a)) and np.isnan(np.float32(b)))
+    for i, (p, r) in enumerate(zip(prod, ref)):
+        if kinds[p.type] != r.kind:
+            return f"layout {i}: kind {kinds[p.type]} vs {r.kind}"
+        pairs = [(p.top, r.top), (p.left, r.left), (p.width, r.width), (p.height, r.height), (p.rotation_degrees, r.rotation)]
+        pairs += list(zip(p.border_radius, r.border_radius.tup()))
+        if r.kind == "shadow":
+            pairs.append((p.blur_radius, r.blur_radius))
+        else:
+            pairs.append((p.border_width, r.border_width))
+        if r.kind == "child":
+            pairs += [(p.crop_top, r.crop.top), (p.crop_left, r.crop.left), (p.crop_width, r.crop.width), (p.crop_height, r.crop.height)]
+            if p.child_index != r.index:
+                return f"layout {i}: child index {p.child_index} vs {r.index}"
+        if p.masks_len != len(r.masks):
+            return f"layout {i}: {p.masks_len} masks vs {len(r.masks)}"
+        for k in range(p.masks_len):
+            m, q = p.masks[k], r.masks[k]
+            pairs += list(zip(m.radius, q.radius.tup())) + [(m.top, q.top), (m.left, q.left), (m.width, q.width), (m.height, q.height)]
+        if not all(eq(a, b) for a, b in pairs):
+            return f"layout {i} ({r.kind}): {[(float(a), float(b)) for a, b in pairs if not eq(a, b)][:4]}"
+    return None
 
 
 def node_texture(frame: s.Frame):
@@ -65,10 +121,17 @@ def oracle_output(renderer, scene, frames, resolution, out_format, mode, pts, li
         rgba = node_texture(fr)
     else:
         layouts, (rw, rh) = renderer.debug_layouts(OUTPUT_ID, pts)
+        ref = getattr(renderer, "ref_scenes", {}).get(OUTPUT_ID)
+        if ref is not None:   # layouts from the independent engine; the product's must be identical
+            res = {k: (f.resolution.width, f.resolution.height) for k, f in live.items()}
+            ref_layouts, ref_root = ref.layouts(pts, res)
+            assert (rw, rh) == ref_root, f"root resolution {(rw, rh)} vs independent engine {ref_root}"
+            d = layouts_equal(layouts, ref_layouts)
+            assert d is None, f"product layouts differ from the independent engine: {d}"
         if rw == 0 or rh == 0:
             return black(resolution, out_format)
         nodes = [node_texture(live[i]) if i in live else None for i in leaf_inputs(scene)]
-        layouts = [to_oracle_layout(l) for l in layouts]
+        layouts = [from_ref_layout(l) for l in ref_layouts] if ref is not None else [to_oracle_layout(l) for l in layouts]
         rgba = orc.render_layout_node(rw, rh, layouts, nodes, mode=mode, max_layouts=renderer.opts.max_layouts_count)
     W, H = resolution.width, resolution.height
     if out_format == s.OutputFrameFormat.RgbaWgpuTexture:
@@ -109,7 +172,7 @@ def product_planes(frame: s.Frame):
 def run_case(scene, frames, resolution=s.Resolution(640, 360), out_format=s.OutputFrameFormat.PlanarYuv420Bytes,
              mode=s.RenderingMode.GpuOptimized, pts=0.0, renderer=None, updates=None, max_layouts=100):
     """frames: {input_id: Frame}.  Returns (product planes, oracle planes, renderer)."""
-    r = renderer or s.Renderer(s.RendererOptions(rendering_mode=mode, max_layouts_count=max_layouts))
+    r = renderer or TrackedRenderer(s.RendererOptions(rendering_mode=mode, max_layouts_count=max_layouts))
     if renderer is None:
         for iid in frames:
             r.register_input(iid)

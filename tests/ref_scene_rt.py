@@ -36,7 +36,7 @@ def Padding(top=0.0, right=0.0, bottom=0.0, left=0.0):
 
 
 def Resolution(width, height):
-    return s.Resolution(width, height)
+    return s.Resolution(int(width), int(height))   # usize arithmetic in the Rust tests (e.g. height / 2) truncates
 
 
 def InputId(x):

@@ -7,7 +7,7 @@ import pytest
 
 import smelter_b200 as s
 from tests import harness
-from tests.parity import OUTPUT_ID, assert_identical, nv12_frame, run_case, wide_chroma_frame, yuv_frame
+from tests.parity import OUTPUT_ID, TrackedRenderer, assert_identical, nv12_frame, run_case, wide_chroma_frame, yuv_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -102,7 +102,7 @@ def test_missing_frame_gives_black_and_culls_layer():
     assert np.all(y == 16) and np.all(u == 128) and np.all(v == 128)
     # missing input inside Tiles: slot reserved, nothing drawn there
     fr = inputs(1)
-    r2 = s.Renderer()
+    r2 = TrackedRenderer()
     for i in (1, 2):
         r2.register_input(f"input_{i}")
     scene = s.TilesComponent(children=streams(2), background_color=BG)
@@ -218,7 +218,7 @@ def test_transition_fractional_geometry(pts):
         return V(background_color=BG, children=[
             s.RescalerComponent(id="r", child=streams(1)[0], transition=tr,
                                 position=s.Position.Absolute(width=w, height=w * 9 / 16, left=left, top=33.0))])
-    r = s.Renderer()
+    r = TrackedRenderer()
     r.register_input("input_1")
     r.update_scene(OUTPUT_ID, RES, YUV, scene(200.0, 10.0))
     fr = inputs(1)
