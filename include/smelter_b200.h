@@ -8,7 +8,10 @@
  *
  * Conventions: plain C types only; every function returns smr_status (0 = ok) and never throws or
  * aborts across the boundary; ids are NUL-terminated UTF-8 (the reference's `InputId`/`OutputId`
- * are `Arc<str>`); all pointers are borrowed for the duration of the call only; a handle is
+ * are `Arc<str>`); all pointers are borrowed for the duration of the call only -- with ONE exception: the HOST planes
+ * (inputs and outputs) handed to smr_render_begin are read / written by asynchronous copies and must stay valid and
+ * untouched until the smr_render_end that retires that tick (smr_render has no such window: it returns when the tick
+ * it submitted is complete); a handle is
  * internally synchronised exactly like the reference's `Arc<Mutex<InnerRenderer>>` (state.rs:54-55).
  * The product path has NO CPU fallback: every pixel is produced by sm_100a CUDA kernels.
  */
@@ -230,8 +233,10 @@ smr_status smr_unregister_output(smr_renderer *r, const char *output_id);
 smr_status smr_render(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
                       smr_output_frame *outputs, uint32_t n_outputs);
 
-/* The same with the waits split off, so a caller can overlap ticks:
- * smr_render_begin enqueues uploads + kernels + downloads and returns; smr_render_end waits. */
+/* The same with the waits split off, so a caller can overlap ticks (at most two in flight):
+ * smr_render_begin enqueues uploads + kernels + downloads and returns; smr_render_end retires the OLDEST tick in
+ * flight.  Host planes of a tick belong to the library from its smr_render_begin until the smr_render_end that
+ * retires it.  A plane's pitch must be >= its row bytes (SMR_ERR_INVALID_ARGUMENT otherwise). */
 smr_status smr_render_begin(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
                             smr_output_frame *outputs, uint32_t n_outputs);
 smr_status smr_render_end(smr_renderer *r);

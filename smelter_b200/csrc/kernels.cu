@@ -100,7 +100,6 @@ struct Tables {  // per-block shared-memory copies (divergent indices would seri
     float dec[256];
     float thr[256];
     float yl[256];
-    unsigned char enc0[420];
 };
 
 __device__ __forceinline__ void load_tables(Tables &t) {
@@ -109,8 +108,6 @@ __device__ __forceinline__ void load_tables(Tables &t) {
         t.dec[i] = c_dec[i];
         t.thr[i] = c_thr[i];
         t.yl[i] = c_yl[i];
-        t.enc0[i] = c_enc0[i];
-        if (i + 256 < 420) t.enc0[i + 256] = c_enc0[i + 256];
     }
     __syncthreads();
 }
@@ -120,16 +117,14 @@ __device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }  //
 __device__ __forceinline__ int unorm8(float x) { return __float2int_rn(clamp01(x) * 255.0f); }  // NC-2
 
 // NC-4: the encoded byte is the number of decision thresholds <= x (thr[] ascending, thr[255] is a sentinel).
-// enc0[] holds that count at the lower edge of each bucket of the float's (exponent, top 5 mantissa bits), so the
-// scan from there passes the few thresholds inside the bucket (at most 2: the curve is steepest, 0.8 codes per
-// bucket, just above the linear segment) instead of evaluating pow().
+// c_enc1[] holds that count at the lower edge of each bucket of the float's (exponent, top 8 mantissa bits); a bucket
+// contains at most one threshold (checked when the table is built), so one comparison finishes the count -- no
+// pow(), no search loop, no divergence.  The table is read through L1 (3.3 KB, read-only).
 __device__ __forceinline__ int srgb_encode(const Tables &t, float lin) {
     const float x = clamp01(lin);                                  // NaN -> 0
-    const int k = (__float_as_int(x) >> 18) - ENC_KEY0;
-    if (k < 0) return 0;
-    int e = t.enc0[k];
-    while (x >= t.thr[e]) e++;
-    return e;
+    const int k = max((__float_as_int(x) >> 15) - ENC1_KEY0, 0);   // below 2^-13 < thr[0]: bucket 0, count 0
+    const int e = __ldg(c_enc1 + k);
+    return e + (x >= t.thr[e] ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1321,6 +1316,39 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
                     const float v = (((float)(y0 + j) + 0.5f) - L.top) / L.height;
                     ay[j] = linear_tap(v * L.crop_sy + L.crop_oy, S.height);
                     if (ay[j].f == 1.0f) { ay[j].i0 = ay[j].i1; ay[j].f = 0.0f; }
+                }
+                if (S.kind != TEX_RGBA8) {
+                    // planar 4:2:0 / NV12 child scaled by the layout shader itself (CpuOptimized): the four taps of a
+                    // pixel are texels of the virtual node texture; when they form one chroma-aligned quad (e.g. an
+                    // exact 2:1 grid) K1/K2 shares the chroma interpolation between them
+#pragma unroll 1
+                    for (int j = 0; j < CT_H; j++) {
+                        const float fy = ay[j].f;
+#pragma unroll 1
+                        for (int i = 0; i < CT_W; i++) {
+                            const float fx = ax[i].f;
+                            uchar4 p00, p10, p01, p11;
+                            if (ax[i].i1 == ax[i].i0 + 1 && ay[j].i1 == ay[j].i0 + 1 && yuv_quad_ok(S, ax[i].i0, ay[j].i0)) {
+                                yuv_quad(T, S, ax[i].i0, ay[j].i0, p00, p10, p01, p11);
+                            } else {
+                                p00 = node_texel(T, S, ax[i].i0, ay[j].i0);
+                                p10 = fx != 0.0f ? node_texel(T, S, ax[i].i1, ay[j].i0) : p00;
+                                p01 = fy != 0.0f ? node_texel(T, S, ax[i].i0, ay[j].i1) : p00;
+                                p11 = (fx != 0.0f && fy != 0.0f) ? node_texel(T, S, ax[i].i1, ay[j].i1) : (fx != 0.0f ? p10 : p01);
+                            }
+                            uchar4 o;
+                            if (fx == 0.0f && fy == 0.0f) o = p00;
+                            else {
+                                o.x = (unsigned char)unorm8(filter_u8(p00.x, p10.x, p01.x, p11.x, fx, fy));
+                                o.y = (unsigned char)unorm8(filter_u8(p00.y, p10.y, p01.y, p11.y, fx, fy));
+                                o.z = (unsigned char)unorm8(filter_u8(p00.z, p10.z, p01.z, p11.z, fx, fy));
+                            }
+                            o.w = 255;
+                            if (j == 0) { if (i == 0) px[0][0] = o; else if (i == 1) px[0][1] = o; else if (i == 2) px[0][2] = o; else px[0][3] = o; }
+                            else { if (i == 0) px[1][0] = o; else if (i == 1) px[1][1] = o; else if (i == 2) px[1][2] = o; else px[1][3] = o; }
+                        }
+                    }
+                    break;
                 }
 #pragma unroll
                 for (int j = 0; j < CT_H; j++) {

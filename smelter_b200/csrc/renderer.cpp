@@ -244,6 +244,7 @@ class Renderer {
     smr_status unregister_output(const char *id);
     smr_status render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out, uint32_t n_out);
     smr_status render_end();
+    smr_status render_end_all();
     smr_status preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch, int32_t mem_kind);
     smr_status debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
     smr_status debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap, uint32_t *n,
@@ -584,6 +585,13 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
             if (!plane_layout(f->format, f->width, f->height, p, row_bytes, rows)) continue;
             if (!f->planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
             size_t spitch = f->pitch[p] ? f->pitch[p] : row_bytes;
+            if (spitch < row_bytes) { set_error("input plane pitch is smaller than a row"); return SMR_ERR_INVALID_ARGUMENT; }
+            if (f->mem_kind == SMR_MEM_DEVICE && (f->format == SMR_FRAME_UYVY422 || f->format == SMR_FRAME_YUYV422 ||
+                                                  f->format == SMR_FRAME_RGBA8 || f->format == SMR_FRAME_BGRA || f->format == SMR_FRAME_ARGB) &&
+                (((uintptr_t)f->planes[p] | spitch) & 3)) {
+                set_error("4-byte texel planes must be 4-byte aligned (pointer and pitch)");
+                return SMR_ERR_INVALID_ARGUMENT;
+            }
             if (f->mem_kind == SMR_MEM_DEVICE) {
                 ptrs[p] = (const uint8_t *)f->planes[p];
                 pitches[p] = (int)spitch;
@@ -877,9 +885,14 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
                 d.fast |= dev::FAST_IDENT;
                 if (tex_opaque_[tex_index]) d.fast |= dev::FAST_OPAQUE;
                 d.tx_off = -(int)l.left; d.ty_off = -(int)l.top;
-            } else if (l.kind == RenderLayout::ChildNode && tex_index >= 0 && tex_opaque_[tex_index] &&
-                       tex_table_[tex_index].kind == dev::TEX_RGBA8 && l.width > 0.0f && l.height > 0.0f) {
-                // opaque resampled child at a fractional position / size: filtered sample alone, target ignored
+            } else if (l.kind == RenderLayout::ChildNode && tex_index >= 0 && tex_opaque_[tex_index] && l.width > 0.0f &&
+                       l.height > 0.0f &&
+                       (tex_table_[tex_index].kind == dev::TEX_RGBA8 ||
+                        (opts_.rendering_mode == SMR_MODE_CPU_OPTIMIZED &&
+                         (tex_table_[tex_index].kind == dev::TEX_NV12 || tex_table_[tex_index].kind == dev::TEX_YUV420)))) {
+                // opaque child at a fractional position / size: filtered sample alone, target ignored.  RGBA8: a
+                // resampled child; planar 4:2:0 / NV12 in CpuOptimized: the layout shader's own bilinear scaling of
+                // the (virtual) node texture, K1/K2 evaluated per tap quad
                 d.fast |= dev::FAST_SAMPLE | dev::FAST_OPAQUE;
             }
         }
@@ -1024,6 +1037,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
         if (!row_bytes[p]) continue;
         if (!of.planes[p]) { set_error("output plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
         size_t user_pitch = of.pitch[p] ? of.pitch[p] : row_bytes[p];
+        if (user_pitch < row_bytes[p]) { set_error("output plane pitch is smaller than a row"); return SMR_ERR_INVALID_ARGUMENT; }
         if (of.mem_kind == SMR_MEM_DEVICE) {
             dst[p] = (uint8_t *)of.planes[p];
             pitch[p] = (int)user_pitch;
@@ -1504,6 +1518,19 @@ smr_status Renderer::render_end() {   // retires the OLDEST tick in flight
     return SMR_OK;
 }
 
+smr_status Renderer::render_end_all() {   // smr_render: "blocks until the output planes are complete" -- of THIS tick
+    std::lock_guard<std::mutex> g(mu_);
+    if (inflight_.empty()) return SMR_OK;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    while (!inflight_.empty()) {
+        int s = inflight_.front();
+        inflight_.pop_front();
+        CUDA_OK(cudaEventSynchronize(tick_done_[s]));
+    }
+    fold_profile();
+    return SMR_OK;
+}
+
 void Renderer::fold_profile() {
     // fold this tick's event pairs into the per-kernel-class totals
     for (size_t i = 1; i < prof_marks_.size(); i++) {
@@ -1593,6 +1620,7 @@ smr_status Renderer::comm_destroy() {
     std::lock_guard<std::mutex> g(mu_);
     if (nccl_comm_) {
         cudaSetDevice(opts_.cuda_device);
+        cudaStreamSynchronize(comm_stream_);   // the collectives run here
         cudaStreamSynchronize(stream_);
         g_nccl.CommDestroy(nccl_comm_);
         nccl_comm_ = nullptr;
@@ -1727,7 +1755,7 @@ smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, 
     if (!r) return SMR_ERR_INVALID_ARGUMENT;
     smr_status st = smr_render_begin(r, pts, in, n_in, out, n_out);
     if (st != SMR_OK) return st;
-    return smr_render_end(r);
+    SMR_GUARD(r->impl.render_end_all())   // every tick in flight, the one just submitted included
 }
 smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap,
                              uint32_t *n, uint32_t *rw, uint32_t *rh) { SMR_GUARD(r->impl.debug_layouts(output_id, pts, out, cap, n, rw, rh)) }

@@ -540,3 +540,43 @@ def test_many_layers_beyond_the_parameter_bank():
         kids.append(V(position=s.Position.Absolute(width=90.0 - i, height=70.0 - i, left=300.0 + i * 0.5, top=150.0 + i * 0.25),
                       background_color=s.RGBAColor((i * 5) % 256, 200, (i * 17) % 256, 200)))
     check(V(children=kids, background_color=BG), inputs(1), max_layouts=400)
+
+
+def test_failed_tick_does_not_poison_the_weight_cache():
+    """A tick that fails AFTER planning (its second output is not registered) created Lanczos weight-cache entries whose
+    k_weights launch never ran; the next good tick must recompute them (the cache used to keep the
+    uninitialised tables forever)."""
+    fr = inputs(2)
+    scene = s.TilesComponent(children=streams(2), background_color=BG)
+    r = TrackedRenderer()
+    for i in fr:
+        r.register_input(i)
+    r.update_scene(OUTPUT_ID, RES, YUV, scene)
+    r._outputs["ghost"] = (RES, YUV)          # known to the Python mirror only: the library refuses it after output_1
+    with pytest.raises(s.RenderSceneError):
+        r.render(s.FrameSet(frames=fr, pts=0.0), outputs=[OUTPUT_ID, "ghost"])
+    del r._outputs["ghost"]
+    got, exp, _ = run_case(scene, fr, renderer=r)
+    assert_identical(got, exp, "good tick after a failed one")
+
+
+def test_pitch_smaller_than_a_row_is_refused():
+    from smelter_b200 import _ffi as F
+    import ctypes as C
+    r = s.Renderer()
+    r.register_input("input_1")
+    r.update_scene(OUTPUT_ID, RES, YUV, V(children=streams(1)))
+    y, u, v = harness.test_input(1)
+    keep = []
+    arr = r._input_frames(s.FrameSet(frames={"input_1": yuv_frame((y, u, v), 640, 360)}, pts=0.0), keep)
+    arr[0].pitch[0] = 320                      # luma rows are 640 bytes
+    out = (F.OutputFrame * 1)()
+    bufs = [np.empty(640 * 360, np.uint8), np.empty(320 * 180, np.uint8), np.empty(320 * 180, np.uint8)]
+    out[0].output_id = OUTPUT_ID.encode()
+    out[0].mem_kind = F.MEM_HOST
+    for p in range(3):
+        out[0].planes[p] = bufs[p].ctypes.data
+    assert r._lib.smr_render(r._h, 0, arr, 1, out, 1) == 1   # SMR_ERR_INVALID_ARGUMENT
+    arr[0].pitch[0] = 0
+    out[0].pitch[1] = 100                      # chroma rows are 320 bytes
+    assert r._lib.smr_render(r._h, 0, arr, 1, out, 1) == 1
