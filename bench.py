@@ -246,6 +246,95 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, nvar=2):
+    """BASELINE config 4 on the running process group: 8 outputs per GPU, every tick replicates the pool of 8 shared
+    1080p inputs from their ingest GPUs over NVLink (smr_comm_exchange_inputs) and composites 8 frames.  Returns the
+    device-timed aggregate frames/s (max over ranks) and the bytes the exchange moved per tick."""
+    import smelter_b200 as s
+    from smelter_b200 import _ffi as F
+    wl = workload("cfg4")
+    n, iw, ih, W, H, n_out = wl["n"], wl["iw"], wl["ih"], wl["W"], wl["H"], wl["n_out"]
+    r = s.Renderer(s.RendererOptions(rendering_mode=wl["mode"], cuda_device=local))
+    ids = [f"input_{i}".encode() for i in range(1, n + 1)]
+    for b in ids:
+        r.register_input(b.decode())
+    out_ids = [f"output_{k + 1}".encode() for k in range(n_out)]
+    for k in range(n_out):
+        r.update_scene(out_ids[k].decode(), s.Resolution(W, H), s.OutputFrameFormat.Nv12WgpuTexture, cfg4_scene(rank * n_out + k, n))
+    roots = [i % world for i in range(n)]
+    if world > 1:
+        uid = [r.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        r.comm_init(uid[0], rank, world)
+    order = sorted(range(n), key=lambda i: (roots[i], i))
+    frames, arrs = [], []
+    for v in range(nvar):
+        planes = [synth_planes_torch(torch, dev, iw, ih, 0x5EED4000 + 1000 * v + i + 97 * rank) for i in range(n)]
+        pool = torch.empty(sum(t.numel() for i in order for t in planes[i]), dtype=torch.uint8, device=dev)
+        off, packed = 0, {}
+        for i in order:   # one pool per ingest GPU, identical layout on every rank (SMR_COMM_POOLED)
+            views = []
+            for t in planes[i]:
+                view = pool[off:off + t.numel()].view(t.shape)
+                view.copy_(t)
+                views.append(view)
+                off += t.numel()
+            packed[i] = tuple(views)
+        frames.append((pool, packed))
+        arr = (F.InputFrame * n)()
+        for k, i in enumerate(order):
+            yv, uvv = packed[i]
+            arr[k].input_id = ids[i]
+            arr[k].format = F.FRAME_NV12
+            arr[k].width, arr[k].height = iw, ih
+            arr[k].mem_kind = F.MEM_DEVICE
+            arr[k].planes[0], arr[k].planes[1] = yv.data_ptr(), uvv.data_ptr()
+        arrs.append(arr)
+    comm_roots = [roots[i] for i in order]
+    out_y = [torch.empty((H, W), dtype=torch.uint8, device=dev) for _ in range(n_out)]
+    out_uv = [torch.empty((H // 2, W // 2, 2), dtype=torch.uint8, device=dev) for _ in range(n_out)]
+    dev_out = (F.OutputFrame * n_out)()
+    for k in range(n_out):
+        dev_out[k].output_id = out_ids[k]
+        dev_out[k].mem_kind = F.MEM_DEVICE
+        dev_out[k].planes[0], dev_out[k].planes[1] = out_y[k].data_ptr(), out_uv[k].data_ptr()
+    stream = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
+    frame_ns = 33_333_333
+
+    def step(k):
+        a = arrs[k % nvar]
+        for f in a:
+            f.pts_ns = k * frame_ns
+        if world > 1:
+            r.comm_exchange_inputs(a, n, comm_roots, None, pooled=True)
+        r.render_raw(k * frame_ns, a, n, dev_out, n_out, wait=False)
+
+    for k in range(warmup):
+        step(k)
+    r.wait()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        step(warmup + k)
+    r.wait()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if world > 1:
+        r.comm_destroy()
+    moved = sum(iw * ih * 3 // 2 for i in range(n)) * (world - 1) if world > 1 else 0   # every input reaches the other N-1 GPUs
+    return {"workload": "cfg4", "detail": wl["desc"], "value": world * n_out * steps / (ms * 1e-3), "unit": "frames/s",
+            "ms_per_tick": ms / steps, "steps": steps, "outputs_per_gpu": n_out,
+            "nvlink_broadcast_bytes_per_tick": moved, "scaling": "weak"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -257,6 +346,7 @@ def main():
     ap.add_argument("--variants", type=int, default=4, help="distinct synthetic frames per input, cycled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the cfg4 (NVLink exchange) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = workload(args.workload)
@@ -363,7 +453,7 @@ def main():
         for a in dev_in[k % nvar]:
             a.pts_ns = k * frame_ns
         if roots is not None:   # the tick's exchange step: one NCCL group on the render stream
-            r.comm_broadcast_inputs(comm_in[k % nvar], n, comm_roots)
+            r.comm_exchange_inputs(comm_in[k % nvar], n, comm_roots, None, pooled=True)
         r.render_raw(k * frame_ns, dev_in[k % nvar], n, dev_out, n_out, wait=False)
 
     # ---- value: device-resident, device-timed ---------------------------------------------------------
@@ -486,9 +576,24 @@ def main():
             e2e_s = float(t.item())
         h2d_expected = n * iw * ih * 3 // 2
         assert (st1["h2d_bytes"] - st0["h2d_bytes"]) == h2d_expected * ke, "e2e leg: some ticks did not upload their inputs"
+        h2d_step = (st1["h2d_bytes"] - st0["h2d_bytes"]) // ke
+        d2h_step = (st1["d2h_bytes"] - st0["d2h_bytes"]) // ke
+        # what the link can do on this box: pinned H2D of the same planes, back to back on one stream, nothing else running
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        probe_dst = [torch.empty_like(host_frames[0][i][0], device=dev) for i in range(n)]
+        for rep in range(2):
+            pe0.record()
+            for i in range(n):
+                probe_dst[i].copy_(host_frames[0][i][0], non_blocking=True)
+            pe1.record()
+            torch.cuda.synchronize()
+        probe_gbs = sum(t.numel() for t in probe_dst) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+        fps_rank = n_out * ke / e2e_s
         e2e = {"value": world * n_out * ke / e2e_s, "unit": "frames/s", "steps": ke,
-               "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // ke,
-               "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // ke}
+               "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+               "pcie_h2d_gbs": h2d_step * (ke / e2e_s) / 1e9, "pcie_d2h_gbs": d2h_step * (ke / e2e_s) / 1e9,
+               "pcie_h2d_probe_gbs": probe_gbs, "pcie_frac_of_probe": h2d_step * (ke / e2e_s) / 1e9 / probe_gbs,
+               "per_gpu_frames_s": fps_rank}
 
     # ---- cpu baseline (rank 0, N = 1 only) ------------------------------------------------------------------
     cpu = None
@@ -497,16 +602,20 @@ def main():
         cpu = {"value": 1.0 / float(np.median(times)), "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
                "spread": {"min_ms": float(np.min(times)) * 1e3, "max_ms": float(np.max(times)) * 1e3, "steps": len(times)}}
 
+    secondary = None
+    if world > 1 and wl["name"] == "cfg3" and not args.no_secondary:
+        secondary = measure_cfg4(torch, dist, dev, rank, world, local, max(args.steps, 20), args.warmup)
     if rank == 0:
         line = {"metric": metric_name(wl),
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 math on u8 planes (f16 resampler scratch)", "data": "synthetic",
                 "config": {"workload": wl["name"], "detail": wl["desc"], "outputs_per_gpu": n_out,
-                           "nvlink_broadcast_bytes_per_tick": (n * iw * ih * 3 // 2) * (world - 1) if roots is not None else 0,
+                           "nvlink_broadcast_bytes_per_tick": (n * iw * ih * 3 // 2) * (world - 1) if roots is not None else (secondary or {}).get("nvlink_broadcast_bytes_per_tick", 0),
                            "l2_policy": f"inputs larger than L2: {nvar} distinct frame sets of "
                                         f"{wl['alg_bytes'] / 1e6:.0f} MB cycled (> 126 MB L2)",
-                           "algorithmic_bytes_per_frame": wl["alg_bytes"], "wall_s_timed_region": t_wall},
+                           "algorithmic_bytes_per_frame": wl["alg_bytes"], "wall_s_timed_region": t_wall,
+                           "secondary": secondary},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if roots is not None:

@@ -284,11 +284,25 @@ smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, i
  * Asynchronous: the NCCL group runs on the handle's communication stream, after every tick submitted BEFORE the most
  * recent smr_render_begin has finished and before the next smr_render_begin's kernels -- i.e. it overlaps the tick in
  * flight.  The planes must therefore not be the ones the most recently submitted tick reads (alternate two sets).
- * Consecutive planes of the list that share a root and are contiguous in memory are sent as ONE ncclBroadcast, so
- * every rank must lay its planes out identically (same contiguity) -- e.g. one frame pool per ingest GPU. */
+ * smr_comm_broadcast_inputs replicates every frame to every rank, one ncclBroadcast per plane.
+ * smr_comm_exchange_inputs is the selective form: consumer_masks[i] has bit k set when rank k hosts an output that
+ * reads frame i (NULL = every rank); a frame all ranks need is broadcast, any other is sent point to point
+ * (ncclSend / ncclRecv in the same group) to exactly its consumers.  flags: SMR_COMM_POOLED declares that the planes
+ * are laid out identically on every rank (one frame pool per ingest GPU); only then are consecutive planes that share
+ * root and consumers and are contiguous in memory merged into one message.  All ranks must pass the same list. */
+#define SMR_COMM_POOLED 1u
 smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n,
                                      const int32_t *root_ranks);
+smr_status smr_comm_exchange_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks,
+                                    const uint64_t *consumer_masks, uint32_t flags);
 smr_status smr_comm_destroy(smr_renderer *r);
+
+/* Texture upload / read-back glue of smelter-core (pipeline/decoder/ffmpeg_utils.rs:67-79 copy_plane_from_av,
+ * pipeline/encoder/ffmpeg_utils.rs:77-84 write_plane_to_av_frame): a frame pool the caller keeps across ticks is
+ * page-locked ONCE; SMR_MEM_HOST planes inside a registered range are then moved by direct DMA (no staging copy in
+ * the driver), uploads of a tick are spread over two copy streams.  Already registered memory is not an error. */
+smr_status smr_host_register(void *ptr, size_t bytes);
+smr_status smr_host_unregister(void *ptr);
 
 smr_status smr_get_stats(smr_renderer *r, smr_stats *out);
 smr_status smr_set_profiling(smr_renderer *r, int32_t enabled);   /* also resets the accumulated times */

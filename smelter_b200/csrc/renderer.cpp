@@ -173,6 +173,8 @@ static struct {
     nccl_init_fn CommInitRank = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -189,11 +191,13 @@ static bool nccl_load(std::string &err) {
     g_nccl.CommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
     g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclBroadcast");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclRecv");
     g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
     g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Broadcast || !g_nccl.GroupStart ||
-        !g_nccl.GroupEnd) { err = "libnccl lacks required symbols"; return false; }
+        !g_nccl.GroupEnd || !g_nccl.Send || !g_nccl.Recv) { err = "libnccl lacks required symbols"; return false; }
     g_nccl.lib = h;
     return true;
 }
@@ -356,7 +360,9 @@ class Renderer {
     DevBuf frame_dev_;
     std::map<WeightKey, WeightEntry> weights_;
     // up to two ticks in flight: uploads of tick n+1 (copy stream) overlap the kernels of tick n
-    cudaStream_t copy_stream_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr, copy_stream2_ = nullptr;   // uploads alternate between two streams (two DMA engines)
+    cudaEvent_t h2d_done2_[2] = {nullptr, nullptr};
+    int upload_rr_ = 0;
     cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, tick_done_[2] = {nullptr, nullptr};
     // the tick's exchange step overlaps the previous tick's kernels: NCCL runs on its own stream, ordered after
     // everything submitted BEFORE the most recent tick and before the next one
@@ -370,6 +376,7 @@ class Renderer {
     void drain() {
         if (stream_) cudaStreamSynchronize(stream_);
         if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+        if (copy_stream2_) cudaStreamSynchronize(copy_stream2_);
         if (comm_stream_) cudaStreamSynchronize(comm_stream_);
         fold_profile();
         inflight_.clear();
@@ -389,7 +396,8 @@ class Renderer {
     int comm_rank_ = 0, comm_size_ = 1;
   public:
     smr_status comm_init(const uint8_t *id, int rank, int nranks);
-    smr_status comm_broadcast(const smr_input_frame *frames, uint32_t n, const int32_t *roots);
+    smr_status comm_exchange(const smr_input_frame *frames, uint32_t n, const int32_t *roots, const uint64_t *consumers,
+                             uint32_t flags);
     smr_status comm_destroy();
     smr_status set_profiling(int enabled);
     void kernel_times(smr_kernel_times *out) { std::lock_guard<std::mutex> g(mu_); *out = prof_; }
@@ -400,6 +408,8 @@ Renderer::~Renderer() {
         cudaSetDevice(opts_.cuda_device);
         cudaStreamSynchronize(stream_);
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+        if (copy_stream2_) { cudaStreamSynchronize(copy_stream2_); cudaStreamDestroy(copy_stream2_); }
+        for (int i = 0; i < 2; i++) if (h2d_done2_[i]) cudaEventDestroy(h2d_done2_[i]);
         if (comm_stream_) { cudaStreamSynchronize(comm_stream_); cudaStreamDestroy(comm_stream_); }
         if (comm_done_) cudaEventDestroy(comm_done_);
         if (tick_start_) cudaEventDestroy(tick_start_);
@@ -436,6 +446,8 @@ smr_status Renderer::init() {
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&copy_stream2_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CUDA_OK(cudaEventCreateWithFlags(&h2d_done2_[i], cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&comm_done_, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&tick_start_, cudaEventDisableTiming));
@@ -597,12 +609,12 @@ smr_status Renderer::populate_inputs(uint64_t pts, const smr_input_frame *in, ui
                 pitches[p] = (int)spitch;
             } else {
                 CUDA_OK(I.planes[slot_][p].ensure(row_bytes * rows));
+                cudaStream_t cs = (upload_rr_++ & 1) ? copy_stream2_ : copy_stream_;
                 if (spitch == row_bytes)   // tightly packed (the reference's bytes::Bytes planes): one linear DMA
-                    CUDA_OK(cudaMemcpyAsync(I.planes[slot_][p].p, f->planes[p], row_bytes * rows, cudaMemcpyHostToDevice,
-                                            copy_stream_));
+                    CUDA_OK(cudaMemcpyAsync(I.planes[slot_][p].p, f->planes[p], row_bytes * rows, cudaMemcpyHostToDevice, cs));
                 else
                     CUDA_OK(cudaMemcpy2DAsync(I.planes[slot_][p].p, row_bytes, f->planes[p], spitch, row_bytes, rows,
-                                              cudaMemcpyHostToDevice, copy_stream_));
+                                              cudaMemcpyHostToDevice, cs));
                 uploaded_ = true;
                 stats_.h2d_bytes += row_bytes * rows;
                 ptrs[p] = I.planes[slot_][p].p;
@@ -1328,6 +1340,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     if (uploaded_) {   // kernels of this tick start after its uploads; earlier ticks keep running meanwhile
         CUDA_OK(cudaEventRecord(h2d_done_[slot_], copy_stream_));
         CUDA_OK(cudaStreamWaitEvent(stream_, h2d_done_[slot_], 0));
+        CUDA_OK(cudaEventRecord(h2d_done2_[slot_], copy_stream2_));
+        CUDA_OK(cudaStreamWaitEvent(stream_, h2d_done2_[slot_], 0));
     }
     if (frame_used_ + 512 > frame_dev_.cap && !inflight_.empty()) CUDA_OK(cudaStreamSynchronize(stream_));
     CUDA_OK(frame_dev_.ensure(frame_used_ + 512));
@@ -1578,39 +1592,61 @@ smr_status Renderer::comm_init(const uint8_t *id, int rank, int nranks) {
     return SMR_OK;
 }
 
-smr_status Renderer::comm_broadcast(const smr_input_frame *frames, uint32_t n, const int32_t *roots) {
+// consumers[i]: bit k set = rank k hosts an output that reads frame i (NULL: every rank).  A frame every rank needs
+// goes out as ncclBroadcast (ring / tree / NVLS inside NCCL); a frame only some ranks need is sent point to point to
+// exactly those ranks, so a rank that does not consume it neither receives nor stores it.
+smr_status Renderer::comm_exchange(const smr_input_frame *frames, uint32_t n, const int32_t *roots, const uint64_t *consumers,
+                                   uint32_t flags) {
     std::lock_guard<std::mutex> g(mu_);
     if (!nccl_comm_) { set_error("smr_comm_init was not called"); return SMR_ERR_INVALID_ARGUMENT; }
     if (n && (!frames || !roots)) return SMR_ERR_INVALID_ARGUMENT;
+    if (comm_size_ > 64 && consumers) { set_error("consumer masks cover at most 64 ranks"); return SMR_ERR_UNSUPPORTED; }
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     // Runs on its own stream so that it overlaps the kernels of the tick submitted last; it is ordered after every
     // EARLIER tick (whose buffers the caller may be recycling) and before the next smr_render_begin.
     if (tick_started_) CUDA_OK(cudaStreamWaitEvent(comm_stream_, tick_start_, 0));
-    // one ncclBroadcast per run of planes that share a root and are contiguous in memory (an ingest GPU's frame pool):
-    // the host cost of the group scales with the number of calls, not with the bytes
-    struct Run { uint8_t *p; size_t bytes; int root; };
+    const uint64_t all = comm_size_ >= 64 ? ~0ull : ((1ull << comm_size_) - 1ull);
+    // SMR_COMM_POOLED: the caller declares that the planes are laid out identically on every rank (e.g. one frame pool
+    // per ingest GPU), so consecutive planes with the same root and consumers that are contiguous HERE are contiguous
+    // everywhere and go out as one message.  Without the declaration nothing is merged: the sequence of collectives
+    // must not depend on a rank's allocator.
+    struct Run { uint8_t *p; size_t bytes; int root; uint64_t mask; };
     std::vector<Run> runs;
     for (uint32_t i = 0; i < n; i++) {
         const smr_input_frame &f = frames[i];
-        if (f.mem_kind != SMR_MEM_DEVICE) { set_error("broadcast needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (f.mem_kind != SMR_MEM_DEVICE) { set_error("the exchange needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
         if (roots[i] < 0 || roots[i] >= comm_size_) return SMR_ERR_INVALID_ARGUMENT;
+        const uint64_t mask = ((consumers ? consumers[i] : all) | (1ull << roots[i])) & all;
         for (int p = 0; p < 3; p++) {
             size_t row_bytes = 0, rows = 0;
             if (!plane_layout(f.format, f.width, f.height, p, row_bytes, rows)) continue;
             if (!f.planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
             size_t pitch = f.pitch[p] ? f.pitch[p] : row_bytes;
+            if (pitch < row_bytes) { set_error("input plane pitch is smaller than a row"); return SMR_ERR_INVALID_ARGUMENT; }
             size_t bytes = pitch * (rows - 1) + row_bytes;
             uint8_t *ptr = (uint8_t *)f.planes[p];
-            if (!runs.empty() && runs.back().root == roots[i] && runs.back().p + runs.back().bytes == ptr) runs.back().bytes += bytes;
-            else runs.push_back({ptr, bytes, roots[i]});
+            if ((flags & SMR_COMM_POOLED) && !runs.empty() && runs.back().root == roots[i] && runs.back().mask == mask &&
+                runs.back().p + runs.back().bytes == ptr)
+                runs.back().bytes += bytes;
+            else
+                runs.push_back({ptr, bytes, roots[i], mask});
         }
     }
     int rc = g_nccl.GroupStart();
-    for (size_t i = 0; i < runs.size() && rc == 0; i++)
-        rc = g_nccl.Broadcast(runs[i].p, runs[i].p, runs[i].bytes, /*ncclUint8*/ 1, runs[i].root, nccl_comm_, comm_stream_);
+    for (size_t i = 0; i < runs.size() && rc == 0; i++) {
+        const Run &R = runs[i];
+        if (R.mask == all) {
+            rc = g_nccl.Broadcast(R.p, R.p, R.bytes, /*ncclUint8*/ 1, R.root, nccl_comm_, comm_stream_);
+        } else if (comm_rank_ == R.root) {
+            for (int k = 0; k < comm_size_ && rc == 0; k++)
+                if (k != R.root && ((R.mask >> k) & 1ull)) rc = g_nccl.Send(R.p, R.bytes, 1, k, nccl_comm_, comm_stream_);
+        } else if ((R.mask >> comm_rank_) & 1ull) {
+            rc = g_nccl.Recv(R.p, R.bytes, 1, R.root, nccl_comm_, comm_stream_);
+        }
+    }
     int rc2 = g_nccl.GroupEnd();
     if (rc == 0) rc = rc2;
-    if (rc != 0) { set_error(std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
+    if (rc != 0) { set_error(std::string("NCCL exchange: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
     CUDA_OK(cudaEventRecord(comm_done_, comm_stream_));
     comm_pending_ = true;
     return SMR_OK;
@@ -1770,7 +1806,9 @@ smr_status smr_comm_get_unique_id(uint8_t id[128]) {
     return SMR_OK;
 }
 smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, int32_t nranks) { SMR_GUARD(r->impl.comm_init(id, rank, nranks)) }
-smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks) { SMR_GUARD(r->impl.comm_broadcast(frames, n, root_ranks)) }
+smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks) { SMR_GUARD(r->impl.comm_exchange(frames, n, root_ranks, nullptr, 0)) }
+smr_status smr_comm_exchange_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks,
+                                    const uint64_t *consumer_masks, uint32_t flags) { SMR_GUARD(r->impl.comm_exchange(frames, n, root_ranks, consumer_masks, flags)) }
 smr_status smr_comm_destroy(smr_renderer *r) { SMR_GUARD(r->impl.comm_destroy()) }
 smr_status smr_set_profiling(smr_renderer *r, int32_t enabled) { SMR_GUARD(r->impl.set_profiling(enabled)) }
 smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out) {
@@ -1784,6 +1822,19 @@ smr_status smr_get_stats(smr_renderer *r, smr_stats *out) {
     return SMR_OK;
 }
 void *smr_cuda_stream(smr_renderer *r) { return r ? r->impl.stream() : nullptr; }
+// page-lock a caller-owned frame buffer once, so that every later upload / download of it is a direct DMA
+smr_status smr_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return SMR_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SMR_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return SMR_ERR_CUDA; }
+    return SMR_OK;
+}
+smr_status smr_host_unregister(void *ptr) {
+    if (!ptr) return SMR_ERR_INVALID_ARGUMENT;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return SMR_ERR_CUDA; }
+    return SMR_OK;
+}
 const char *smr_last_error(smr_renderer *r) { return r ? r->impl.last_error() : g_create_error.c_str(); }
 const char *smr_version(void) { return "smelter_b200 0.1 (sm_100a)"; }
 

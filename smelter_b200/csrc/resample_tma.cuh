@@ -170,10 +170,11 @@ struct ChunkIter {
     int pi, pend;
     int job, ox0, x0, oy_end, onext, ocur;
     int produced_hi, rnext, rhi;
-    bool in_group;
+    int H, tv, fv0;   // of the current piece's job; fv0 = first_v[0] when the vertical mapping is the integer ratio
+    bool in_group, vs;
     __device__ void init(const FusedJob *j, const FusedPiece *p, int b, int e) {
         jobs = j; pieces = p; pi = b - 1; pend = e; in_group = false; onext = 0; oy_end = 0;
-        job = ox0 = x0 = ocur = 0; produced_hi = rnext = rhi = 0;
+        job = ox0 = x0 = ocur = 0; produced_hi = rnext = rhi = 0; H = tv = fv0 = 0; vs = false;
     }
     __device__ Chunk next() {
         Chunk c;
@@ -184,15 +185,20 @@ struct ChunkIter {
                 if (pi >= pend) return c;
                 const FusedPiece P = pieces[pi];
                 job = P.job; ox0 = P.strip * Cfg<S>::NOUT; onext = P.oy_begin; oy_end = P.oy_end;
-                x0 = __ldg(jobs[job].first_h + ox0) - Cfg<S>::A;
+                const FusedJob &J = jobs[job];
+                x0 = __ldg(J.first_h + ox0) - Cfg<S>::A;
+                H = J.src.height; tv = J.taps_v; vs = J.v_same != 0;
+                fv0 = __ldg(J.first_v);
                 produced_hi = -0x40000000;
             }
-            const FusedJob &J = jobs[job];
-            const int H = J.src.height;
             ocur = onext;
             const int o_l = min(ocur + kWarps - 1, oy_end - 1);
-            const int need_lo = min(max(__ldg(J.first_v + ocur), 0), H - 1);
-            const int need_hi = min(max(__ldg(J.first_v + o_l) + J.taps_v - 1, 0), H - 1);
+            // same integer ratio vertically: first_v(o) = first_v(0) + S * o (resample.wgsl:45-50 in exact arithmetic), no
+            // dependent global loads on the way to the next TMA issue
+            const int f_lo = vs ? fv0 + S * ocur : __ldg(jobs[job].first_v + ocur);
+            const int f_hi = vs ? fv0 + S * o_l : __ldg(jobs[job].first_v + o_l);
+            const int need_lo = min(max(f_lo, 0), H - 1);
+            const int need_hi = min(max(f_hi + tv - 1, 0), H - 1);
             rnext = max(produced_hi + 1, need_lo);
             rhi = need_hi;
             produced_hi = max(produced_hi, need_hi);
@@ -324,11 +330,14 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
             const uint32_t c_off = (uint32_t)((dc & ~3) + lane * (NV12 ? 8 : 4)), c_sh = (uint32_t)(dc & 3) * 8u;
             // ---- phase A: one source row per warp step ------------------------------------------------------------
             for (int r = cur.r0 + warp; r < cur.r0 + cur.nrows; r += kWarps) {
-                // raw bytes of this lane's 8 pixels
+                // raw bytes of this lane's 8 pixels: 12 bytes from a 4-byte aligned address; the half that is 8-byte aligned
+                // (warp-uniform) goes as one LDS.64 (lanes 8 bytes apart: conflict-free, an LDS.32 is 2-way)
                 uint32_t yw[2];
                 {
                     const uint32_t la = sb + (uint32_t)((r - cur.r0) * kLumaBox) + l_off;
-                    const uint32_t w0 = lds32v(la), w1 = lds32v(la + 4), w2 = lds32v(la + 8);
+                    uint32_t w0, w1, w2;
+                    if (l_off & 4u) { w0 = lds32v(la); lds64v(la + 4, w1, w2); }
+                    else { lds64v(la, w0, w1); w2 = lds32v(la + 8); }
                     yw[0] = __funnelshift_r(w0, w1, l_sh);
                     yw[1] = __funnelshift_r(w1, w2, l_sh);
                 }
@@ -338,8 +347,14 @@ __global__ void __launch_bounds__(32 * kWarps, 3) k_resample_tma(const FusedJob 
                 if (NV12) {
                     const uint32_t bh = sb + kLumaBytes + (uint32_t)((ch - cyb) * kNv12Box) + c_off;
                     const uint32_t bl = sb + kLumaBytes + (uint32_t)((cl - cyb) * kNv12Box) + c_off;
-                    const uint32_t h0 = lds32v(bh), h1 = lds32v(bh + 4), h2 = lds32v(bh + 8), h3 = lds32v(bh + 12);
-                    const uint32_t l0 = lds32v(bl), l1 = lds32v(bl + 4), l2 = lds32v(bl + 8), l3 = lds32v(bl + 12);
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    if (c_off & 4u) {
+                        h0 = lds32v(bh); lds64v(bh + 4, h1, h2); h3 = lds32v(bh + 12);
+                        l0 = lds32v(bl); lds64v(bl + 4, l1, l2); l3 = lds32v(bl + 12);
+                    } else {
+                        lds64v(bh, h0, h1); lds64v(bh + 8, h2, h3);
+                        lds64v(bl, l0, l1); lds64v(bl + 8, l2, l3);
+                    }
                     // words of two texels each: (cx-1, cx), (cx+1, cx+2), (cx+3, cx+4)
                     const uint32_t ph0 = __funnelshift_r(h0, h1, c_sh), ph1 = __funnelshift_r(h1, h2, c_sh), ph2 = __funnelshift_r(h2, h3, c_sh);
                     const uint32_t pl0 = __funnelshift_r(l0, l1, c_sh), pl1 = __funnelshift_r(l1, l2, c_sh), pl2 = __funnelshift_r(l2, l3, c_sh);

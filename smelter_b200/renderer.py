@@ -598,6 +598,15 @@ class Renderer:
         arr = (C.c_int32 * max(1, n))(*roots)
         self._check(self._lib.smr_comm_broadcast_inputs(self._h, in_arr, n, arr))
 
+    COMM_POOLED = 1
+
+    def comm_exchange_inputs(self, in_arr, n, roots, consumer_masks=None, pooled=False):
+        """selective replication: frame i goes from rank roots[i] to the ranks whose bit is set in consumer_masks[i]
+        (None: to every rank); pooled=True declares an identical plane layout on every rank (contiguous runs merge)"""
+        arr = (C.c_int32 * max(1, n))(*roots)
+        masks = None if consumer_masks is None else (C.c_uint64 * max(1, n))(*consumer_masks)
+        self._check(self._lib.smr_comm_exchange_inputs(self._h, in_arr, n, arr, masks, self.COMM_POOLED if pooled else 0))
+
     def comm_destroy(self):
         self._check(self._lib.smr_comm_destroy(self._h))
 

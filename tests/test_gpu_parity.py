@@ -580,3 +580,33 @@ def test_pitch_smaller_than_a_row_is_refused():
     arr[0].pitch[0] = 0
     out[0].pitch[1] = 100                      # chroma rows are 320 bytes
     assert r._lib.smr_render(r._h, 0, arr, 1, out, 1) == 1
+
+
+def glyph_like_rgba(w, h, seed):
+    """premultiplied RGBA8 with soft (anti-aliased) coverage, like a CPU-rasterised text / image layer
+    (transformations/text_renderer.rs:282-369 ends in exactly such a texture)"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    cov = np.clip(1.2 * (np.sin(xx / 7.0 + seed) * np.cos(yy / 5.0) + 0.35), 0.0, 1.0)
+    cov = np.where(rng.random((h, w)) < 0.05, 0.0, cov)                    # holes: alpha exactly 0
+    a = np.rint(cov * 255).astype(np.uint8)
+    col = np.stack([np.full((h, w), 230), 40 + (xx * 3) % 200, 200 - (yy * 2) % 180], axis=-1).astype(np.float64)
+    rgb = np.rint(col * (a[..., None] / 255.0)).astype(np.uint8)          # premultiplied: rgb <= alpha
+    return np.concatenate([rgb, a[..., None]], axis=-1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("mode", [s.RenderingMode.GpuOptimized, s.RenderingMode.CpuOptimized])
+def test_translucent_premultiplied_rgba_layers(mode):
+    """SURVEY 8f-2 route: a text / image node arrives as a premultiplied RGBA8 input and is an ordinary
+    K9 texture layer.  1:1 over video (per-pixel alpha through the blend), scaled by a Rescaler (Lanczos on a
+    translucent RGBA source / bilinear in CpuOptimized) and with rounded corners."""
+    fr = inputs(1)
+    fr["label"] = s.Frame(s.FrameData.Rgba8(glyph_like_rgba(200, 64, 3)), s.Resolution(200, 64), 0.0)
+    fr["logo"] = s.Frame(s.FrameData.Rgba8(glyph_like_rgba(96, 96, 5)), s.Resolution(96, 96), 0.0)
+    label = V(position=s.Position.Absolute(width=200.0, height=64.0, left=40.0, top=250.0),
+              children=[s.InputStreamComponent(input_id="label")])
+    logo = s.RescalerComponent(position=s.Position.Absolute(width=171.0, height=150.0, right=20.0, top=15.0),
+                               child=s.InputStreamComponent(input_id="logo"),
+                               border_radius=s.BorderRadius.new_with_radius(18.0))
+    scene = V(background_color=BG, children=[s.RescalerComponent(child=streams(1)[0]), label, logo])
+    check(scene, fr, mode=mode)
