@@ -473,6 +473,7 @@ def main():
     e0.record(stream)
     for k in range(args.steps):
         step_dev(args.warmup + k)
+    t_submit = time.perf_counter() - t_wall0     # host time to plan and enqueue the ticks (GPU-bound when << the device time)
     r.wait()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -480,10 +481,15 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = r.stats()["kernel_launches"] - launches0
+    ms_by_rank = [ms]
     if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        g = [torch.zeros(2, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([ms, t_submit * 1e3], device=dev))
+        ms_by_rank = [float(x[0].item()) for x in g]
+        submit_by_rank = [float(x[1].item()) for x in g]
+        ms = max(ms_by_rank)
+    else:
+        submit_by_rank = [t_submit * 1e3]
     clk = clocks.stop()
     ms_per_step = ms / args.steps
     value = world * n_out * args.steps / (ms * 1e-3)
@@ -615,6 +621,8 @@ def main():
                            "l2_policy": f"inputs larger than L2: {nvar} distinct frame sets of "
                                         f"{wl['alg_bytes'] / 1e6:.0f} MB cycled (> 126 MB L2)",
                            "algorithmic_bytes_per_frame": wl["alg_bytes"], "wall_s_timed_region": t_wall,
+                           "device_ms_per_step_by_rank": [m / args.steps for m in ms_by_rank],
+                           "host_submit_ms_per_step_by_rank": [m / args.steps for m in submit_by_rank],
                            "secondary": secondary},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -248,6 +248,13 @@ smr_status smr_render_end(smr_renderer *r);
 smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *frame, uint32_t out_width, uint32_t out_height,
                                 void *rgba, uint32_t pitch, int32_t mem_kind);
 
+/* PremultiplyAlphaPipeline (wgpu/utils/add_premultiplied_alpha.rs + .wgsl:24-35), the last pass of the reference's
+ * image-asset upload (transformations/image/svg_image.rs:155-167): a STRAIGHT-alpha RGBA8 frame (format
+ * SMR_FRAME_RGBA8) -> premultiplied RGBA8 through the renderer's texture views (sRGB decode / encode around the
+ * multiplication in GpuOptimized, plain bytes in CpuOptimized).  The result is what SMR_FRAME_RGBA8 inputs of
+ * smr_render are expected to hold.  Blocking; `rgba` has height rows of `pitch` bytes (0 = tightly packed). */
+smr_status smr_premultiply_rgba8(smr_renderer *r, const smr_input_frame *frame, void *rgba, uint32_t pitch, int32_t mem_kind);
+
 /* inspection (no device needed): the balanced row partition the fused resample launch uses for jobs of
  * dst_w[i] x dst_h[i] output pixels on `max_blocks` resident blocks.  pieces: 4 ints each {job, strip, row_begin,
  * row_end}; block b owns pieces [begin[b], begin[b + 1]). */

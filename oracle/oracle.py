@@ -169,6 +169,15 @@ def rgba_to_yuv_planar_scaled(rgba, w, h, cw, ch):
     return y, u, v
 
 
+def add_premultiplied_alpha(rgba, mode=0):
+    """PremultiplyAlphaPipeline: straight-alpha RGBA8 -> premultiplied RGBA8 (add_premultiplied_alpha.wgsl)"""
+    rgba = _u8(rgba)
+    h, w = rgba.shape[:2]
+    out = np.empty((h, w, 4), np.uint8)
+    lib().orc_add_premultiplied_alpha(_p(rgba), w, h, int(mode), _p(out))
+    return out
+
+
 def rescale_rgba(rgba, ow, oh, mode=0):
     """FramePreProcessor rescale: bilinear (NC-6) sample of the node texture, stored through the target format"""
     rgba = _u8(rgba)

@@ -674,6 +674,24 @@ static inline void sample_node(const orc_texture *t, int mode, float tx, float t
  * one full-target draw, `blend: None` (rgba_rescale.rs:38-42): each target pixel is the linear-filtered sample of
  * the node texture at its centre, stored through the target format (sRGB encode in GpuOptimized, plain UNORM8 in
  * CpuOptimized; RescaleTexture::new :199-206). */
+/* wgpu/utils/add_premultiplied_alpha.wgsl:24-35 (PremultiplyAlphaPipeline): the full-screen quad samples the
+ * straight-alpha source at texel centres (one texel, weight 1) through its view, multiplies the colour by
+ * max(alpha, 1e-5), clamps and stores through the target view. */
+void orc_add_premultiplied_alpha(const uint8_t *rgba, int w, int h, int mode, uint8_t *out) {
+    orc_init();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < w * h; i++) {
+        const uint8_t *t = rgba + (size_t)i * 4;
+        uint8_t *o = out + (size_t)i * 4;
+        const float a = g_u8n[t[3]], am = fmaxf(a, 0.00001f);
+        for (int c = 0; c < 3; c++) {
+            const float v = clamp01((mode == ORC_MODE_GPU_OPTIMIZED ? g_dec[t[c]] : g_u8n[t[c]]) * am);
+            o[c] = mode == ORC_MODE_GPU_OPTIMIZED ? orc_srgb_encode_u8(v) : orc_unorm8(v);
+        }
+        o[3] = orc_unorm8(clamp01(a));
+    }
+}
+
 void orc_rescale_rgba(const uint8_t *rgba, int sw, int sh, int ow, int oh, int mode, uint8_t *out) {
     orc_texture t = {sw, sh, rgba};
 #pragma omp parallel for schedule(static)

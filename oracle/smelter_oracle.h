@@ -132,6 +132,8 @@ void orc_render_layout_node(int out_w, int out_h, const orc_layout *layouts, int
 /* --- test-harness inverse used by every reference snapshot (harness/utils.rs:31-65) ------- */
 /* FramePreProcessor's optional rescale (frame_pre_processor.rs:117-132, rgba_rescale.wgsl) */
 void orc_rescale_rgba(const uint8_t *rgba, int sw, int sh, int ow, int oh, int mode, uint8_t *out);
+/* add_premultiplied_alpha.wgsl:24-35: straight alpha -> premultiplied through the mode's texture views */
+void orc_add_premultiplied_alpha(const uint8_t *rgba, int w, int h, int mode, uint8_t *out);
 void orc_harness_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w,
                                 int h, uint8_t *rgba);
 

@@ -1644,6 +1644,15 @@ __global__ void __launch_bounds__(256) k_preprocess(Tex src, int mode, int resca
     uchar4 o;
     if (!rescale) {
         o = node_texel(T, src, x, y);
+    } else if (rescale == 2) {
+        // add_premultiplied_alpha.wgsl:24-35: straight-alpha texel fetched through the source view (the full-screen quad
+        // samples at texel centres: weight exactly 1), colour times max(alpha, 1e-5), clamped, stored through the target view
+        const uchar4 t = node_texel(T, src, x, y);
+        const float *lut = mode == 0 ? T.dec : T.u8n;
+        const float a = T.u8n[t.w], am = fmaxf(a, 0.00001f);
+        const float r = clamp01(lut[t.x] * am), g = clamp01(lut[t.y] * am), b = clamp01(lut[t.z] * am);
+        if (mode == 0) o = make_uchar4(srgb_encode(T, r), srgb_encode(T, g), srgb_encode(T, b), unorm8(clamp01(a)));
+        else o = make_uchar4(unorm8(r), unorm8(g), unorm8(b), unorm8(clamp01(a)));
     } else {
         bool exact;
         uchar4 texel;

@@ -249,7 +249,8 @@ class Renderer {
     smr_status render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out, uint32_t n_out);
     smr_status render_end();
     smr_status render_end_all();
-    smr_status preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch, int32_t mem_kind);
+    smr_status preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch, int32_t mem_kind,
+                                bool premultiply = false);
     smr_status debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
     smr_status debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap, uint32_t *n,
                              uint32_t *rw, uint32_t *rh);
@@ -914,8 +915,12 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
 
 // FramePreProcessor::process_to_bytes / process_to_texture (state/frame_pre_processor.rs:60-100)
 smr_status Renderer::preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch,
-                                      int32_t mem_kind) {
+                                      int32_t mem_kind, bool premultiply) {
     if (!f || !rgba) return SMR_ERR_INVALID_ARGUMENT;
+    if (premultiply && (f->format != SMR_FRAME_RGBA8 || ow != 0 || oh != 0)) {
+        set_error("premultiply takes a straight-alpha RGBA8 frame at its own resolution");
+        return SMR_ERR_INVALID_ARGUMENT;
+    }
     std::lock_guard<std::mutex> g(mu_);
     if (host_only_) { set_error("host-only handle (cuda_device = -1) has no device: no CPU fallback"); return SMR_ERR_CUDA; }
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
@@ -960,7 +965,7 @@ smr_status Renderer::preprocess_frame(const smr_input_frame *f, uint32_t ow, uin
         CUDA_OK(pre_out_.ensure(row * oh));
         dst = pre_out_.p; dpitch = row;
     }
-    if (dev::launch_preprocess(t, opts_.rendering_mode, rescale ? 1 : 0, dst, (int)dpitch, (int)ow, (int)oh, stream_) < 0) {
+    if (dev::launch_preprocess(t, opts_.rendering_mode, premultiply ? 2 : (rescale ? 1 : 0), dst, (int)dpitch, (int)ow, (int)oh, stream_) < 0) {
         set_error(dev::last_launch_error());
         return SMR_ERR_CUDA;
     }
@@ -1786,6 +1791,9 @@ smr_status smr_debug_partition(const int32_t *dst_w, const int32_t *dst_h, uint3
 }
 smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch,
                                 int32_t mem_kind) { SMR_GUARD(r->impl.preprocess_frame(f, ow, oh, rgba, pitch, mem_kind)) }
+smr_status smr_premultiply_rgba8(smr_renderer *r, const smr_input_frame *f, void *rgba, uint32_t pitch, int32_t mem_kind) {
+    SMR_GUARD(r->impl.preprocess_frame(f, 0, 0, rgba, pitch, mem_kind, true))
+}
 smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,
                       uint32_t n_out) {
     if (!r) return SMR_ERR_INVALID_ARGUMENT;

@@ -542,6 +542,17 @@ class Renderer:
         self._check(self._lib.smr_preprocess_frame(self._h, arr, ow, oh, out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
         return out
 
+    def premultiply_rgba8(self, rgba: np.ndarray) -> np.ndarray:
+        """PremultiplyAlphaPipeline (wgpu/utils/add_premultiplied_alpha.wgsl): straight-alpha (h, w, 4) uint8 ->
+        premultiplied RGBA8 through the renderer's views; the result is a valid FrameData.Rgba8 input."""
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        h, w = rgba.shape[:2]
+        keep = []
+        arr = self._input_frames(FrameSet(frames={"_": Frame(FrameData.Rgba8(rgba), Resolution(w, h), 0.0)}), keep)
+        out = np.empty((h, w, 4), np.uint8)
+        self._check(self._lib.smr_premultiply_rgba8(self._h, arr, out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
+        return out
+
     # -- zero-copy path (device pointers in and out; used by bench.py's `value` leg) ---------------
     def render_raw(self, pts_ns, in_arr, n_in, out_arr, n_out, wait=True):
         st = self._lib.smr_render_begin(self._h, pts_ns, in_arr, n_in, out_arr, n_out)

@@ -610,3 +610,20 @@ def test_translucent_premultiplied_rgba_layers(mode):
                                border_radius=s.BorderRadius.new_with_radius(18.0))
     scene = V(background_color=BG, children=[s.RescalerComponent(child=streams(1)[0]), label, logo])
     check(scene, fr, mode=mode)
+
+
+@pytest.mark.parametrize("mode", [s.RenderingMode.GpuOptimized, s.RenderingMode.CpuOptimized])
+def test_add_premultiplied_alpha_pass(mode):
+    """wgpu/utils/add_premultiplied_alpha.wgsl:24-35 (PremultiplyAlphaPipeline): straight-alpha RGBA8 asset ->
+    premultiplied RGBA8 through the renderer's views, byte-exact against the oracle twin; every alpha value occurs"""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    h, w = 64, 256
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    rgba[:, :, 3] = np.arange(w, dtype=np.uint8)[None, :]          # alpha 0..255 across the row
+    rgba[0, :, :3] = 255
+    r = s.Renderer(s.RendererOptions(rendering_mode=mode))
+    got = r.premultiply_rgba8(rgba)
+    exp = orc.add_premultiplied_alpha(rgba, orc.MODE_GPU_OPTIMIZED if mode == s.RenderingMode.GpuOptimized else orc.MODE_CPU_OPTIMIZED)
+    assert np.array_equal(got, exp), f"{np.count_nonzero(got != exp)} bytes differ"
+    assert np.all(got[..., :3].astype(int) <= got[..., 3:4].astype(int) + (1 if mode == s.RenderingMode.GpuOptimized else 0) * 255)
