@@ -865,6 +865,22 @@ static bool launch_fused_src(int src, const FusedJob *jobs_dev, const FusedPiece
 namespace smr {
 namespace dev {
 #include "resample_tma.cuh"
+#include "resample_tma3.cuh"
+
+template <int S, int SRC>
+static bool launch_tma3(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks, cudaStream_t s) {
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(v6::k_resample_tma3<S, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::Cfg<S>::SMEM);
+        done.fetch_or(bit, std::memory_order_release);
+    }
+    const int grid = (nblocks + v6::kGroups - 1) / v6::kGroups;   // the host cut the work for `nblocks` eight-warp groups
+    v6::k_resample_tma3<S, SRC><<<grid, dim3(32, v6::kWarps * v6::kGroups), v6::Cfg<S>::SMEM, s>>>(jobs_dev, pieces, piece_begin, nblocks);
+    return check_launch("k_resample_tma3");
+}
 
 template <int S, int SRC>
 static bool launch_tma(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks, cudaStream_t s) {
@@ -887,10 +903,16 @@ int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const 
     cudaStream_t st = (cudaStream_t)s;
     bool ok = false;
     static_assert(v5::Cfg<4>::NOUT == kTmaStripCols4 && v5::Cfg<2>::NOUT == kTmaStripCols2, "strip widths");
+    static_assert(v6::Cfg<4>::NOUT == kTmaStripCols4 && v6::Cfg<2>::NOUT == kTmaStripCols2 && v6::Cfg<4>::RROWS == kTmaRing4 &&
+                  v6::Cfg<2>::RROWS == kTmaRing2 && v6::kChunkRows == kTma3LumaBoxH && v6::kChromaRows == kTma3ChromaBoxH, "grouped kernel");
     static_assert(v5::Cfg<4>::RROWS == kTmaRing4 && v5::Cfg<2>::RROWS == kTmaRing2, "ring rows");
     static_assert(v5::kLumaBox == 2 * kTmaLumaBoxW && v5::kChunkRows == kTmaLumaBoxH && v5::kNv12Box == 2 * kTmaNv12BoxW &&
                   v5::kPlanarBox == kTmaPlanarBoxW && v5::kChromaRows == kTmaChromaBoxH, "TMA boxes");
     switch (variant) {
+        case 22: ok = src == 1 ? launch_tma3<2, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                               : launch_tma3<2, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 24: ok = src == 1 ? launch_tma3<4, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
+                               : launch_tma3<4, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         case 12: ok = src == 1 ? launch_tma<2, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)
                                : launch_tma<2, 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         case 14: ok = src == 1 ? launch_tma<4, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)

@@ -341,6 +341,7 @@ class Renderer {
     std::vector<CUtensorMap> tick_tmaps_;      // three per TMA job
     std::vector<int> fused_tmap_idx_;          // per fused job: first of its three entries in tick_tmaps_, or -1
     bool disable_tma_ = false;                 // SMR_DISABLE_TMA=1: A/B switch back to the LDG-staged kernels
+    bool tma_grouped_ = true;                  // SMR_TMA_GROUPED=0: the three-blocks-per-SM form of the TMA kernel
     std::vector<dev::FusedJob> fused_jobs_;
     std::vector<std::pair<int, size_t>> fused_src_dst_;   // (raw tex index, frame offset of dst)
     std::vector<dev::WeightJob> weight_jobs_;
@@ -434,6 +435,7 @@ smr_status Renderer::init() {
     if (opts_.max_layouts_count > 1024) opts_.max_layouts_count = 1024;
     if (opts_.cuda_device == -1) { host_only_ = true; return SMR_OK; }  // scene/layout inspection only
     if (const char *e = getenv("SMR_DISABLE_TMA")) disable_tma_ = e[0] == '1';
+    if (const char *e = getenv("SMR_TMA_GROUPED")) tma_grouped_ = e[0] != '0';
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
@@ -695,15 +697,16 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
             (int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 1 <= ring) {
             CUtensorMap m[3];
             memset(m, 0, sizeof(m));
-            bool ok = plane_tmap(t.p0, t.pitch0, t.width, t.height, 0, &m[0]);
-            if (src_class == 1) ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 1, &m[1]);
-            else ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 2, &m[1]) &&
-                      plane_tmap(t.p2, t.pitch2, t.width / 2, t.height / 2, 2, &m[2]);
+            const int gk = tma_grouped_ ? 4 : 0;
+            bool ok = plane_tmap(t.p0, t.pitch0, t.width, t.height, 0 | gk, &m[0]);
+            if (src_class == 1) ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 1 | gk, &m[1]);
+            else ok = ok && plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 2 | gk, &m[1]) &&
+                      plane_tmap(t.p2, t.pitch2, t.width / 2, t.height / 2, 2 | gk, &m[2]);
             if (ok) {
                 tmap_idx = (int)tick_tmaps_.size();
                 tick_tmaps_.insert(tick_tmaps_.end(), m, m + 3);
                 j.v_same = vm.crop_offset == 0.0f && sv == sh && tv == th;
-                j.variant += 10;
+                j.variant += tma_grouped_ ? 20 : 10;
             }
         }
     }
@@ -723,9 +726,11 @@ bool Renderer::plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, C
     TmapKey key{(uintptr_t)p, pitch, w, h, kind};
     auto it = tmap_cache_.find(key);
     if (it != tmap_cache_.end()) { *out = it->second; return true; }
-    bool ok = kind == 0   ? encode_plane_tmap(p, pitch, w / 2, h, 2, dev::kTmaLumaBoxW, dev::kTmaLumaBoxH, out)
-              : kind == 1 ? encode_plane_tmap(p, pitch, w, h, 2, dev::kTmaNv12BoxW, dev::kTmaChromaBoxH, out)
-                          : encode_plane_tmap(p, pitch, w, h, 1, dev::kTmaPlanarBoxW, dev::kTmaChromaBoxH, out);
+    // kind: 0 luma, 1 NV12 chroma, 2 planar chroma; + 4 for the 16-row chunks of the grouped kernel
+    const int lh = (kind & 4) ? dev::kTma3LumaBoxH : dev::kTmaLumaBoxH, chh = (kind & 4) ? dev::kTma3ChromaBoxH : dev::kTmaChromaBoxH;
+    bool ok = (kind & 3) == 0   ? encode_plane_tmap(p, pitch, w / 2, h, 2, dev::kTmaLumaBoxW, lh, out)
+              : (kind & 3) == 1 ? encode_plane_tmap(p, pitch, w, h, 2, dev::kTmaNv12BoxW, chh, out)
+                                : encode_plane_tmap(p, pitch, w, h, 1, dev::kTmaPlanarBoxW, chh, out);
     if (!ok) return false;
     if (tmap_cache_.size() > 2048) tmap_cache_.clear();
     tmap_cache_[key] = *out;
