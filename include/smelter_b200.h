@@ -274,6 +274,17 @@ smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pt
                              smr_render_layout *out, uint32_t capacity, uint32_t *n_out,
                              uint32_t *root_width, uint32_t *root_height);
 
+/* The FLATTENED form of the boundary: a host that keeps the reference's scene/** (Component tree,
+ * transitions, NestedLayout::flatten -- all Rust) hands over, per output and whenever they change, the RenderLayout[]
+ * that transformations/layout/params.rs:169-333 would pack into uniform blocks: same fields, same units (pixels of
+ * the root_width x root_height layout node texture), painter's order.  child_ids[k] is the input id of the node's
+ * k-th child (scene/layout.rs:84-93), which `child_index` of a texture layout refers to.  Registers the output like
+ * smr_update_scene does; stays in force until the next smr_set_layouts / smr_update_scene of that output.  The
+ * resampler planning (layout.rs:238-278) and everything below it still happen here, per tick. */
+smr_status smr_set_layouts(smr_renderer *r, const char *output_id, uint32_t width, uint32_t height, int32_t format,
+                           uint32_t root_width, uint32_t root_height, const char *const *child_ids, uint32_t n_children,
+                           const smr_render_layout *layouts, uint32_t n_layouts);
+
 /* inspection: record the pts / input resolutions of a FrameSet exactly as smr_render would
  * (scene.register_render_event + populate_inputs bookkeeping) without touching any plane.  Together
  * with smr_options.cuda_device = -1 (host-only handle: scene + layout engine, smr_render refuses) this

@@ -116,7 +116,7 @@ class KernelTimes(C.Structure):
 
 EXPORTS = [
     "smr_create", "smr_destroy", "smr_register_input", "smr_unregister_input", "smr_update_scene",
-    "smr_unregister_output", "smr_render", "smr_render_begin", "smr_render_end", "smr_preprocess_frame", "smr_premultiply_rgba8", "smr_debug_partition", "smr_output_plane_sizes",
+    "smr_unregister_output", "smr_set_layouts", "smr_render", "smr_render_begin", "smr_render_end", "smr_preprocess_frame", "smr_premultiply_rgba8", "smr_debug_partition", "smr_output_plane_sizes",
     "smr_component_default", "smr_debug_layouts", "smr_debug_set_inputs", "smr_get_stats", "smr_set_profiling", "smr_get_kernel_times",
     "smr_comm_get_unique_id", "smr_comm_init", "smr_comm_broadcast_inputs", "smr_comm_exchange_inputs", "smr_comm_destroy", "smr_host_register", "smr_host_unregister", "smr_cuda_stream", "smr_last_error",
     "smr_version",
@@ -163,6 +163,8 @@ def lib():
     L.smr_comm_get_unique_id.argtypes = [C.POINTER(C.c_uint8 * 128)]
     L.smr_comm_init.argtypes = [vp, C.POINTER(C.c_uint8 * 128), C.c_int32, C.c_int32]
     L.smr_comm_broadcast_inputs.argtypes = [vp, C.POINTER(InputFrame), C.c_uint32, C.POINTER(C.c_int32)]
+    L.smr_set_layouts.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32,
+                                  C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(RenderLayout), C.c_uint32]
     L.smr_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.smr_host_unregister.argtypes = [C.c_void_p]
     L.smr_comm_exchange_inputs.argtypes = [vp, C.POINTER(InputFrame), C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),

@@ -246,6 +246,8 @@ class Renderer {
     smr_status unregister_input(const char *id);
     smr_status update_scene(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, const smr_component *root);
     smr_status unregister_output(const char *id);
+    smr_status set_layouts(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, uint32_t root_w, uint32_t root_h,
+                           const char *const *child_ids, uint32_t n_children, const smr_render_layout *layouts, uint32_t n);
     smr_status render_begin(uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out, uint32_t n_out);
     smr_status render_end();
     smr_status render_end_all();
@@ -274,6 +276,12 @@ class Renderer {
         int32_t format = 0;
         Resolution res;
         DevBuf planes[3];       // device staging for host outputs
+        // smr_set_layouts: the caller flattened the scene itself (the reference's scene/** stays in Rust); used instead
+        // of `node` until the next smr_update_scene of this output
+        bool flat = false;
+        Resolution flat_root;
+        std::vector<std::string> flat_children;
+        std::vector<RenderLayout> flat_layouts;
     };
     struct WeightKey {
         uint32_t scale_bits, offset_bits;
@@ -520,6 +528,48 @@ smr_status Renderer::update_scene(const char *output_id, uint32_t w, uint32_t h,
     o.node = std::move(node);
     o.format = fmt;
     o.res = {w, h};
+    o.flat = false; o.flat_layouts.clear(); o.flat_children.clear();
+    return SMR_OK;
+}
+
+// The flattened boundary (second form): RenderLayout[] exactly as NestedLayout::flatten returns them and
+// LayoutNodeParams consumes them (transformations/layout/params.rs:169-333), child node indices resolved through
+// `child_ids` (the node's children in DFS order, scene/layout.rs:84-93).
+smr_status Renderer::set_layouts(const char *output_id, uint32_t w, uint32_t h, int32_t fmt, uint32_t root_w, uint32_t root_h,
+                                 const char *const *child_ids, uint32_t n_children, const smr_render_layout *layouts, uint32_t n) {
+    if (!output_id || (n && !layouts) || (n_children && !child_ids)) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (fmt < SMR_OUT_PLANAR_YUV420 || fmt > SMR_OUT_NV12) { set_error("unsupported output format"); return SMR_ERR_UNSUPPORTED; }
+    if (w == 0 || h == 0 || w > 16384 || h > 16384) { set_error("output resolution out of range"); return SMR_ERR_INVALID_ARGUMENT; }
+    std::vector<RenderLayout> ls(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const smr_render_layout &d = layouts[i];
+        RenderLayout &l = ls[i];
+        if (d.type < 0 || d.type > 2 || d.masks_len < 0 || d.masks_len > SMR_MAX_MASKS) { set_error("malformed layout"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (d.type == 0 && (d.child_index < 0 || (uint32_t)d.child_index >= n_children)) { set_error("child index outside child_ids"); return SMR_ERR_INVALID_ARGUMENT; }
+        l.kind = (RenderLayout::Kind)d.type;
+        l.top = d.top; l.left = d.left; l.width = d.width; l.height = d.height; l.rotation_degrees = d.rotation_degrees;
+        l.border_radius = {d.border_radius[0], d.border_radius[1], d.border_radius[2], d.border_radius[3]};
+        l.color = {d.color.r, d.color.g, d.color.b, d.color.a};
+        l.border_color = {d.border_color.r, d.border_color.g, d.border_color.b, d.border_color.a};
+        l.border_width = d.border_width; l.blur_radius = d.blur_radius;
+        l.index = (size_t)std::max(d.child_index, 0);
+        l.crop = {d.crop_top, d.crop_left, d.crop_width, d.crop_height};
+        for (int m = 0; m < d.masks_len; m++) {
+            Mask mk;
+            mk.radius = {d.masks[m].radius[0], d.masks[m].radius[1], d.masks[m].radius[2], d.masks[m].radius[3]};
+            mk.top = d.masks[m].top; mk.left = d.masks[m].left; mk.width = d.masks[m].width; mk.height = d.masks[m].height;
+            l.masks.push_back(mk);
+        }
+    }
+    Output &o = outputs_[output_id];
+    o.format = fmt;
+    o.res = {w, h};
+    o.flat = true;
+    o.flat_root = {root_w, root_h};
+    o.flat_children.clear();
+    for (uint32_t i = 0; i < n_children; i++) o.flat_children.push_back(child_ids[i] ? child_ids[i] : "");
+    o.flat_layouts = std::move(ls);
     return SMR_OK;
 }
 
@@ -1089,7 +1139,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
         output_src_tex_.push_back(src_tex);
     };
 
-    if (o.node.root_is_input) {  // pass-through: the root texture IS the input's node texture
+    if (!o.flat && o.node.root_is_input) {  // pass-through: the root texture IS the input's node texture
         auto it = inputs_.find(o.node.root_input_id);
         if (it == inputs_.end() || !it->second.has_frame) { push_fill(); return SMR_OK; }
         Input &in = it->second;
@@ -1132,14 +1182,14 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
     // child node resolutions (sources[i].resolution(), layout.rs:176-179)
     std::vector<std::optional<Resolution>> child_res;
     std::vector<Input *> child_in;
-    for (const std::string &id : o.node.child_input_ids) {
+    for (const std::string &id : (o.flat ? o.flat_children : o.node.child_input_ids)) {
         auto it = inputs_.find(id);
         if (it != inputs_.end() && it->second.has_frame) { child_res.push_back(it->second.res); child_in.push_back(&it->second); }
         else { child_res.push_back(std::nullopt); child_in.push_back(nullptr); }
     }
-    Resolution root = o.node.layout_resolution(pts);
+    Resolution root = o.flat ? o.flat_root : o.node.layout_resolution(pts);
     if (root.width == 0 || root.height == 0 || root.width > 16384 || root.height > 16384) { push_fill(); return SMR_OK; }
-    std::vector<RenderLayout> layouts = o.node.layouts(pts, child_res).flatten(child_res, root);
+    std::vector<RenderLayout> layouts = o.flat ? o.flat_layouts : o.node.layouts(pts, child_res).flatten(child_res, root);
     if (layouts.size() > opts_.max_layouts_count) layouts.resize(opts_.max_layouts_count);  // params.rs:176-182
 
     const int W = (int)root.width, H = (int)root.height;
@@ -1690,7 +1740,7 @@ smr_status Renderer::debug_layouts(const char *output_id, uint64_t pts, smr_rend
     if (it == outputs_.end()) { set_error("output not registered"); return SMR_ERR_OUTPUT_NOT_REGISTERED; }
     Output &o = it->second;
     *n = 0;
-    if (o.node.root_is_input) { if (rw) *rw = 0; if (rh) *rh = 0; return SMR_OK; }
+    if (!o.flat && o.node.root_is_input) { if (rw) *rw = 0; if (rh) *rh = 0; return SMR_OK; }
     OutputNode copy = o.node;  // do not advance Tiles::last_layout
     std::vector<std::optional<Resolution>> child_res;
     for (const std::string &id : copy.child_input_ids) {
@@ -1698,10 +1748,10 @@ smr_status Renderer::debug_layouts(const char *output_id, uint64_t pts, smr_rend
         if (ii != inputs_.end() && ii->second.has_frame) child_res.push_back(ii->second.res);
         else child_res.push_back(std::nullopt);
     }
-    Resolution root = copy.layout_resolution(pts);
+    Resolution root = o.flat ? o.flat_root : copy.layout_resolution(pts);
     if (rw) *rw = (uint32_t)root.width;
     if (rh) *rh = (uint32_t)root.height;
-    std::vector<RenderLayout> layouts = copy.layouts(pts, child_res).flatten(child_res, root);
+    std::vector<RenderLayout> layouts = o.flat ? o.flat_layouts : copy.layouts(pts, child_res).flatten(child_res, root);
     *n = (uint32_t)layouts.size();
     if (!out) return SMR_OK;
     if (cap < layouts.size()) return SMR_ERR_BUFFER_TOO_SMALL;
@@ -1773,6 +1823,9 @@ smr_status smr_unregister_input(smr_renderer *r, const char *id) { SMR_GUARD(r->
 smr_status smr_update_scene(smr_renderer *r, const char *output_id, uint32_t w, uint32_t h, int32_t fmt,
                             const smr_component *root) { SMR_GUARD(r->impl.update_scene(output_id, w, h, fmt, root)) }
 smr_status smr_unregister_output(smr_renderer *r, const char *id) { SMR_GUARD(r->impl.unregister_output(id)) }
+smr_status smr_set_layouts(smr_renderer *r, const char *output_id, uint32_t w, uint32_t h, int32_t fmt, uint32_t root_w,
+                           uint32_t root_h, const char *const *child_ids, uint32_t n_children, const smr_render_layout *layouts,
+                           uint32_t n) { SMR_GUARD(r->impl.set_layouts(output_id, w, h, fmt, root_w, root_h, child_ids, n_children, layouts, n)) }
 smr_status smr_render_begin(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in,
                             smr_output_frame *out, uint32_t n_out) { SMR_GUARD(r->impl.render_begin(pts, in, n_in, out, n_out)) }
 smr_status smr_render_end(smr_renderer *r) { SMR_GUARD(r->impl.render_end()) }

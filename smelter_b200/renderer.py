@@ -542,6 +542,16 @@ class Renderer:
         self._check(self._lib.smr_preprocess_frame(self._h, arr, ow, oh, out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
         return out
 
+    def set_layouts(self, output_id: str, resolution: Resolution, output_format: int, root: Tuple[int, int],
+                    child_input_ids: List[str], layouts):
+        """the flattened boundary (smr_set_layouts): `layouts` are _ffi.RenderLayout structs (e.g. from debug_layouts
+        of another handle, or built by a host that runs the reference's scene/** itself)"""
+        ids = (C.c_char_p * max(1, len(child_input_ids)))(*[i.encode() for i in child_input_ids])
+        arr = (F.RenderLayout * max(1, len(layouts)))(*layouts)
+        self._check(self._lib.smr_set_layouts(self._h, output_id.encode(), resolution.width, resolution.height, output_format,
+                                              root[0], root[1], ids, len(child_input_ids), arr, len(layouts)), UpdateSceneError)
+        self._outputs[output_id] = (resolution, output_format)
+
     def premultiply_rgba8(self, rgba: np.ndarray) -> np.ndarray:
         """PremultiplyAlphaPipeline (wgpu/utils/add_premultiplied_alpha.wgsl): straight-alpha (h, w, 4) uint8 ->
         premultiplied RGBA8 through the renderer's views; the result is a valid FrameData.Rgba8 input."""

@@ -627,3 +627,21 @@ def test_add_premultiplied_alpha_pass(mode):
     exp = orc.add_premultiplied_alpha(rgba, orc.MODE_GPU_OPTIMIZED if mode == s.RenderingMode.GpuOptimized else orc.MODE_CPU_OPTIMIZED)
     assert np.array_equal(got, exp), f"{np.count_nonzero(got != exp)} bytes differ"
     assert np.all(got[..., :3].astype(int) <= got[..., 3:4].astype(int) + (1 if mode == s.RenderingMode.GpuOptimized else 0) * 255)
+
+
+def test_set_layouts_renders_like_the_scene():
+    """the flattened boundary (smr_set_layouts): feeding the RenderLayout[] of a scene renders the same bytes as the scene"""
+    fr = inputs(3)
+    kids = [s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(12.0)) for c in streams(3)]
+    scene = V(background_color=BG, children=[s.TilesComponent(children=kids, background_color=BG, margin=6.0),
+                                             V(position=s.Position.Absolute(width=100.0, height=40.0, left=7.0, bottom=9.0),
+                                               background_color=s.RGBAColor(10, 20, 30, 99))])
+    got, exp, r = run_case(scene, fr)
+    assert_identical(got, exp, "scene path")
+    ls, root = r.debug_layouts(OUTPUT_ID)
+    b = s.Renderer()
+    for i in fr:
+        b.register_input(i)
+    b.set_layouts(OUTPUT_ID, RES, YUV, root, [f"input_{i}" for i in range(1, 4)], ls)
+    out = b.render(s.FrameSet(frames=fr, pts=0.0))
+    assert_identical([np.asarray(p) for p in out.frames[OUTPUT_ID].data.planes], exp, "flattened path")

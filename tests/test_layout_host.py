@@ -416,3 +416,30 @@ def test_frame_pre_processor_without_gpu_fails_loudly():
     with pytest.raises(s.RendererError) as e:
         s.FramePreProcessor(r).process_to_bytes(fr)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_set_layouts_flattened_boundary_round_trip():
+    """smr_set_layouts (flattened form): the layouts one handle flattened from a scene, handed to another
+    handle as RenderLayout[], come back field for field from debug_layouts -- what smr_render then consumes"""
+    V = s.ViewComponent
+    kids = [s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(12.0),
+                                box_shadow=[s.BoxShadow(3.0, 4.0, 10.0, s.RGBAColor(0, 0, 0, 128))]) for c in inputs(3)]
+    scene = V(background_color=BG, children=[s.TilesComponent(children=kids, background_color=BG, margin=6.0),
+                                             V(position=s.Position.Absolute(width=100.0, height=40.0, left=7.0, bottom=9.0),
+                                               background_color=s.RGBAColor(10, 20, 30, 99), border_width=2.0,
+                                               border_color=s.RGBAColor(255, 255, 255, 255))])
+    a = setup(scene, 3)
+    ls, root = a.debug_layouts("output_1")
+    b = host_renderer()
+    for i in range(1, 4):
+        b.register_input(f"input_{i}")
+    b.set_layouts("output_1", RES, s.OutputFrameFormat.PlanarYuv420Bytes, root, [f"input_{i}" for i in range(1, 4)], ls)
+    b.debug_set_inputs(0.0, {f"input_{i}": RES for i in range(1, 4)})
+    ls2, root2 = b.debug_layouts("output_1")
+    assert root2 == root and len(ls2) == len(ls)
+    for x, y in zip(ls, ls2):
+        assert bytes(x) == bytes(y)
+    # a later update_scene of the same output replaces the flattened layouts
+    b.update_scene("output_1", RES, s.OutputFrameFormat.PlanarYuv420Bytes, V(background_color=BG))
+    ls3, _ = b.debug_layouts("output_1")
+    assert len(ls3) == 1 and ls3[0].type == 1
