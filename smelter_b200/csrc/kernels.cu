@@ -1201,11 +1201,13 @@ struct CompositeParams {
 };
 
 template <bool PARAM>
-__device__ __forceinline__ void composite_body(const Tables &T, const CompositeJob &J, const LayerDev *__restrict__ LAYERS,
-                                               const int tile_x0, const int tile_y0) {
+__device__ __forceinline__ void composite_body(const CompositeJob &J, const LayerDev *__restrict__ LAYERS) {
+    __shared__ Tables T;
     __shared__ unsigned short s_list[MAX_TILE_LAYERS];
     __shared__ int s_count;
     __shared__ LayerDev s_layers[PARAM ? 1 : SM_LAYERS];
+    load_tables(T);
+    const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H * CT_ITERS);
     const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H * CT_ITERS, J.height);
     // per-tile layer culling, painter's order preserved.  One layer per thread (a serial loop over the layer
     // list costs one dependent global-load latency per layer while the whole block waits), ordered compaction
@@ -1561,71 +1563,26 @@ __device__ __forceinline__ void composite_body(const Tables &T, const CompositeJ
     }  // it
 }
 
-// Persistent blocks with a dynamic tile queue: the grid is the number of resident blocks (SMs x 3), every block keeps
-// drawing the next 128 x 16 tile from an atomic counter (zeroed with the tick's parameter upload).  Tiles differ a lot
-// in cost (a tile of plain video is a copy, one with rounded corners or a translucent overlay runs the fragment
-// maths), and a static grid left 28 - 40 % of the SM cycles idle in its last wave (profiles/r02_*).
-template <bool PARAM>
-__device__ __forceinline__ void composite_queue(const CompositeJob &J, const LayerDev *__restrict__ LAYERS, int *counter) {
-    __shared__ Tables T;
-    __shared__ int s_tile;
-    load_tables(T);
-    const int gx = (J.width + CB_X * CT_W - 1) / (CB_X * CT_W), gy = (J.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS);
-    for (;;) {
-        if (threadIdx.x == 0 && threadIdx.y == 0) s_tile = atomicAdd(counter, 1);
-        __syncthreads();
-        const int t = s_tile;
-        if (t >= gx * gy) break;
-        composite_body<PARAM>(T, J, LAYERS, (t % gx) * (CB_X * CT_W), (t / gx) * (CB_Y * CT_H * CT_ITERS));
-        __syncthreads();
-    }
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_p(const __grid_constant__ CompositeParams P) {
+    composite_body<true>(P.job, P.layers);
 }
 
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite(CompositeJob J, int *counter) { composite_queue<false>(J, J.layers, counter); }
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_p(const __grid_constant__ CompositeParams P, int *counter) {
-    composite_queue<true>(P.job, P.layers, counter);
-}
-
-// all outputs of a tick in one launch: the queue runs over (output, tile); the tails of the single launches disappear
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_multi(const CompositeJob *__restrict__ jobs, int n_jobs, int gx, int gy,
-                                                                    int *counter) {
-    __shared__ Tables T;
+// all outputs of a tick in one launch (blockIdx.z = output): a 1080p frame alone is 2.3 waves of 444 resident
+// blocks, eight of them back to back are 18.4 -- the per-launch tails disappear
+__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_multi(const CompositeJob *__restrict__ jobs) {
     __shared__ CompositeJob J;
-    __shared__ int s_tile;
-    load_tables(T);
-    const int tid = threadIdx.y * CB_X + threadIdx.x;
-    int cur_job = -1;
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(counter, 1);
-        __syncthreads();
-        const int t = s_tile;
-        if (t >= gx * gy * n_jobs) break;
-        const int job = t / (gx * gy), r = t - job * (gx * gy);
-        if (job != cur_job) {   // block-uniform
-            const unsigned int *src = reinterpret_cast<const unsigned int *>(jobs + job);
-            if (tid < (int)(sizeof(CompositeJob) / 4)) reinterpret_cast<unsigned int *>(&J)[tid] = __ldg(src + tid);
-            cur_job = job;
-            __syncthreads();
-        }
-        const int tx0 = (r % gx) * (CB_X * CT_W), ty0 = (r / gx) * (CB_Y * CT_H * CT_ITERS);
-        if (tx0 < J.width && ty0 < J.height) composite_body<false>(T, J, J.layers, tx0, ty0);
-        __syncthreads();
+    {
+        const int tid = threadIdx.y * CB_X + threadIdx.x;
+        const unsigned int *src = reinterpret_cast<const unsigned int *>(jobs + blockIdx.z);
+        if (tid < (int)(sizeof(CompositeJob) / 4)) reinterpret_cast<unsigned int *>(&J)[tid] = __ldg(src + tid);
     }
+    __syncthreads();
+    if ((int)blockIdx.x * (CB_X * CT_W) >= J.width || (int)blockIdx.y * (CB_Y * CT_H * CT_ITERS) >= J.height) return;
+    composite_body<false>(J, J.layers);
 }
 
-static int composite_resident_blocks() {
-    static int n[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!n[dev & 63]) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n[dev & 63] = sms * 3;
-    }
-    return n[dev & 63];
-}
-
-int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *jobs_host, int n, int *counter_dev, Stream s) {
+int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *jobs_host, int n, Stream s) {
     static_assert(sizeof(CompositeJob) % 4 == 0 && sizeof(CompositeJob) / 4 <= CB_X * CB_Y, "job copied by one block pass");
     int gx = 0, gy = 0;
     for (int i = 0; i < n; i++) {
@@ -1633,23 +1590,20 @@ int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *job
         gy = max(gy, (jobs_host[i].height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
     }
     if (n <= 0 || gx == 0 || gy == 0) return 0;
-    const int grid = min(gx * gy * n, composite_resident_blocks());
-    k_composite_multi<<<grid, dim3(CB_X, CB_Y), 0, (cudaStream_t)s>>>(jobs_dev, n, gx, gy, counter_dev);
+    k_composite_multi<<<dim3(gx, gy, n), dim3(CB_X, CB_Y), 0, (cudaStream_t)s>>>(jobs_dev);
     return check_launch("k_composite_multi") ? 1 : -1;
 }
 
-int launch_composite(const CompositeJob &job, int *counter_dev, Stream s) {
-    const int gx = (job.width + CB_X * CT_W - 1) / (CB_X * CT_W), gy = (job.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS);
-    if (gx <= 0 || gy <= 0) return 0;
-    dim3 b(CB_X, CB_Y), g(min(gx * gy, composite_resident_blocks()));
+int launch_composite(const CompositeJob &job, Stream s) {
+    dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
     if (job.n_layers <= PARAM_LAYERS && job.layers_host != nullptr) {
         CompositeParams P;   // ~26 KB on the host stack; the driver copies the parameter block at launch
         P.job = job;
         memcpy(P.layers, job.layers_host, sizeof(LayerDev) * (size_t)job.n_layers);
-        k_composite_p<<<g, b, 0, (cudaStream_t)s>>>(P, counter_dev);
+        k_composite_p<<<g, b, 0, (cudaStream_t)s>>>(P);
         return check_launch("k_composite_p") ? 1 : -1;
     }
-    k_composite<<<g, b, 0, (cudaStream_t)s>>>(job, counter_dev);
+    k_composite<<<g, b, 0, (cudaStream_t)s>>>(job);
     return check_launch("k_composite") ? 1 : -1;
 }
 

@@ -177,10 +177,9 @@ int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const 
                           const int *piece_begin_dev, int nblocks, Stream s);
 // integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping
 void set_int_weights(int S, const float *weights_dev, const float *inv_dev, int taps, Stream s);
-// counter_dev: one int32 in device memory, ZERO when the kernel starts (the tile queue of the persistent blocks)
-int launch_composite(const CompositeJob &job, int *counter_dev, Stream s);
+int launch_composite(const CompositeJob &job, Stream s);
 // every output of a tick in one launch; jobs_dev[i] == jobs_host[i], layers / masks / textures device pointers
-int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *jobs_host, int n, int *counter_dev, Stream s);
+int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *jobs_host, int n, Stream s);
 int launch_output(const OutputJob &job, Stream s);
 int launch_fill_yuv(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,
                     int out_format, uint8_t y, uint8_t u, uint8_t v, Stream s);

@@ -1469,7 +1469,6 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     // composite jobs: their device pointers are known once the arena is sized; with two or more outputs in the tick
     // the jobs travel in the arena and run as ONE launch
     const size_t cj_off = param_alloc(sizeof(dev::CompositeJob) * std::max<size_t>(composites_.size(), 1));
-    const size_t cnt_off = param_alloc(sizeof(int) * std::max<size_t>(composites_.size(), 1));   // tile queues, uploaded as zeros
     if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
     CUDA_OK(param_pinned_[slot_].ensure(param_used_));
     CUDA_OK(param_dev_[slot_].ensure(param_used_));
@@ -1494,7 +1493,6 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             memcpy(param_host_.data() + cj_off + i * sizeof(dev::CompositeJob), &pc.job, sizeof(dev::CompositeJob));
         }
     }
-    memset(param_host_.data() + cnt_off, 0, sizeof(int) * std::max<size_t>(composites_.size(), 1));
     memcpy(param_pinned_[slot_].p, param_host_.data(), param_used_);
     CUDA_OK(cudaMemcpyAsync(param_dev_[slot_].p, param_pinned_[slot_].p, param_used_, cudaMemcpyHostToDevice, stream_));
     uint8_t *pd = param_dev_[slot_].p;
@@ -1527,12 +1525,11 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     if (composites_.size() >= 2) {
         if (!launched(dev::launch_composite_multi((const dev::CompositeJob *)(pd + cj_off),
                                                   (const dev::CompositeJob *)(param_host_.data() + cj_off),
-                                                  (int)composites_.size(), (int *)(pd + cnt_off), stream_))) goto fail;
+                                                  (int)composites_.size(), stream_))) goto fail;
         prof_mark(SMR_KERNEL_COMPOSITE);
     } else {
-        for (size_t ci = 0; ci < composites_.size(); ci++) {
-            PendingComposite &pc = composites_[ci];
-            if (!launched(dev::launch_composite(pc.job, (int *)(pd + cnt_off) + ci, stream_))) goto fail;
+        for (PendingComposite &pc : composites_) {
+            if (!launched(dev::launch_composite(pc.job, stream_))) goto fail;
             prof_mark(SMR_KERNEL_COMPOSITE);
         }
     }
