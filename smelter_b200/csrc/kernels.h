@@ -139,7 +139,7 @@ constexpr int kFusedStripCols = 64, kFusedWarps = 8, kFusedRing = 64, kFusedSpan
 constexpr int kTmaStripCols4 = 58, kTmaStripCols2 = 122, kTmaRing4 = 54, kTmaRing2 = 28;
 // luma and NV12 chroma are addressed in 2-byte elements (a box may be at most 256 elements wide), planar chroma in bytes
 constexpr int kTmaLumaBoxW = 136, kTmaLumaBoxH = 32, kTmaNv12BoxW = 144, kTmaPlanarBoxW = 160, kTmaChromaBoxH = 18;
-constexpr int kTma3LumaBoxH = 16, kTma3ChromaBoxH = 10;   // the grouped kernel (resample_tma3.cuh, variants 22 / 24) loads 16-row chunks
+constexpr int kTma3LumaBoxH = 32, kTma3ChromaBoxH = 18;   // the grouped kernel (resample_tma3.cuh, variants 22 / 24)
 inline int fused_strip_cols(int variant) { return (variant % 10 == 4 && variant > 10) ? kTmaStripCols4 : (variant % 10 == 2 && variant > 10) ? kTmaStripCols2 : kFusedStripCols; }
 
 struct WeightJob {          // resample.wgsl:42-86 evaluated once per output coordinate

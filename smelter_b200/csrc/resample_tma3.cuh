@@ -7,7 +7,8 @@
 //     32 i + l, i.e. in bank l, and the 24 data-dependent lookups of a row never conflict (they were 3-way on average,
 //     44 % of the shared-memory wavefronts of k_resample_tma; profiles/r02_*).  The table has exactly 256 entries, so
 //     the clamp of NC-2 moves back in front of the rounding as the .SAT of the matrix row's last fma;
-//   * 16-row TMA chunks (two per 8-output-row step of a 4:1 pass) keep three groups' stages + rings inside 227 KB;
+//   * ONE 32-row TMA stage per group (a whole 8-output-row step of a 4:1 pass): it is refilled right after the
+//     horizontal pass has consumed it, i.e. while the vertical pass runs; three groups' stages + rings fit in 227 KB;
 //   * the vertical pass of a same-ratio job runs on four warps (one per scheduler) that produce TWO output rows each:
 //     consecutive output rows share TAPS - S of their ring rows, every row is loaded once for both.
 #pragma once
@@ -16,9 +17,9 @@ namespace v6 {
 
 constexpr int kWarps = 8;
 constexpr int kGroups = 3;                            // independent 8-warp groups per block (one block per SM)
-constexpr int kChunkRows = 16;                       // source rows per TMA chunk
+constexpr int kChunkRows = 32;                       // source rows per TMA chunk: one 8-output-row step of a 4:1 pass
 // box widths in BYTES: 256 pixels + up to 14 bytes of alignment slack (luma); 6 chroma texels per lane + slack
-constexpr int kLumaBox = 272, kNv12Box = 288, kPlanarBox = 160, kChromaRows = 10;
+constexpr int kLumaBox = 272, kNv12Box = 288, kPlanarBox = 160, kChromaRows = 18;
 constexpr int kLumaBytes = kLumaBox * kChunkRows;                                    
 constexpr int kChromaBytesNv12 = ((kNv12Box * kChromaRows + 127) / 128) * 128;      
 constexpr int kChromaBytesPlanar = ((kPlanarBox * kChromaRows + 127) / 128) * 128;  
@@ -50,7 +51,7 @@ struct Cfg {
     static constexpr int RROWS = S == 4 ? 54 : 28;   // ring rows >= taps_v + ceil(7 * scale_v) + 1
     static constexpr int RROW_BYTES = 32 * 3 * OUT * 4;
     static constexpr int RING_BYTES = RROWS * RROW_BYTES;
-    static constexpr int GROUP_BYTES = 2 * kStageBytes + RING_BYTES;
+    static constexpr int GROUP_BYTES = kStageBytes + RING_BYTES;   // ONE stage: it is refilled while the vertical pass runs
     static constexpr int SMEM = kGroups * GROUP_BYTES + 256 * kDecRep * 4 + 256 * 4 + 128;
 };
 
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
     float *s_thr = s_dec + 256 * kDecRep;
     unsigned char *smem = smem_all + (size_t)grp * K::GROUP_BYTES;          // this group's stages + ring
     const uint32_t stage0 = v5::smem_u32(smem);
-    float *ring = reinterpret_cast<float *>(smem + 2 * kStageBytes);
+    float *ring = reinterpret_cast<float *>(smem + kStageBytes);
     const uint32_t bar0 = v5::smem_u32(s_thr + 256) + 16u * (uint32_t)grp;
     volatile uint32_t *s_kaddr = reinterpret_cast<volatile uint32_t *>(reinterpret_cast<unsigned char *>(s_thr + 256) + 64);
     {
@@ -155,10 +156,10 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
     ChunkIter<S> it;
     it.init(jobs, pieces, __ldg(piece_begin + vb), __ldg(piece_begin + vb + 1));
 
-    auto issue = [&](const Chunk &c, int buf) {   // one thread: TMA loads of the chunk's boxes
+    auto issue = [&](const Chunk &c) {   // one thread: TMA loads of the chunk's boxes into the group's stage
         if (!c.valid || c.nrows == 0) return;
         const FusedJob &J = jobs[c.job];
-        const uint32_t bar = bar0 + 8u * (uint32_t)buf, dst = stage0 + (uint32_t)buf * kStageBytes;
+        const uint32_t bar = bar0, dst = stage0;
         const int cyb = (c.r0 >> 1) - 1;
         const int xt = c.x0 & ~15;                         // luma tile: first byte, 16-byte boundary (may be negative)
         if (NV12) {
@@ -177,31 +178,26 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
 
     Chunk cur = it.next();
     if (!cur.valid) return;
-    if (tid == 0) issue(cur, 0);
-    uint32_t nchunk = 0;        // chunks that carried a TMA load so far (stage / parity bookkeeping)
+    if (tid == 0) issue(cur);
+    uint32_t nchunk = 0;        // chunks that carried a TMA load so far (mbarrier parity)
 
     while (cur.valid) {
         Chunk nxt = it.next();
-        // every warp is done with the stage the next load overwrites (it was read two chunks ago) and with the
-        // previous group's vertical pass (the ring rows it read may be overwritten now)
-        group_sync(grp);
         const bool cur_tma = cur.nrows > 0;
-        const int buf = (int)(nchunk & 1u);
-        if (tid == 0) issue(nxt, cur_tma ? buf ^ 1 : buf);
         const FusedJob &J = jobs[cur.job];
         const int W = J.src.width, H = J.src.height, chei = H >> 1;
         const bool full_range = J.src.full_range != 0;
         const float nk16 = full_range ? 0.0f : -K16, rcp_y = full_range ? 1.0f : RCP_Y, rcp_c = full_range ? 1.0f : RCP_C;
-        const uint32_t sb = stage0 + (uint32_t)buf * kStageBytes;
+        const uint32_t sb = stage0;
         if (cur_tma) {
-            v5::mbar_wait(bar0 + 8u * (uint32_t)buf, (nchunk >> 1) & 1u);
+            v5::mbar_wait(bar0, nchunk & 1u);
             // ---- image borders: the tap index is clamped (resample.wgsl), the TMA unit zero-fills ----------------
             const int x0 = cur.x0;
             const int cyb = (cur.r0 >> 1) - 1;
             const int xt = x0 & ~15, xc = NV12 ? ((x0 - 2) & ~15) : (((x0 >> 1) - 1) & ~15);
             const int cw = W >> 1;
             if (xt < 0 || xt + kLumaBox > W || xc < 0 || (NV12 ? xc + kNv12Box > W : xc + kPlanarBox > cw)) {
-                unsigned char *st = smem + (size_t)buf * kStageBytes;
+                unsigned char *st = smem;
                 const int sub = tid & 7;
                 {   // luma: tile byte b <-> pixel xt + b; valid bytes [bl, br)
                     const int bl = min(max(0, -xt), kLumaBox - 1), br = min(max(W - xt, 1), kLumaBox);
@@ -388,8 +384,11 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
             }
             nchunk++;
         }
+        // every warp has read its rows of the stage (and, for a last chunk, stored them in the ring): the next chunk's
+        // loads refill the stage while the vertical pass runs
+        group_sync(grp);
+        if (tid == 0) issue(nxt);
         if (cur.last) {
-            group_sync(grp);
             // ---- phase B: vertical pass ------------------------------------------------------------------------------
             const int tv = J.taps_v;
             const float *lbase = ring + lane * 3 * OUT;
@@ -479,6 +478,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                 const int oy = cur.o0 + warp;
                 if (oy < row_end) one_row(oy);
             }
+            group_sync(grp);   // the ring rows this pass read may be overwritten by the next step's horizontal pass
         }
         cur = nxt;
     }
