@@ -129,7 +129,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -365,6 +365,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the compositor has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # nvidia-smi needs a few hundred ms before its first row: started now, it is streaming by the time the timed region
+    # begins (rank 0 only -- its line is the one that is printed)
+    clocks = ClockSampler(local)
+    if int(os.environ.get("RANK", "0")) == 0:
+        clocks.start()
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -459,9 +464,6 @@ def main():
     # ---- value: device-resident, device-timed ---------------------------------------------------------
     # already streaming when the timed region starts (nvidia-smi takes ~0.2 s to start); rank 0 only -- its line is the
     # one that is printed, and N concurrent nvidia-smi loops would only contend for the driver lock
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     # set-up, not warm-up: the first ticks of a handle compute the Lanczos weight tables, encode the TMA descriptors of
     # every frame buffer, size the arenas and take the clocks out of idle; the W warm-up steps follow
     for k in range(-8, 0):

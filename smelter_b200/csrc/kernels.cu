@@ -26,6 +26,8 @@
 namespace smr {
 namespace dev {
 
+#include "ptx_helpers.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // tables (NC-1, NC-3, NC-4) -- pushed from the host so host and device agree bit-for-bit.  Plain global
 // memory: every block copies them to shared memory with one coalesced load per warp (a per-thread index into
@@ -926,6 +928,97 @@ int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// FAST_HALF: K1/K2 of one source row of an aligned 8-pixel run (x0 even, interior: 2 <= x0, x0 + 9 <= W - 1, chroma rows
+// inside), packed FP32 as in resample_tma.cuh; the bytes of pixels (2i, 2i + 1) are ADDED to sums[i][c].  The result of
+// yuv_to_rgba8() bit for bit (same operations, two pixels per instruction).
+// ------------------------------------------------------------------------------------------------
+// one source row: yw = its 8 luma bytes, v[k] = 3 * heavy + light chroma texel cx - 1 + k (u in bits 0..15, v in 16..31)
+__device__ __forceinline__ void half_row_convert(const uint32_t (&yw)[2], const uint32_t (&v)[6], float nk16, float rcp_y, float rcp_c,
+                                                 int (&sums)[4][3]);
+
+template <bool NV12>
+__device__ __forceinline__ void half_row_sums(const Tex &S, int x0, int r, float nk16, float rcp_y, float rcp_c, int (&sums)[4][3]) {
+    const uint8_t *yrow = S.p0 + (size_t)r * S.pitch0 + x0;
+    const uint32_t yw[2] = {__ldg(reinterpret_cast<const uint32_t *>(yrow)), __ldg(reinterpret_cast<const uint32_t *>(yrow) + 1)};
+    const int ch = r >> 1, cl = (r & 1) ? ch + 1 : ch - 1, cx = x0 >> 1;
+    uint32_t v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t h, l;
+        if (NV12) {
+            const uint32_t th = __ldg(reinterpret_cast<const unsigned short *>(S.p1 + (size_t)ch * S.pitch1) + (cx - 1 + k));
+            const uint32_t tl = __ldg(reinterpret_cast<const unsigned short *>(S.p1 + (size_t)cl * S.pitch1) + (cx - 1 + k));
+            h = __byte_perm(th, 0, 0x4140); l = __byte_perm(tl, 0, 0x4140);
+        } else {
+            h = __ldg(S.p1 + (size_t)ch * S.pitch1 + cx - 1 + k) | ((uint32_t)__ldg(S.p2 + (size_t)ch * S.pitch2 + cx - 1 + k) << 16);
+            l = __ldg(S.p1 + (size_t)cl * S.pitch1 + cx - 1 + k) | ((uint32_t)__ldg(S.p2 + (size_t)cl * S.pitch2 + cx - 1 + k) << 16);
+        }
+        v[k] = 3u * h + l;
+    }
+    half_row_convert(yw, v, nk16, rcp_y, rcp_c, sums);
+}
+
+// NV12, x0 % 4 == 0, chroma plane 4-byte aligned: both source rows (r even, r + 1) of one output row.  The three chroma rows
+// they touch are loaded once as 16-byte windows [x0 - 4, x0 + 12) and spread once; the heavy row (r / 2) is shared.
+__device__ __forceinline__ void half_pair_sums_nv12(const Tex &S, int x0, int r, float nk16, float rcp_y, float rcp_c, int (&sums)[4][3]) {
+    const int ch = r >> 1;
+    auto spread_row = [&](int crow, uint32_t (&t)[6]) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(S.p1 + (size_t)crow * S.pitch1 + x0 - 4);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        t[0] = __byte_perm(w0, 0, 0x4342); t[1] = __byte_perm(w1, 0, 0x4140); t[2] = __byte_perm(w1, 0, 0x4342);
+        t[3] = __byte_perm(w2, 0, 0x4140); t[4] = __byte_perm(w2, 0, 0x4342); t[5] = __byte_perm(w3, 0, 0x4140);
+    };
+    uint32_t th[6], tl[6], v[6];
+    spread_row(ch, th);
+#pragma unroll
+    for (int k = 0; k < 6; k++) th[k] *= 3u;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        spread_row(half ? ch + 1 : ch - 1, tl);
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] = th[k] + tl[k];
+        const uint32_t *yrow = reinterpret_cast<const uint32_t *>(S.p0 + (size_t)(r + half) * S.pitch0 + x0);
+        const uint32_t yw[2] = {__ldg(yrow), __ldg(yrow + 1)};
+        half_row_convert(yw, v, nk16, rcp_y, rcp_c, sums);
+    }
+}
+
+__device__ __forceinline__ void half_row_convert(const uint32_t (&yw)[2], const uint32_t (&v)[6], float nk16, float rcp_y, float rcp_c,
+                                                 int (&sums)[4][3]) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t ne = v[p] + 3u * v[p + 1], no = 3u * v[p + 1] + v[p + 2];
+        const float m23 = -8388608.0f;
+        float2 nu = v5::add2(make_float2(__uint_as_float(__byte_perm(ne, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(no, 0x4B000000u, 0x7610))), v5::splat(m23));
+        float2 nv = v5::add2(make_float2(__uint_as_float(__byte_perm(ne, 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(no, 0x4B000000u, 0x7632))), v5::splat(m23));
+        const uint32_t ywd = yw[p >> 1];
+        float2 ny = v5::add2(make_float2(__uint_as_float(__byte_perm(ywd, 0x4B000000u, (p & 1) ? 0x7642 : 0x7640)),
+                                         __uint_as_float(__byte_perm(ywd, 0x4B000000u, (p & 1) ? 0x7643 : 0x7641))), v5::splat(m23));
+        const float c1 = __uint_as_float(0x3b808081u), lo1 = __uint_as_float(0xaf7efeffu);
+        const float c16 = __uint_as_float(0x39808081u), lo16 = __uint_as_float(0xad7efeffu);
+        float2 y = v5::fma2(ny, v5::splat(c1), v5::mul2(ny, v5::splat(lo1)));
+        float2 u = v5::fma2(nu, v5::splat(c16), v5::mul2(nu, v5::splat(lo16)));
+        float2 w = v5::fma2(nv, v5::splat(c16), v5::mul2(nv, v5::splat(lo16)));
+        y = v5::add2(y, v5::splat(nk16)); u = v5::add2(u, v5::splat(nk16)); w = v5::add2(w, v5::splat(nk16));
+        y = make_float2(__saturatef(y.x * rcp_y), __saturatef(y.y * rcp_y));
+        u = make_float2(__saturatef(u.x * rcp_c), __saturatef(u.y * rcp_c));
+        w = make_float2(__saturatef(w.x * rcp_c), __saturatef(w.y * rcp_c));
+        const float2 um = v5::add2(u, v5::splat(-0.5f)), vm = v5::add2(w, v5::splat(-0.5f));
+        const float2 gi = v5::fma2(v5::splat(-0.1873f), um, y);
+        const float2 rr = make_float2(__saturatef(fmaf(1.5748f, vm.x, y.x)), __saturatef(fmaf(1.5748f, vm.y, y.y)));
+        const float2 gg = make_float2(__saturatef(fmaf(-0.4681f, vm.x, gi.x)), __saturatef(fmaf(-0.4681f, vm.y, gi.y)));
+        const float2 bb = make_float2(__saturatef(fmaf(1.8556f, um.x, y.x)), __saturatef(fmaf(1.8556f, um.y, y.y)));
+        const float magic = 12582912.0f;   // 1.5 * 2^23: the add rounds to the nearest-even integer (NC-2)
+        const float2 qr = v5::add2_after_mul(v5::mul2(rr, v5::splat(255.0f)), v5::splat(magic));
+        const float2 qg = v5::add2_after_mul(v5::mul2(gg, v5::splat(255.0f)), v5::splat(magic));
+        const float2 qb = v5::add2_after_mul(v5::mul2(bb, v5::splat(255.0f)), v5::splat(magic));
+        sums[p][0] += (int)(__float_as_uint(qr.x) & 0xffu) + (int)(__float_as_uint(qr.y) & 0xffu);
+        sums[p][1] += (int)(__float_as_uint(qg.x) & 0xffu) + (int)(__float_as_uint(qg.y) & 0xffu);
+        sums[p][2] += (int)(__float_as_uint(qb.x) & 0xffu) + (int)(__float_as_uint(qb.y) & 0xffu);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9 (+K10/K11): composite
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float smoothstep_f(float e0, float e1, float x) {
@@ -1321,6 +1414,39 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
                         px[j][i] = make_uchar4(lut[p.x].x, lut[p.y].y, lut[p.z].z, lut[p.w].w);
                     }
                 break;
+            }
+            if (all_in && (L.fast & FAST_HALF)) {
+                // exact 2:1 planar 4:2:0 / NV12 child (CpuOptimized): this thread's 4 x 2 pixels are the weight-1/2 taps of an
+                // aligned 8 x 4 texel block; away from the texture border K1/K2 runs on pixel pairs with packed FP32
+                const Tex &S = J.textures[L.tex];
+                const int sx = 2 * (x0 + L.tx_off), sy = 2 * (y0 + L.ty_off);
+                if (sx >= 2 && sx + 9 <= S.width - 1 && sy >= 2 && sy + 5 <= S.height - 1) {
+                    const bool fr = S.full_range != 0;
+                    const float nk16 = fr ? 0.0f : -K16, rcp_y = fr ? 1.0f : RCP_Y, rcp_c = fr ? 1.0f : RCP_C;
+#pragma unroll
+                    for (int j = 0; j < CT_H; j++) {
+                        int sums[4][3];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) sums[i][0] = sums[i][1] = sums[i][2] = 0;
+                        if (S.kind == TEX_NV12 && (S.pitch1 & 3) == 0 && ((size_t)S.p1 & 3) == 0) {
+                            half_pair_sums_nv12(S, sx, sy + 2 * j, nk16, rcp_y, rcp_c, sums);
+                        } else if (S.kind == TEX_NV12) {
+                            half_row_sums<true>(S, sx, sy + 2 * j, nk16, rcp_y, rcp_c, sums);
+                            half_row_sums<true>(S, sx, sy + 2 * j + 1, nk16, rcp_y, rcp_c, sums);
+                        } else {
+                            half_row_sums<false>(S, sx, sy + 2 * j, nk16, rcp_y, rcp_c, sums);
+                            half_row_sums<false>(S, sx, sy + 2 * j + 1, nk16, rcp_y, rcp_c, sums);
+                        }
+#pragma unroll
+                        for (int i = 0; i < CT_W; i++) {
+                            // filter_u8 at weights (128, 128): N = 16384 (t00 + t10 + t01 + t11), NC-6u, stored through NC-2
+                            px[j][i] = make_uchar4((unsigned char)unorm8(div255((float)(sums[i][0] << 14), 1.0f / 65536.0f)),
+                                                   (unsigned char)unorm8(div255((float)(sums[i][1] << 14), 1.0f / 65536.0f)),
+                                                   (unsigned char)unorm8(div255((float)(sums[i][2] << 14), 1.0f / 65536.0f)), 255);
+                        }
+                    }
+                    break;
+                }
             }
             if (all_in && (L.fast & FAST_SAMPLE)) {
                 // opaque RGBA8 child sampled at a fractional position / size, axis-aligned: the taps depend on the

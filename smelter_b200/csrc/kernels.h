@@ -77,7 +77,9 @@ struct alignas(16) LayerDev {
 // whose alpha is 255 everywhere) -- earlier layers cannot show through there
 // FAST_SAMPLE: axis-aligned opaque RGBA8 child that is NOT 1:1 -- inside the bars each pixel is the filtered,
 // re-encoded sample alone (source alpha exactly 1)
-enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2, FAST_LUT = 4, FAST_OPAQUE = 8, FAST_SAMPLE = 16 };
+// FAST_HALF (with FAST_SAMPLE): CpuOptimized, planar 4:2:0 / NV12 child shown at exactly half its size on whole pixels
+// -- every output pixel is the weight-1/2 bilinear tap of one aligned 2x2 texel quad: texel = (2 (px + tx_off), 2 (py + ty_off))
+enum : int32_t { FAST_IDENT = 1, FAST_CONST = 2, FAST_LUT = 4, FAST_OPAQUE = 8, FAST_SAMPLE = 16, FAST_HALF = 32 };
 
 struct CompositeJob {
     int32_t width, height;           // render target (root node texture) size

@@ -962,6 +962,16 @@ void Renderer::prepare_layer(const RenderLayout &l, int W, int H, int tex_index,
                 // resampled child; planar 4:2:0 / NV12 in CpuOptimized: the layout shader's own bilinear scaling of
                 // the (virtual) node texture, K1/K2 evaluated per tap quad
                 d.fast |= dev::FAST_SAMPLE | dev::FAST_OPAQUE;
+                const dev::Tex &tt = tex_table_[tex_index];
+                if (tt.kind != dev::TEX_RGBA8 && ((tex_w | tex_h) & 1) == 0 && tex_w <= 4096 && tex_h <= 4096 &&
+                    l.width * 2.0f == (float)tex_w && l.height * 2.0f == (float)tex_h && l.crop.left == 0.0f && l.crop.top == 0.0f &&
+                    l.crop.width == (float)tex_w && l.crop.height == (float)tex_h && integral(l.left) && integral(l.top) &&
+                    ((int)l.left & 1) == 0 && (tt.pitch0 & 3) == 0 && ((uintptr_t)tt.p0 & 3) == 0) {
+                    // exact 2:1 on whole pixels (a 2x2 grid of same-size inputs): sample coordinate = 2 k + 1/2 with an error
+                    // far below the 1/512 weight step, so the taps are the aligned texel quad at weights exactly 1/2
+                    d.fast |= dev::FAST_HALF;
+                    d.tx_off = -(int)l.left; d.ty_off = -(int)l.top;
+                }
             }
         }
     }
