@@ -66,6 +66,11 @@ def workload(name):
                                                  overlay])
         mode = s.RenderingMode.GpuOptimized
         desc = "16x(1920x1080 NV12)->3840x2160 NV12, Tiles 4x4, Lanczos3 2:1, rounded corners + alpha overlay"
+    elif name == "grid25":  # 25 x 4K -> 4K, Tiles 5x5: ratio 5:1 > 4 -> one box pre-decimation level + Lanczos (the generic path)
+        W, H, n, iw, ih = 3840, 2160, 25, 3840, 2160
+        scene = s.TilesComponent(children=streams(n), background_color=bg)
+        mode = s.RenderingMode.GpuOptimized
+        desc = "25x(3840x2160 NV12)->3840x2160 NV12, Tiles 5x5, box 2:1 + Lanczos3 2.5:1 (resampler.rs:56-67), GpuOptimized"
     elif name == "cfg2":  # 4 x 1080p NV12 -> 1080p NV12, Tiles 2x2, CpuOptimized (gamma blend, bilinear)
         W, H, n, iw, ih = 1920, 1080, 4, 1920, 1080
         scene = s.TilesComponent(children=streams(n), background_color=bg)

@@ -69,6 +69,13 @@ def test_cfg4_bench_scenes_eight_outputs_one_tick():
 
 
 @pytest.mark.slow
+def test_grid25_bench_scene_full_size():
+    """25 x 4K -> 4K, Tiles 5x5 (5:1): box pre-decimation + Lanczos through the generic resampler passes
+    (resampler.rs:56-67,305-340, downsample.wgsl:28-41) at full size"""
+    check_workload("grid25", 7600)
+
+
+@pytest.mark.slow
 def test_cfg5_bench_scene_full_size():
     """32 x 4K -> 8K, 6x6 grid with margins (any-ratio kernel, fractional tile positions), radius + box shadows"""
     check_workload("cfg5", 7500)
