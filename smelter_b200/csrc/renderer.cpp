@@ -105,11 +105,13 @@ static int resample_taps(float scale) {  // resample.wgsl:43-48
 // output rows a block produces per step).  Block b owns pieces [begin[b], begin[b+1]); every output row of every
 // strip belongs to exactly one piece.
 void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst_h, int n_jobs, int max_blocks,
-                          std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin, int strip_cols = dev::kFusedStripCols) {
+                          std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin, int strip_cols_all = dev::kFusedStripCols,
+                          const int *strip_cols_per_job = nullptr) {
     pieces.clear(); begin.clear();
     long long total = 0;
+    auto cols_of = [&](int i) { return strip_cols_per_job ? strip_cols_per_job[i] : strip_cols_all; };
     for (int i = 0; i < n_jobs; i++)
-        if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + strip_cols - 1) / strip_cols) * dst_h[i];
+        if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + cols_of(i) - 1) / cols_of(i)) * dst_h[i];
     if (total <= 0 || max_blocks <= 0) return;
     const int nblocks = (int)std::min<long long>((long long)max_blocks, (total + 7) / 8);
     const long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
@@ -117,7 +119,7 @@ void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst
     long long room = per_block;
     for (int i = 0; i < n_jobs; i++) {
         if (dst_w[i] <= 0 || dst_h[i] <= 0) continue;
-        const int strips = (dst_w[i] + strip_cols - 1) / strip_cols;
+        const int strips = (dst_w[i] + cols_of(i) - 1) / cols_of(i);
         for (int st = 0; st < strips; st++) {
             int y = 0;
             while (y < dst_h[i]) {
@@ -345,6 +347,9 @@ class Renderer {
         bool operator<(const TmapKey &o) const { return std::tie(p, pitch, w, h, kind) < std::tie(o.p, o.pitch, o.w, o.h, o.kind); }
     };
     std::map<TmapKey, CUtensorMap> tmap_cache_;
+    // any-ratio TMA kernel: per (horizontal mapping, strip width) the lane <-> column-pair deal of every strip
+    std::map<std::tuple<uint32_t, uint32_t, int32_t, int32_t>, uint8_t *> lane_perms_;
+    const uint8_t *lane_perm(float scale, float offset, int n_out, int cols);
     bool plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, CUtensorMap *out);
     std::vector<CUtensorMap> tick_tmaps_;      // three per TMA job
     std::vector<int> fused_tmap_idx_;          // per fused job: first of its three entries in tick_tmaps_, or -1
@@ -428,6 +433,7 @@ Renderer::~Renderer() {
         for (auto &kv : weights_) {
             cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
         }
+        for (auto &kv : lane_perms_) cudaFree(kv.second);
         cudaStreamDestroy(stream_);
     }
 }
@@ -760,6 +766,32 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
             }
         }
     }
+    if (j.variant < 10 && !disable_tma_ && tma_grouped_ && src_class < 2 && (dw & 1) == 0 && th <= dev::kTma0MaxTaps &&
+        (int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 1 <= dev::kTmaRing4) {
+        // any other ratio <= 4 (fractional, 3, with a crop offset): the any-ratio TMA kernel; its strips are narrowed so that
+        // a strip's source span fits the 256 pixels a warp converts per row
+        int cols = 64;
+        while (cols > 2 && (int)std::ceil((cols - 1) * sh) + th + 3 > dev::kTma0MaxSpan) cols -= 2;
+        // slots of a lane's window: taps + the widest distance of two adjacent columns' first taps + the pad slots crossed
+        const int gmax = sh == std::floor(sh) ? (int)sh : (int)std::floor(sh) + 1;
+        const int win = th + gmax, winp = win + ((7 + win - 1) >> 3);
+        int bucket = 0;
+        while (bucket < 4 && dev::kTma0Window[bucket] < winp) bucket++;
+        CUtensorMap m[3];
+        memset(m, 0, sizeof(m));
+        bool ok = bucket < 4 && (int)std::ceil((cols - 1) * sh) + th + 3 <= dev::kTma0MaxSpan &&
+                  plane_tmap(t.p0, t.pitch0, t.width, t.height, 4, &m[0]);
+        if (ok && src_class == 1) ok = plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 1 | 4, &m[1]);
+        else if (ok) ok = plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 2 | 4, &m[1]) &&
+                          plane_tmap(t.p2, t.pitch2, t.width / 2, t.height / 2, 2 | 4, &m[2]);
+        if (ok) {
+            tmap_idx = (int)tick_tmaps_.size();
+            tick_tmaps_.insert(tick_tmaps_.end(), m, m + 3);
+            j.strip_cols = cols;
+            j.lane_perm = lane_perm(sh, hm.crop_offset, dw, cols);   // nullptr (identity) if the table could not be made
+            j.variant = 30 + bucket;
+        }
+    }
     fused_jobs_.push_back(j);
     fused_tmap_idx_.push_back(tmap_idx);
     fused_src_dst_.push_back({in.raw_tex, dst_off});
@@ -770,6 +802,53 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     tex_opaque_.push_back(1);   // the fused kernel reads YUV and writes alpha 255
     tex_frame_off_.push_back(dst_off);
     return idx;
+}
+
+// The deal of a strip's 32 column pairs to the 32 lanes (resample_tma0.cuh): a tap of the horizontal pass is one LDS.128
+// per lane at the lane's window start + tap, served a quarter-warp (8 lanes) at a time; two lanes of a quarter whose
+// starts fall in the same 16-byte bank group cost an extra wavefront.  Sorting the pairs by bank group and dealing them
+// round-robin to the four quarters gives every quarter ceil(n_k / 4) lanes of group k at most -- the minimum.  Only the
+// speed depends on this table: the first-tap indices are recomputed here the way k_weights computes them, and a pair
+// owned by the "wrong" lane is still resampled exactly.
+const uint8_t *Renderer::lane_perm(float scale, float offset, int n_out, int cols) {
+    uint32_t sb, ob;
+    memcpy(&sb, &scale, 4); memcpy(&ob, &offset, 4);
+    auto key = std::make_tuple(sb, ob, (int32_t)n_out, (int32_t)cols);
+    auto it = lane_perms_.find(key);
+    if (it != lane_perms_.end()) return it->second;
+    if (lane_perms_.size() > 4096) {
+        cudaStreamSynchronize(stream_);
+        for (auto &e : lane_perms_) cudaFree(e.second);
+        lane_perms_.clear();
+    }
+    const float ks = std::fmax(scale, 1.0f);
+    auto first = [&](int o) {
+        volatile float c = offset + ((float)o + 0.5f) * scale;
+        volatile float d = c - 0.5f;
+        return (int)std::ceil(d - 3.0f * ks);
+    };
+    const int strips = (n_out + cols - 1) / cols;
+    std::vector<uint8_t> perm((size_t)strips * 32);
+    for (int st = 0; st < strips; st++) {
+        const int ox0 = st * cols, x0 = first(ox0) & ~1;
+        int order[32], group[32];
+        for (int p = 0; p < 32; p++) {
+            const int rel = std::max(first(std::min(ox0 + 2 * p, n_out - 1)) - x0, 0);
+            group[p] = (rel + (rel >> 3)) & 7;
+            order[p] = p;
+        }
+        std::stable_sort(order, order + 32, [&](int a, int b) { return group[a] < group[b]; });
+        for (int i = 0; i < 32; i++) perm[(size_t)st * 32 + (i & 3) * 8 + (i >> 2)] = (uint8_t)order[i];
+    }
+    uint8_t *dev_perm = nullptr;
+    if (cudaMalloc(&dev_perm, perm.size()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // pageable source: staged before the call returns
+    if (cudaMemcpyAsync(dev_perm, perm.data(), perm.size(), cudaMemcpyHostToDevice, stream_) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(dev_perm); return nullptr;
+    }
+    cudaStreamSynchronize(stream_);   // once per geometry; keeps the pageable staging out of the steady state
+    lane_perms_[key] = dev_perm;
+    return dev_perm;
 }
 
 bool Renderer::plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, CUtensorMap *out) {
@@ -1448,16 +1527,17 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             if (std::find(variants.begin(), variants.end(), v) == variants.end()) variants.push_back(v);
         }
         for (auto &v : variants) {
-            std::vector<int> idx, widths, heights;
+            std::vector<int> idx, widths, heights, cols;
             for (size_t ji = 0; ji < fused_jobs_.size(); ji++) {
                 const dev::FusedJob &j = fused_jobs_[ji];
                 if (j.variant != v.first || dev::fused_source_class(j.src.kind) != v.second) continue;
                 idx.push_back((int)ji); widths.push_back(j.dst_w); heights.push_back(j.dst_h);
+                cols.push_back(v.first >= 30 ? j.strip_cols : dev::fused_strip_cols(v.first));
             }
             std::vector<dev::FusedPiece> pieces;
             std::vector<int> begin;
-            partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(), sm_count_ * 3, pieces, begin,
-                                 dev::fused_strip_cols(v.first));
+            partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(),
+                                 sm_count_ * (v.first >= 30 ? dev::kTma0Groups : 3), pieces, begin, dev::kFusedStripCols, cols.data());
             if (pieces.empty()) continue;
             FusedLaunch fl;
             fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
