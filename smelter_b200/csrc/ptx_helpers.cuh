@@ -84,6 +84,15 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return upk(d);
 }
 __device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+// the packed operands as they stand (no unpack / repack the compiler could turn into second copies of the registers)
+__device__ __forceinline__ unsigned long long fma2q(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void lds128q(uint32_t addr, unsigned long long &lo, unsigned long long &hi) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
 // a + c for an `a` that is the result of mul2(): ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under
 // --fmad=false (it does not for the scalar forms), which would round once instead of twice.  a * 1 + c as an explicit
 // fma is the same value as a + c and leaves the product alone.

@@ -44,7 +44,8 @@ struct Cfg {
     static constexpr int ROWBUF_PX = 320;            // 288 slots of the 256 converted pixels + the zero tail
     static constexpr int ROWBUF_BYTES = ROWBUF_PX * 16;   // (r, g, b, b) per pixel: one LDS.128 per tap
     static constexpr int GROUP_BYTES = kStageBytes + RING_BYTES + kWarps * ROWBUF_BYTES;
-    static constexpr int SMEM = kGroups * GROUP_BYTES + 256 * kDecRep * 4 + 256 * 4 + 128;
+    static constexpr int STASH_BYTES = 1024;         // per group and parity: the chunk iterator + the next chunk, parked during the phases
+    static constexpr int SMEM = kGroups * GROUP_BYTES + 256 * kDecRep * 4 + 256 * 4 + 128 + STASH_BYTES;
 };
 
 struct Chunk {      // warp-uniform description of one pipeline step
@@ -147,6 +148,12 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
     const int vb = blockIdx.x * kGroups + grp;         // the host cut the launch for SMs x 3 eight-warp blocks
     if (vb >= n_virtual_blocks) return;
 
+    // The iterator (20 registers) and the next chunk (9) are not needed while a chunk is being processed: thread 0 of the
+    // group parks them in shared memory, everybody reloads them at the end of the step -- the tap loop gets the registers
+    struct Stash { ChunkIter it; Chunk nxt; };
+    static_assert(sizeof(Stash) * 2 * kGroups <= K::STASH_BYTES, "stash");
+    Stash *stash = reinterpret_cast<Stash *>(reinterpret_cast<unsigned char *>(s_thr + 256) + 128) + 2 * grp;
+    uint32_t step = 0;
     ChunkIter it;
     it.init(jobs, pieces, __ldg(piece_begin + vb), __ldg(piece_begin + vb + 1));
 
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
     };
 
     static_assert(WINP <= K::WINP_MAX, "window");
-    float2 wq[WINP];      // registers (every index is a compile-time constant after unrolling): (weight of column 2 lane,
+    unsigned long long wq[WINP];      // registers (every index is a compile-time constant after unrolling): (weight of column 2 lane,
                             // weight of column 2 lane + 1) for source pixel j of the lane's union window
     float inv0 = 0.f, inv1 = 0.f;
     int rel0 = 0, w_job = -1, w_ox0 = -1;
@@ -183,7 +190,11 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
     uint32_t nchunk = 0;        // chunks that carried a TMA load so far (mbarrier parity)
 
     while (cur.valid) {
-        Chunk nxt = it.next();
+        Stash *const parked = stash + (step & 1u);   // the slot of step k is rewritten in step k + 2: a group_sync lies between
+        {
+            const Chunk nxt = it.next();
+            if (tid == 0) { parked->it = it; parked->nxt = nxt; }
+        }
         const bool cur_tma = cur.nrows > 0;
         const FusedJob &J = jobs[cur.job];
         const int W = J.src.width, H = J.src.height, chei = H >> 1;
@@ -212,8 +223,8 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                 const int slot = rel0 + jj, q = slot / 9;
                 const bool pad = slot - 9 * q == 8;
                 const int j = slot - q - rel, t = j - gD;     // pixel of the window, tap of the second column
-                wq[jj].x = (!pad && j < th) ? __ldg(J.w_h + (size_t)oc0 * th + j) : 0.0f;
-                wq[jj].y = (!pad && t >= 0 && t < th) ? __ldg(J.w_h + (size_t)oc1 * th + t) : 0.0f;
+                wq[jj] = v5::pk(make_float2((!pad && j < th) ? __ldg(J.w_h + (size_t)oc0 * th + j) : 0.0f,
+                                            (!pad && t >= 0 && t < th) ? __ldg(J.w_h + (size_t)oc1 * th + t) : 0.0f));
             }
         }
         if (cur_tma) {
@@ -368,16 +379,24 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                 // leaves the sum alone
                 {
                     float r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f;
-                    float2 ab = make_float2(0.f, 0.f);
-                    const float4 *wp = rowbuf + rel0;
+                    unsigned long long abq = 0ull;
+                    const uint32_t wa = v5::smem_u32(rowbuf + rel0);
+                    // three loads in flight: a tap's LDS.128 is issued three taps ahead of its five FMAs
+                    constexpr int DEPTH = 3;
+                    unsigned long long brg[DEPTH], bbb[DEPTH];
+#pragma unroll
+                    for (int j = 0; j < DEPTH; j++) v5::lds128q(wa + 16u * j, brg[j], bbb[j]);
 #pragma unroll
                     for (int j = 0; j < WINP; j++) {
-                        const float4 v = wp[j];          // (r, g, b, b), or a pad / tail slot of zeros under weight 0
-                        r0 = fmaf(v.x, wq[j].x, r0); r1 = fmaf(v.x, wq[j].y, r1);
-                        g0 = fmaf(v.y, wq[j].x, g0); g1 = fmaf(v.y, wq[j].y, g1);
-                        ab = v5::fma2(make_float2(v.z, v.w), wq[j], ab);
+                        const float2 rg = v5::upk(brg[j % DEPTH]);   // (r, g) | (b, b); a pad / tail slot holds zeros under weight 0
+                        const unsigned long long bb = bbb[j % DEPTH];
+                        const float2 w = v5::upk(wq[j]);
+                        r0 = fmaf(rg.x, w.x, r0); r1 = fmaf(rg.x, w.y, r1);
+                        g0 = fmaf(rg.y, w.x, g0); g1 = fmaf(rg.y, w.y, g1);
+                        abq = v5::fma2q(bb, wq[j], abq);
+                        if (j + DEPTH < WINP) v5::lds128q(wa + 16u * (j + DEPTH), brg[j % DEPTH], bbb[j % DEPTH]);
                     }
-                    const float2 a0 = make_float2(r0, g0), a1 = make_float2(r1, g1);
+                    const float2 a0 = make_float2(r0, g0), a1 = make_float2(r1, g1), ab = v5::upk(abq);
                     // normalise, quantise to f16 (NC-5) and park the row in the ring: [row][lane][channel][column]
                     float *dst = ring + (size_t)(r % K::RROWS) * (K::RROW_BYTES / 4) + lane * 6;
                     *reinterpret_cast<float2 *>(dst) = __half22float2(__floats2half2_rn(a0.x * inv0, a1.x * inv1));
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
         // every warp has read its rows of the stage (and, for a last chunk, stored them in the ring): the next chunk's
         // loads refill the stage while the vertical pass runs
         group_sync(grp);
-        if (tid == 0) issue(nxt);
+        if (tid == 0) issue(parked->nxt);
         if (cur.last) {
             // ---- phase B: vertical pass ------------------------------------------------------------------------------
             const int tv = J.taps_v;
@@ -460,7 +479,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
             }
             group_sync(grp);   // the ring rows this pass read may be overwritten by the next step's horizontal pass
         }
-        cur = nxt;
+        cur = parked->nxt; it = parked->it; step++;   // written before this step's group_sync
     }
 }
 
