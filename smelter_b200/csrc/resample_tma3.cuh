@@ -52,7 +52,8 @@ struct Cfg {
     static constexpr int RROW_BYTES = 32 * 3 * OUT * 4;
     static constexpr int RING_BYTES = RROWS * RROW_BYTES;
     static constexpr int GROUP_BYTES = kStageBytes + RING_BYTES;   // ONE stage: it is refilled while the vertical pass runs
-    static constexpr int SMEM = kGroups * GROUP_BYTES + 256 * kDecRep * 4 + 256 * 4 + 128;
+    static constexpr int STASH_BYTES = 1024;   // per group and parity: the chunk iterator + the next chunk, parked during the phases
+    static constexpr int SMEM = kGroups * GROUP_BYTES + 256 * kDecRep * 4 + 256 * 4 + 128 + STASH_BYTES;
 };
 
 struct Chunk {      // warp-uniform description of one pipeline step
@@ -153,6 +154,12 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
     const int vb = blockIdx.x * kGroups + grp;         // the host cut the launch for SMs x 3 eight-warp blocks
     if (vb >= n_virtual_blocks) return;
 
+    // The iterator and the next chunk are not needed while a chunk is being processed: thread 0 of the group parks them in
+    // shared memory, everybody reloads them at the end of the step -- some 30 registers less across the phases
+    struct Stash { ChunkIter<S> it; Chunk nxt; };
+    static_assert(sizeof(Stash) * 2 * kGroups <= K::STASH_BYTES, "stash");
+    Stash *stash = reinterpret_cast<Stash *>(reinterpret_cast<unsigned char *>(s_thr + 256) + 128) + 2 * grp;
+    uint32_t step = 0;
     ChunkIter<S> it;
     it.init(jobs, pieces, __ldg(piece_begin + vb), __ldg(piece_begin + vb + 1));
 
@@ -182,7 +189,11 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
     uint32_t nchunk = 0;        // chunks that carried a TMA load so far (mbarrier parity)
 
     while (cur.valid) {
-        Chunk nxt = it.next();
+        Stash *const parked = stash + (step & 1u);   // the slot of step k is rewritten in step k + 2: a group_sync lies between
+        {
+            const Chunk nxt = it.next();
+            if (tid == 0) { parked->it = it; parked->nxt = nxt; }
+        }
         const bool cur_tma = cur.nrows > 0;
         const FusedJob &J = jobs[cur.job];
         const int W = J.src.width, H = J.src.height, chei = H >> 1;
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
         // every warp has read its rows of the stage (and, for a last chunk, stored them in the ring): the next chunk's
         // loads refill the stage while the vertical pass runs
         group_sync(grp);
-        if (tid == 0) issue(nxt);
+        if (tid == 0) issue(parked->nxt);
         if (cur.last) {
             // ---- phase B: vertical pass ------------------------------------------------------------------------------
             const int tv = J.taps_v;
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
             }
             group_sync(grp);   // the ring rows this pass read may be overwritten by the next step's horizontal pass
         }
-        cur = nxt;
+        cur = parked->nxt; it = parked->it; step++;   // written before this step's group_sync
     }
 }
 
