@@ -870,18 +870,18 @@ namespace dev {
 #include "resample_tma3.cuh"
 #include "resample_tma0.cuh"
 
-template <int SRC, int WINP>
+template <int SRC, int WINP, int BOX>
 static bool launch_tma0(const FusedJob *jobs_dev, const FusedPiece *pieces, const int *piece_begin, int nblocks, cudaStream_t s) {
     static std::atomic<unsigned long long> done{0};
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(done.load(std::memory_order_acquire) & bit)) {
-        cudaFuncSetAttribute(v7::k_resample_tma0<SRC, WINP>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::Cfg::SMEM);
+        cudaFuncSetAttribute(v7::k_resample_tma0<SRC, WINP, BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::Cfg::SMEM);
         done.fetch_or(bit, std::memory_order_release);
     }
     const int grid = (nblocks + v7::kGroups - 1) / v7::kGroups;
-    v7::k_resample_tma0<SRC, WINP><<<grid, dim3(32, v7::kWarps * v7::kGroups), v7::Cfg::SMEM, s>>>(jobs_dev, pieces, piece_begin, nblocks);
+    v7::k_resample_tma0<SRC, WINP, BOX><<<grid, dim3(32, v7::kWarps * v7::kGroups), v7::Cfg::SMEM, s>>>(jobs_dev, pieces, piece_begin, nblocks);
     return check_launch("k_resample_tma0");
 }
 
@@ -929,8 +929,10 @@ int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const 
                   v5::kPlanarBox == kTmaPlanarBoxW && v5::kChromaRows == kTmaChromaBoxH, "TMA boxes");
     switch (variant) {
 #define SMR_TMA0_CASE(B) \
-        case 30 + B: ok = src == 1 ? launch_tma0<1, kTma0Window[B]>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st) \
-                                   : launch_tma0<0, kTma0Window[B]>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
+        case 30 + B: ok = src == 1 ? launch_tma0<1, kTma0Window[B], 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st) \
+                                   : launch_tma0<0, kTma0Window[B], 0>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break; \
+        case 40 + B: ok = src == 1 ? launch_tma0<1, kTma0Window[B], 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st) \
+                                   : launch_tma0<0, kTma0Window[B], 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st); break;
         SMR_TMA0_CASE(0) SMR_TMA0_CASE(1) SMR_TMA0_CASE(2) SMR_TMA0_CASE(3)
 #undef SMR_TMA0_CASE
         case 22: ok = src == 1 ? launch_tma3<2, 1>(jobs_dev, pieces_dev, piece_begin_dev, nblocks, st)

@@ -714,22 +714,36 @@ int Renderer::materialised_input(Input &in) {
 // The common case -- a YUV input scaled on both axes, horizontal pass first, no box pre-pass -- runs as ONE
 // kernel (k_resample_fused).  Returns the texture-table index of the result, -1 when not eligible
 // (the generic multi-pass path is used), -2 on error.
-int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMapping &vm, int dw, int dh) {
+int Renderer::try_fused_resample(Input &in, const AxisMapping &hm_in, const AxisMapping &vm_in, int dw, int dh) {
     const dev::Tex &t = in.tex;
     const int src_class = dev::fused_source_class(t.kind);
     if (src_class < 0) return -1;
     if (src_class < 2 && ((t.width | t.height) & 1)) return -1;
     // interleaved 4:2:2: texel-centre fast form holds for even widths >= 8 and 4-byte aligned rows
     if (src_class >= 2 && ((t.width & 1) || t.width < 8 || (t.pitch0 & 3) || ((uintptr_t)t.p0 & 3))) return -1;
-    if (hm.predecimate_levels() != 0 || vm.predecimate_levels() != 0) return -1;
+    // one box pre-decimation level on both axes (ratios in (4, 8], resampler.rs:56-67): the any-ratio TMA kernel reduces
+    // the source 2:1 on the fly and resamples the reduced texture; other level combinations take the generic passes
+    const int lv_h = hm_in.predecimate_levels(), lv_v = vm_in.predecimate_levels();
+    const bool box = lv_h == 1 && lv_v == 1;
+    if (!box && (lv_h != 0 || lv_v != 0)) return -1;
+    if (box && (disable_tma_ || !tma_grouped_ || src_class >= 2 || (dw & 1))) return -1;
+    const AxisMapping hm = box ? hm_in.on_reduced_source(1) : hm_in, vm = box ? vm_in.on_reduced_source(1) : vm_in;
     KernelPass passes[2];
     if (plan_passes(hm, vm, passes) != 2 || passes[0].mapping.axis != 0) return -1;
     float sh = hm.scale(), sv = vm.scale();
     if (!(sh > 0.0f) || !(sv > 0.0f) || !(sh <= 4.001f) || !(sv <= 4.001f)) return -1;
     int th = resample_taps(sh), tv = resample_taps(sv);
     if (th > dev::kFusedMaxTaps || tv > dev::kFusedMaxTaps) return -1;
-    if ((int)std::ceil((dev::kFusedStripCols - 1) * sh) + th + 2 > dev::kFusedSpan) return -1;
-    if ((int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 2 > dev::kFusedRing) return -1;
+    if (!box) {
+        if ((int)std::ceil((dev::kFusedStripCols - 1) * sh) + th + 2 > dev::kFusedSpan) return -1;
+        if ((int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 2 > dev::kFusedRing) return -1;
+    } else {
+        int cols = 64;
+        const int max_span = dev::kTma0MaxSpan / 2;
+        while (cols > 2 && (int)std::ceil((cols - 1) * sh) + th + 3 > max_span) cols -= 2;
+        if ((int)std::ceil((cols - 1) * sh) + th + 3 > max_span) return -1;
+        if ((int)std::ceil((dev::kFusedWarps - 1) * sv) + tv + 1 > dev::kTmaRing4) return -1;
+    }
     WeightEntry wh, wv;
     if (get_weights(passes[0], wh) != SMR_OK || get_weights(passes[1], wv) != SMR_OK) return -2;
     size_t dst_off = frame_alloc((size_t)dw * dh * 4);
@@ -740,7 +754,7 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
     j.w_v = wv.weights; j.inv_v = wv.inv; j.first_v = wv.first;
     j.variant = 0;
     int tmap_idx = -1;
-    if (hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) {
+    if (!box && hm.crop_offset == 0.0f && (sh == 2.0f || sh == 3.0f || sh == 4.0f)) {
         j.variant = (int)sh;
         if (!int_weights_set_[j.variant]) {   // enqueued after k_weights of this tick (same stream)
             int_weights_set_[j.variant] = true;
@@ -771,7 +785,8 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
         // any other ratio <= 4 (fractional, 3, with a crop offset): the any-ratio TMA kernel; its strips are narrowed so that
         // a strip's source span fits the 256 pixels a warp converts per row
         int cols = 64;
-        while (cols > 2 && (int)std::ceil((cols - 1) * sh) + th + 3 > dev::kTma0MaxSpan) cols -= 2;
+        const int max_span = box ? dev::kTma0MaxSpan / 2 : dev::kTma0MaxSpan;   // the row buffer holds 256 source pixels = 128 reduced ones
+        while (cols > 2 && (int)std::ceil((cols - 1) * sh) + th + 3 > max_span) cols -= 2;
         // slots of a lane's window: taps + the widest distance of two adjacent columns' first taps + the pad slots crossed
         const int gmax = sh == std::floor(sh) ? (int)sh : (int)std::floor(sh) + 1;
         const int win = th + gmax, winp = win + ((7 + win - 1) >> 3);
@@ -779,7 +794,7 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
         while (bucket < 4 && dev::kTma0Window[bucket] < winp) bucket++;
         CUtensorMap m[3];
         memset(m, 0, sizeof(m));
-        bool ok = bucket < 4 && (int)std::ceil((cols - 1) * sh) + th + 3 <= dev::kTma0MaxSpan &&
+        bool ok = bucket < 4 && (int)std::ceil((cols - 1) * sh) + th + 3 <= max_span &&
                   plane_tmap(t.p0, t.pitch0, t.width, t.height, 4, &m[0]);
         if (ok && src_class == 1) ok = plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 1 | 4, &m[1]);
         else if (ok) ok = plane_tmap(t.p1, t.pitch1, t.width / 2, t.height / 2, 2 | 4, &m[1]) &&
@@ -789,9 +804,10 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm, const AxisMap
             tick_tmaps_.insert(tick_tmaps_.end(), m, m + 3);
             j.strip_cols = cols;
             j.lane_perm = lane_perm(sh, hm.crop_offset, dw, cols);   // nullptr (identity) if the table could not be made
-            j.variant = 30 + bucket;
+            j.variant = (box ? 40 : 30) + bucket;
         }
     }
+    if (box && j.variant < 40) return -1;   // no other fused kernel reduces (the arena bytes stay unused this tick): generic passes
     fused_jobs_.push_back(j);
     fused_tmap_idx_.push_back(tmap_idx);
     fused_src_dst_.push_back({in.raw_tex, dst_off});

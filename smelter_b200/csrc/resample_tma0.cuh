@@ -64,8 +64,10 @@ struct ChunkIter {
     int job, ox0, x0, oy_end, onext, ocur;
     int produced_hi, rnext, rhi;
     int H, tv, fv0;   // of the current piece's job; fv0 = first_v[0] when the vertical mapping is the integer ratio
+    int bx;           // 1, or 2 when the kernel box-reduces the source 2:1 on the fly: rows, x0 and H are then in reduced units
     bool in_group, vs;
-    __device__ void init(const FusedJob *j, const FusedPiece *p, int b, int e) {
+    __device__ void init(const FusedJob *j, const FusedPiece *p, int b, int e, int box) {
+        bx = box;
         jobs = j; pieces = p; pi = b - 1; pend = e; in_group = false; onext = 0; oy_end = 0;
         job = ox0 = x0 = ocur = 0; produced_hi = rnext = rhi = 0; H = tv = fv0 = 0; vs = false;
     }
@@ -80,7 +82,7 @@ struct ChunkIter {
                 const FusedJob &J = jobs[P.job];
                 job = P.job; ox0 = P.strip * J.strip_cols; onext = P.oy_begin; oy_end = P.oy_end;
                 x0 = __ldg(J.first_h + ox0) & ~1;   // chroma-aligned
-                H = J.src.height; tv = J.taps_v; vs = J.v_same != 0;
+                H = J.src.height / bx; tv = J.taps_v; vs = J.v_same != 0;
                 fv0 = __ldg(J.first_v);
                 produced_hi = -0x40000000;
             }
@@ -100,8 +102,8 @@ struct ChunkIter {
         }
         c.valid = 1; c.job = job; c.ox0 = ox0; c.x0 = x0; c.o0 = ocur; c.oy_end = oy_end;
         c.r0 = rnext;
-        c.nrows = max(0, min(kChunkRows, rhi - rnext + 1));
-        rnext += kChunkRows;
+        c.nrows = max(0, min(kChunkRows / bx, rhi - rnext + 1));
+        rnext += kChunkRows / bx;
         c.last = rnext > rhi;
         return c;
     }
@@ -111,12 +113,15 @@ struct ChunkIter {
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 // WINP: slots of a lane's window the tap loop walks (host: >= taps + widest distance of two adjacent columns + pads)
-template <int SRC, int WINP>
+// BOX: the source is box-reduced 2:1 on both axes first (downsample.wgsl:28-41, one pre-decimation level of resampler.rs:56-67):
+// the two source rows of a reduced row are converted back to back, summed in the shader's order, quantised to f16
+template <int SRC, int WINP, int BOX>
 __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(const FusedJob *jobs, const FusedPiece *pieces, const int *piece_begin,
                                                                             int n_virtual_blocks) {
     using K = Cfg;
     constexpr int P = K::P, OUT = 2;
     constexpr bool NV12 = SRC == 1;
+    constexpr int BX = BOX ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int lane = threadIdx.x, warp = threadIdx.y % kWarps, grp = threadIdx.y / kWarps, tid = warp * 32 + lane;
     float *s_dec = reinterpret_cast<float *>(smem_all + kGroups * K::GROUP_BYTES);
@@ -155,23 +160,23 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
     Stash *stash = reinterpret_cast<Stash *>(reinterpret_cast<unsigned char *>(s_thr + 256) + 128) + 2 * grp;
     uint32_t step = 0;
     ChunkIter it;
-    it.init(jobs, pieces, __ldg(piece_begin + vb), __ldg(piece_begin + vb + 1));
+    it.init(jobs, pieces, __ldg(piece_begin + vb), __ldg(piece_begin + vb + 1), BX);
 
     auto issue = [&](const Chunk &c) {   // one thread: TMA loads of the chunk's boxes into the group's stage
         if (!c.valid || c.nrows == 0) return;
         const FusedJob &J = jobs[c.job];
         const uint32_t bar = bar0, dst = stage0;
-        const int cyb = (c.r0 >> 1) - 1;
-        const int xt = c.x0 & ~15;                         // luma tile: first byte, 16-byte boundary (may be negative)
+        const int cyb = ((c.r0 * BX) >> 1) - 1;
+        const int xt = (c.x0 * BX) & ~15;                         // luma tile: first byte, 16-byte boundary (may be negative)
         if (NV12) {
-            const int xc = (c.x0 - 2) & ~15;               // chroma tile: texel cx - 1 of the first pair sits at byte x0 - 2
+            const int xc = (c.x0 * BX - 2) & ~15;               // chroma tile: texel cx - 1 of the first pair sits at byte x0 - 2
             v5::mbar_expect_tx(bar, kLumaBox * kChunkRows + kNv12Box * kChromaRows);
-            v5::tma_load_2d(dst, J.tm0, xt >> 1, c.r0, bar);   // both planes are addressed in 2-byte elements
+            v5::tma_load_2d(dst, J.tm0, xt >> 1, c.r0 * BX, bar);   // both planes are addressed in 2-byte elements
             v5::tma_load_2d(dst + kLumaBytes, J.tm1, xc >> 1, cyb, bar);
         } else {
-            const int xc = ((c.x0 >> 1) - 1) & ~15;
+            const int xc = (((c.x0 * BX) >> 1) - 1) & ~15;
             v5::mbar_expect_tx(bar, kLumaBox * kChunkRows + 2 * kPlanarBox * kChromaRows);
-            v5::tma_load_2d(dst, J.tm0, xt >> 1, c.r0, bar);
+            v5::tma_load_2d(dst, J.tm0, xt >> 1, c.r0 * BX, bar);
             v5::tma_load_2d(dst + kLumaBytes, J.tm1, xc, cyb, bar);
             v5::tma_load_2d(dst + kLumaBytes + kChromaBytesPlanar, J.tm2, xc, cyb, bar);
         }
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
         }
         const bool cur_tma = cur.nrows > 0;
         const FusedJob &J = jobs[cur.job];
-        const int W = J.src.width, H = J.src.height, chei = H >> 1;
+        const int W = J.src.width, H = J.src.height, chei = H >> 1, HR = H / BX;
         const bool full_range = J.src.full_range != 0;
         const float nk16 = full_range ? 0.0f : -K16, rcp_y = full_range ? 1.0f : RCP_Y, rcp_c = full_range ? 1.0f : RCP_C;
         const uint32_t sb = stage0;
@@ -230,8 +235,8 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
         if (cur_tma) {
             v5::mbar_wait(bar0, nchunk & 1u);
             // ---- image borders: the tap index is clamped (resample.wgsl), the TMA unit zero-fills ----------------
-            const int x0 = cur.x0;
-            const int cyb = (cur.r0 >> 1) - 1;
+            const int x0 = cur.x0 * BX, sr0 = cur.r0 * BX;   // source pixel / row of the tile's origin
+            const int cyb = (sr0 >> 1) - 1;
             const int xt = x0 & ~15, xc = NV12 ? ((x0 - 2) & ~15) : (((x0 >> 1) - 1) & ~15);
             const int cw = W >> 1;
             if (xt < 0 || xt + kLumaBox > W || xc < 0 || (NV12 ? xc + kNv12Box > W : xc + kPlanarBox > cw)) {
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                 const int sub = tid & 7;
                 {   // luma: tile byte b <-> pixel xt + b; valid bytes [bl, br)
                     const int bl = min(max(0, -xt), kLumaBox - 1), br = min(max(W - xt, 1), kLumaBox);
-                    for (int row = tid >> 3; row < cur.nrows; row += 32) {
+                    for (int row = tid >> 3; row < cur.nrows * BX; row += 32) {
                         unsigned char *lr = st + row * kLumaBox;
                         const unsigned char vl = lr[bl], vr = lr[br - 1];
                         for (int j = sub; j < bl; j += 8) lr[j] = vl;
@@ -272,13 +277,20 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
             const int dl = x0 - xt, dc = (NV12 ? x0 - 2 : (x0 >> 1) - 1) - xc;
             const uint32_t l_off = (uint32_t)((dl & ~3) + lane * 8), l_sh = (uint32_t)(dl & 3) * 8u;
             const uint32_t c_off = (uint32_t)((dc & ~3) + lane * (NV12 ? 8 : 4)), c_sh = (uint32_t)(dc & 3) * 8u;
-            // ---- phase A: one source row per warp step ------------------------------------------------------------
-            for (int r = cur.r0 + warp; r < cur.r0 + cur.nrows; r += kWarps) {
+            // ---- phase A: one (reduced) row per warp step ---------------------------------------------------------
+            for (int R = cur.r0 + warp; R < cur.r0 + cur.nrows; R += kWarps) {
+                float2 prg[P];   // (r, g) of pixel i of the row handed to the horizontal pass (BOX: the first P / 2)
+                float pb[P];     // b of pixel i
+                float2 hrg[P / 2];   // BOX: (t00 + t01) of the 2 x 2 block, kept while the block's second row is converted
+                float hb[P / 2];
+#pragma unroll
+                for (int k = 0; k < BX; k++) {
+                const int r = R * BX + k;   // source row
                 // raw bytes of this lane's 8 pixels: 12 bytes from a 4-byte aligned address; the half that is 8-byte aligned
                 // (warp-uniform) goes as one LDS.64 (lanes 8 bytes apart: conflict-free, an LDS.32 is 2-way)
                 uint32_t yw[2];
                 {
-                    const uint32_t la = sb + (uint32_t)((r - cur.r0) * kLumaBox) + l_off;
+                    const uint32_t la = sb + (uint32_t)((r - sr0) * kLumaBox) + l_off;
                     uint32_t w0, w1, w2;
                     if (l_off & 4u) { w0 = v5::lds32v(la); v5::lds64v(la + 4, w1, w2); }
                     else { v5::lds64v(la, w0, w1); w2 = v5::lds32v(la + 8); }
@@ -327,8 +339,8 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                     v[5] = 3u * (__byte_perm(uh1, vh1, 0x0501) & 0x00ff00ffu) + (__byte_perm(ul1, vl1, 0x0501) & 0x00ff00ffu);
                 }
                 // A1: K1/K2 -> u8 -> sRGB decode, two pixels per instruction
-                float2 prg[P];   // (r, g) of pixel i
-                float pb[P];     // b of pixel i
+                float2 crg[P];   // (r, g) of source pixel i of this row
+                float cb[P];     // b
 #pragma unroll
                 for (int p = 0; p < P / 2; p++) {
                     // 16 x chroma of the even / odd pixel of the pair (NC-6u with the .25 / .75 taps)
@@ -362,14 +374,52 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                     const float2 qr = v5::add2_after_mul(v5::mul2(rr, v5::splat(255.0f)), v5::splat(kMagicRound));
                     const float2 qg = v5::add2_after_mul(v5::mul2(gg, v5::splat(255.0f)), v5::splat(kMagicRound));
                     const float2 qb = v5::add2_after_mul(v5::mul2(bb, v5::splat(255.0f)), v5::splat(kMagicRound));
-                    prg[2 * p] = make_float2(v5::lds_tab((__float_as_uint(qr.x) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.x) << 7) + kaddr));
-                    prg[2 * p + 1] = make_float2(v5::lds_tab((__float_as_uint(qr.y) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.y) << 7) + kaddr));
-                    pb[2 * p] = v5::lds_tab((__float_as_uint(qb.x) << 7) + kaddr);
-                    pb[2 * p + 1] = v5::lds_tab((__float_as_uint(qb.y) << 7) + kaddr);
+                    crg[2 * p] = make_float2(v5::lds_tab((__float_as_uint(qr.x) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.x) << 7) + kaddr));
+                    crg[2 * p + 1] = make_float2(v5::lds_tab((__float_as_uint(qr.y) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.y) << 7) + kaddr));
+                    cb[2 * p] = v5::lds_tab((__float_as_uint(qb.x) << 7) + kaddr);
+                    cb[2 * p + 1] = v5::lds_tab((__float_as_uint(qb.y) << 7) + kaddr);
                 }
-                // park the decoded pixels in this warp's row buffer: pixel X0 + 8 lane + i at slot 9 lane + i
+                if (!BOX) {
 #pragma unroll
-                for (int i = 0; i < P; i++) rowbuf[lane * (P + 1) + i] = make_float4(prg[i].x, prg[i].y, pb[i], pb[i]);
+                    for (int i = 0; i < P; i++) { prg[i] = crg[i]; pb[i] = cb[i]; }
+                } else if (k == 0) {
+#pragma unroll
+                    for (int i = 0; i < P / 2; i++) { hrg[i] = v5::add2(crg[2 * i], crg[2 * i + 1]); hb[i] = cb[2 * i] + cb[2 * i + 1]; }
+                } else {
+                    // downsample.wgsl:28-41: sum in the order (0,0) (1,0) (0,1) (1,1), / 4, stored in the Rgba16Float reduced texture
+#pragma unroll
+                    for (int i = 0; i < P / 2; i++) {
+                        const float2 srg = v5::add2(v5::add2(hrg[i], crg[2 * i]), crg[2 * i + 1]);
+                        const float sb4 = (hb[i] + cb[2 * i]) + cb[2 * i + 1];
+                        prg[i] = __half22float2(__floats2half2_rn(srg.x * 0.25f, srg.y * 0.25f));
+                        pb[i] = __half2float(__float2half_rn(sb4 * 0.25f));
+                    }
+                }
+                }   // k: the source rows of R
+                // park the pixels in this warp's row buffer: pixel X0 + n at slot n + n / 8 (n = 8 lane + i, BOX: 4 lane + i)
+                if (!BOX) {
+#pragma unroll
+                    for (int i = 0; i < P; i++) rowbuf[lane * (P + 1) + i] = make_float4(prg[i].x, prg[i].y, pb[i], pb[i]);
+                } else {
+                    float4 *mine = rowbuf + 4 * lane + (lane >> 1);
+#pragma unroll
+                    for (int i = 0; i < P / 2; i++) mine[i] = make_float4(prg[i].x, prg[i].y, pb[i], pb[i]);
+                    // The Lanczos pass clamps its taps to the REDUCED texture: a pixel outside it is the nearest reduced pixel
+                    // (the replicate padding of the staged source tile stands for source pixels, not for their 2 x 2 means)
+                    const int RW = W / 2;
+                    if (cur.x0 < 0 || cur.x0 + 128 > RW) {
+                        __syncwarp();
+                        float4 fix[P / 2];
+#pragma unroll
+                        for (int i = 0; i < P / 2; i++) {
+                            const int n = min(max(cur.x0 + 4 * lane + i, 0), RW - 1) - cur.x0;
+                            fix[i] = rowbuf[n + (n >> 3)];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < P / 2; i++) mine[i] = fix[i];
+                    }
+                }
                 __syncwarp();
                 // A2: horizontal Lanczos, two adjacent output columns per lane.  The lane's weights live in registers for
                 // the whole piece: wq[j] = (weight of column 2 lane, weight of column 2 lane + 1 shifted by the distance of the
@@ -398,7 +448,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                     }
                     const float2 a0 = make_float2(r0, g0), a1 = make_float2(r1, g1), ab = v5::upk(abq);
                     // normalise, quantise to f16 (NC-5) and park the row in the ring: [row][lane][channel][column]
-                    float *dst = ring + (size_t)(r % K::RROWS) * (K::RROW_BYTES / 4) + lane * 6;
+                    float *dst = ring + (size_t)(R % K::RROWS) * (K::RROW_BYTES / 4) + lane * 6;
                     *reinterpret_cast<float2 *>(dst) = __half22float2(__floats2half2_rn(a0.x * inv0, a1.x * inv1));
                     *reinterpret_cast<float2 *>(dst + 2) = __half22float2(__floats2half2_rn(a0.y * inv0, a1.y * inv1));
                     *reinterpret_cast<float2 *>(dst + 4) = __half22float2(__floats2half2_rn(ab.x * inv0, ab.y * inv1));
@@ -451,7 +501,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                 float2 acc[3 * OUT / 2];
 #pragma unroll
                 for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = make_float2(0.f, 0.f);
-                if (fv >= 0 && fv + tv <= H) {
+                if (fv >= 0 && fv + tv <= HR) {
                     int slot = fv % K::RROWS;
 #pragma unroll
                     for (int t = 0; t < K::MAXT; t++) {
@@ -465,7 +515,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma0(cons
                 } else {
                     for (int t = 0; t < tv; t++) {   // tap rows clamped to the image (resample.wgsl)
                         const float wt = __shfl_sync(0xffffffffu, wl, t);
-                        const int row = min(max(fv + t, 0), H - 1);
+                        const int row = min(max(fv + t, 0), HR - 1);
                         const float *p = lbase + (row % K::RROWS) * ROWF;
 #pragma unroll
                         for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = v5::fma2(*reinterpret_cast<const float2 *>(p + 2 * k), v5::splat(wt), acc[k]);

@@ -210,6 +210,31 @@ def test_box_predecimation_above_4x():
     check(V(children=[stretch], background_color=BG), fr)
 
 
+@pytest.mark.parametrize("kind", ["nv12", "yuv420"])
+@pytest.mark.parametrize("geom", [(384, 216, 0.0, 0.0), (320, 180, 0.0, 0.0), (240, 135, 0.0, 0.0), (256, 144, 37.0, 21.0), (272, 153, 7.0, 13.0)])
+def test_box_reduced_source_in_the_fused_kernel(kind, geom):
+    """resampler.rs:56-67 + downsample.wgsl:28-41 with one box level on BOTH axes (ratios in (4, 8]): the any-ratio TMA
+    kernel reduces the source 2:1 on the fly (k_resample_tma0<.., BOX>): 5:1, 6:1, 8:1 (the last ratio with one level), 7.5:1
+    and the fractional 7.06:1.  Noise input, so that every tap matters; the image edges exercise the clamp of the REDUCED
+    texture.  Checked: bytes against the oracle, and that no generic pass ran."""
+    dw, dh, left, top = geom
+    w, h = 1920, 1080
+    mk = nv12_frame if kind == "nv12" else yuv_frame
+    fr = {"input_1": mk(harness.random_yuv420(700 + dw, w, h), w, h)}
+    layer = s.RescalerComponent(child=s.InputStreamComponent(input_id="input_1"),
+                                position=s.Position.Absolute(width=float(dw), height=float(dh), left=left, top=top))
+    r = TrackedRenderer()
+    r.register_input("input_1")
+    r.set_profiling(True)
+    scene = V(children=[layer], background_color=BG)
+    r.update_scene(OUTPUT_ID, RES, YUV, scene)
+    got, exp, _ = run_case(scene, fr, renderer=r)
+    assert_identical(got, exp, f"box {kind} {geom}")
+    kt = r.kernel_times()
+    assert kt["resample_fused"][1] >= 1, kt
+    assert kt["resample_box"][1] == 0 and kt["resample_first"][1] == 0 and kt["convert"][1] == 0, kt
+
+
 @pytest.mark.parametrize("pts", [0.25, 0.5, 0.9])
 def test_transition_fractional_geometry(pts):
     """transition.rs: mid-transition layouts have fractional position and size -> non-trivial resample
