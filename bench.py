@@ -86,7 +86,7 @@ def workload(name):
         scene = None   # per-rank scenes are built in main(): output k uses inputs (k + j) % 8, j < 4
         mode = s.RenderingMode.GpuOptimized
         desc = ("8 outputs/GPU of 4x(1920x1080 NV12)->1920x1080 NV12 Tiles 2x2 Lanczos3 2:1, inputs from a pool of 8 "
-                "replicated to every GPU by ncclBroadcast each tick")
+                "shared by every GPU over NVLink each tick (config.secondary.exchange: ncclBroadcast / copy-engine pull / read in place)")
     elif name == "passthrough":  # single_video_pass_through of the reference's benchmark suite
         W, H, n, iw, ih = 3840, 2160, 1, 3840, 2160
         scene = s.InputStreamComponent(input_id="input_1")
@@ -251,14 +251,25 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
-def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, nvar=2):
-    """BASELINE config 4 on the running process group: 8 outputs per GPU, every tick replicates the pool of 8 shared
-    1080p inputs from their ingest GPUs over NVLink (smr_comm_exchange_inputs) and composites 8 frames.  Returns the
-    device-timed aggregate frames/s (max over ranks) and the bytes the exchange moved per tick."""
+class _DevMem:
+    """a raw device range as a CUDA array (torch.as_tensor views it without copying)"""
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, exchange="nccl"):
+    """BASELINE config 4 on the running process group: 8 outputs per GPU; every tick the pool of 8 shared 1080p inputs,
+    ingested round-robin by the GPUs, has to reach every GPU.  exchange:
+      nccl         smr_comm_exchange_inputs: ncclBroadcast of the pooled planes on the communication stream
+      peer_copy    smr_comm_pull_inputs: copy-engine pulls out of the roots' IPC-mapped pools after a 4-byte all-reduce
+      peer_direct  nothing is copied: the fused resample kernel's TMA loads read the roots' pools over NVLink
+    Returns the device-timed aggregate frames/s (max over ranks) and the bytes that cross NVLink per tick."""
     import smelter_b200 as s
     from smelter_b200 import _ffi as F
     wl = workload("cfg4")
     n, iw, ih, W, H, n_out = wl["n"], wl["iw"], wl["ih"], wl["W"], wl["H"], wl["n_out"]
+    peer = exchange in ("peer_copy", "peer_direct") and world > 1
+    nvar = 3 if exchange == "peer_direct" else 2   # header: a directly read pool set may be rewritten three ticks later
     r = s.Renderer(s.RendererOptions(rendering_mode=wl["mode"], cuda_device=local))
     ids = [f"input_{i}".encode() for i in range(1, n + 1)]
     for b in ids:
@@ -272,29 +283,49 @@ def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, nvar=2):
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(uid[0], rank, world)
     order = sorted(range(n), key=lambda i: (roots[i], i))
-    frames, arrs = [], []
+    frames, arrs, peer_arrs, own_pools, opened = [], [], [], [], []
     for v in range(nvar):
         planes = [synth_planes_torch(torch, dev, iw, ih, 0x5EED4000 + 1000 * v + i + 97 * rank) for i in range(n)]
-        pool = torch.empty(sum(t.numel() for i in order for t in planes[i]), dtype=torch.uint8, device=dev)
-        off, packed = 0, {}
+        nbytes = sum(t.numel() for i in order for t in planes[i])
+        if peer:   # one pool per GPU, mappable by the other GPUs' handles; identical layout everywhere
+            base, handle = r.peer_pool_alloc(nbytes)
+            own_pools.append(base)
+            pool = torch.as_tensor(_DevMem(base, nbytes), device=dev)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            bases = [base if k == rank else r.peer_pool_open(handles[k]) for k in range(world)]
+            opened += [b for k, b in enumerate(bases) if k != rank]
+        else:
+            pool = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            base, bases = pool.data_ptr(), None
+        off, packed, offs = 0, {}, {}
         for i in order:   # one pool per ingest GPU, identical layout on every rank (SMR_COMM_POOLED)
             views = []
+            offs[i] = []
             for t in planes[i]:
                 view = pool[off:off + t.numel()].view(t.shape)
                 view.copy_(t)
                 views.append(view)
+                offs[i].append(off)
                 off += t.numel()
             packed[i] = tuple(views)
         frames.append((pool, packed))
-        arr = (F.InputFrame * n)()
-        for k, i in enumerate(order):
-            yv, uvv = packed[i]
-            arr[k].input_id = ids[i]
-            arr[k].format = F.FRAME_NV12
-            arr[k].width, arr[k].height = iw, ih
-            arr[k].mem_kind = F.MEM_DEVICE
-            arr[k].planes[0], arr[k].planes[1] = yv.data_ptr(), uvv.data_ptr()
-        arrs.append(arr)
+
+        def frame_array(base_of):
+            arr = (F.InputFrame * n)()
+            for k, i in enumerate(order):
+                arr[k].input_id = ids[i]
+                arr[k].format = F.FRAME_NV12
+                arr[k].width, arr[k].height = iw, ih
+                arr[k].mem_kind = F.MEM_DEVICE
+                arr[k].planes[0], arr[k].planes[1] = base_of(i) + offs[i][0], base_of(i) + offs[i][1]
+            return arr
+        if exchange == "peer_direct" and world > 1:
+            arrs.append(frame_array(lambda i: bases[roots[i]]))     # read in place: the root's pool
+            peer_arrs.append(None)
+        else:
+            arrs.append(frame_array(lambda i: base))
+            peer_arrs.append(frame_array(lambda i: bases[roots[i]]) if peer else None)
     comm_roots = [roots[i] for i in order]
     out_y = [torch.empty((H, W), dtype=torch.uint8, device=dev) for _ in range(n_out)]
     out_uv = [torch.empty((H // 2, W // 2, 2), dtype=torch.uint8, device=dev) for _ in range(n_out)]
@@ -305,13 +336,19 @@ def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, nvar=2):
         dev_out[k].planes[0], dev_out[k].planes[1] = out_y[k].data_ptr(), out_uv[k].data_ptr()
     stream = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
     frame_ns = 33_333_333
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
 
     def step(k):
         a = arrs[k % nvar]
         for f in a:
             f.pts_ns = k * frame_ns
         if world > 1:
-            r.comm_exchange_inputs(a, n, comm_roots, None, pooled=True)
+            if exchange == "peer_copy":
+                r.comm_pull_inputs(a, peer_arrs[k % nvar], n, comm_roots)
+            else:
+                r.comm_exchange_inputs(a, n, comm_roots, None, pooled=True, peer_direct=exchange == "peer_direct")
         r.render_raw(k * frame_ns, a, n, dev_out, n_out, wait=False)
 
     for k in range(warmup):
@@ -328,16 +365,42 @@ def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, nvar=2):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    step(nvar * 100000)   # one more tick on frame set 0: its outputs must not depend on how the inputs travelled
+    r.wait()
+    torch.cuda.synchronize()
+    digest = int(sum(int(t.to(torch.int64).sum().item()) * (j + 1) for j, t in enumerate(out_y + out_uv)))
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        dist.barrier()    # nobody unmaps a pool another rank may still be reading
     if world > 1:
+        for b in opened:
+            r.peer_pool_close(b)
+        if dist is not None:
+            dist.barrier()
+        for b in own_pools:
+            r.peer_pool_free(b)
         r.comm_destroy()
-    moved = sum(iw * ih * 3 // 2 for i in range(n)) * (world - 1) if world > 1 else 0   # every input reaches the other N-1 GPUs
-    return {"workload": "cfg4", "detail": wl["desc"], "value": world * n_out * steps / (ms * 1e-3), "unit": "frames/s",
+    moved = sum(iw * ih * 3 // 2 for i in range(n) if True) * (world - 1) if world > 1 else 0   # every input reaches the other N-1 GPUs
+    return {"workload": "cfg4", "detail": wl["desc"], "exchange": exchange if world > 1 else "none",
+            "value": world * n_out * steps / (ms * 1e-3), "unit": "frames/s",
             "ms_per_tick": ms / steps, "steps": steps, "outputs_per_gpu": n_out,
-            "nvlink_broadcast_bytes_per_tick": moved, "scaling": "weak"}
+            "nvlink_broadcast_bytes_per_tick": moved, "scaling": "weak", "output_digest_rank": digest}
+
+
+def measure_cfg4_modes(torch, dist, dev, rank, world, local, steps, warmup, modes):
+    """the cfg4 leg under every requested exchange; the line carries the fastest, the others ride along"""
+    res = {m: measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, exchange=m) for m in modes}
+    digests = {m: res[m].pop("output_digest_rank") for m in modes}
+    best = max(modes, key=lambda m: res[m]["value"])
+    out = dict(res[best])
+    out["modes"] = {m: {"value": res[m]["value"], "ms_per_tick": res[m]["ms_per_tick"]} for m in modes}
+    same = torch.tensor([1 if len(set(digests.values())) == 1 else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)   # on every rank
+    out["same_frames_in_every_mode"] = bool(same.item())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,6 +415,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the cfg4 (NVLink exchange) leg")
+    ap.add_argument("--exchange", default="all", choices=["all", "nccl", "peer_copy", "peer_direct"],
+                    help="N > 1, cfg4 leg: how the shared inputs reach the other GPUs (all: measure each, report the fastest)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = workload(args.workload)
@@ -622,7 +687,8 @@ def main():
 
     secondary = None
     if world > 1 and wl["name"] == "cfg3" and not args.no_secondary:
-        secondary = measure_cfg4(torch, dist, dev, rank, world, local, max(args.steps, 20), args.warmup)
+        modes = ["nccl", "peer_copy", "peer_direct"] if args.exchange == "all" else [args.exchange]
+        secondary = measure_cfg4_modes(torch, dist, dev, rank, world, local, max(args.steps, 20), args.warmup, modes)
     if rank == 0:
         line = {"metric": metric_name(wl),
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

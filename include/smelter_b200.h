@@ -313,6 +313,25 @@ smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *fra
                                      const int32_t *root_ranks);
 smr_status smr_comm_exchange_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks,
                                     const uint64_t *consumer_masks, uint32_t flags);
+/* Peer memory over NVLink / NVSwitch (one process per GPU, one node).  A frame pool allocated with smr_peer_pool_alloc can
+ * be mapped by the handles of the other GPUs: pass the 64-byte CUDA IPC handle over the host transport and open it there.
+ * A pointer into an opened pool is an ordinary SMR_MEM_DEVICE plane pointer for smr_render: the kernels read it over
+ * NVLink (the fused resample kernel by TMA tile loads -- the transfer overlaps the arithmetic tile by tile, nothing is
+ * staged in local HBM).  Two ways to use it for the shared inputs of a tick:
+ *   SMR_COMM_PEER_DIRECT (flag of smr_comm_exchange_inputs): no data moves; the call is only the cross-rank ordering (a
+ *     4-byte all-reduce on the communication stream).  The caller passes, in smr_render, plane pointers into the ROOT's
+ *     pool for frames rooted elsewhere.  A pool set may be rewritten three ticks later at the earliest (three sets).
+ *   smr_comm_pull_inputs: after the same ordering step, frames rooted elsewhere are copied from peer_frames[i] (planes in
+ *     the root's opened pool) to frames[i] (local planes) by the copy engines -- no SM time, unlike the NCCL kernels of
+ *     smr_comm_exchange_inputs.  Two sets suffice.
+ * The reference has no counterpart (single device). */
+#define SMR_COMM_PEER_DIRECT 2u
+smr_status smr_peer_pool_alloc(smr_renderer *r, size_t bytes, void **dev_ptr, uint8_t handle[64]);
+smr_status smr_peer_pool_open(smr_renderer *r, const uint8_t handle[64], void **dev_ptr);
+smr_status smr_peer_pool_close(smr_renderer *r, void *dev_ptr);
+smr_status smr_peer_pool_free(smr_renderer *r, void *dev_ptr);
+smr_status smr_comm_pull_inputs(smr_renderer *r, const smr_input_frame *frames, const smr_input_frame *peer_frames, uint32_t n,
+                                const int32_t *root_ranks, const uint64_t *consumer_masks);
 smr_status smr_comm_destroy(smr_renderer *r);
 
 /* Texture upload / read-back glue of smelter-core (pipeline/decoder/ffmpeg_utils.rs:67-79 copy_plane_from_av,

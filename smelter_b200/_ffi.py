@@ -118,7 +118,7 @@ EXPORTS = [
     "smr_create", "smr_destroy", "smr_register_input", "smr_unregister_input", "smr_update_scene",
     "smr_unregister_output", "smr_set_layouts", "smr_render", "smr_render_begin", "smr_render_end", "smr_preprocess_frame", "smr_premultiply_rgba8", "smr_debug_partition", "smr_output_plane_sizes",
     "smr_component_default", "smr_debug_layouts", "smr_debug_set_inputs", "smr_get_stats", "smr_set_profiling", "smr_get_kernel_times",
-    "smr_comm_get_unique_id", "smr_comm_init", "smr_comm_broadcast_inputs", "smr_comm_exchange_inputs", "smr_comm_destroy", "smr_host_register", "smr_host_unregister", "smr_cuda_stream", "smr_last_error",
+    "smr_comm_get_unique_id", "smr_comm_init", "smr_comm_broadcast_inputs", "smr_comm_exchange_inputs", "smr_comm_pull_inputs", "smr_peer_pool_alloc", "smr_peer_pool_open", "smr_peer_pool_close", "smr_peer_pool_free", "smr_comm_destroy", "smr_host_register", "smr_host_unregister", "smr_cuda_stream", "smr_last_error",
     "smr_version",
 ]
 
@@ -169,6 +169,12 @@ def lib():
     L.smr_host_unregister.argtypes = [C.c_void_p]
     L.smr_comm_exchange_inputs.argtypes = [vp, C.POINTER(InputFrame), C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                            C.c_uint32]
+    L.smr_comm_pull_inputs.argtypes = [vp, C.POINTER(InputFrame), C.POINTER(InputFrame), C.c_uint32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_uint64)]
+    L.smr_peer_pool_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint8 * 64)]
+    L.smr_peer_pool_open.argtypes = [vp, C.POINTER(C.c_uint8 * 64), C.POINTER(C.c_void_p)]
+    L.smr_peer_pool_close.argtypes = [vp, C.c_void_p]
+    L.smr_peer_pool_free.argtypes = [vp, C.c_void_p]
     L.smr_comm_destroy.argtypes = [vp]
     L.smr_set_profiling.argtypes = [vp, C.c_int32]
     L.smr_get_kernel_times.argtypes = [vp, C.POINTER(KernelTimes)]

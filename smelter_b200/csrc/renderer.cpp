@@ -177,6 +177,7 @@ static struct {
     int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -195,11 +196,12 @@ static bool nccl_load(std::string &err) {
     g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclBroadcast");
     g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclSend");
     g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
     g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.Broadcast || !g_nccl.GroupStart ||
-        !g_nccl.GroupEnd || !g_nccl.Send || !g_nccl.Recv) { err = "libnccl lacks required symbols"; return false; }
+        !g_nccl.GroupEnd || !g_nccl.Send || !g_nccl.Recv || !g_nccl.AllReduce) { err = "libnccl lacks required symbols"; return false; }
     g_nccl.lib = h;
     return true;
 }
@@ -409,11 +411,20 @@ class Renderer {
     // NCCL communicator for shared-input replication; libnccl is dlopen'ed on first use
     void *nccl_comm_ = nullptr;
     int comm_rank_ = 0, comm_size_ = 1;
+    int32_t *barrier_word_ = nullptr;            // 4 device bytes the per-tick all-reduce of the peer modes runs on
+    std::vector<void *> peer_own_, peer_opened_; // pools of smr_peer_pool_alloc / smr_peer_pool_open still alive
   public:
     smr_status comm_init(const uint8_t *id, int rank, int nranks);
     smr_status comm_exchange(const smr_input_frame *frames, uint32_t n, const int32_t *roots, const uint64_t *consumers,
                              uint32_t flags);
     smr_status comm_destroy();
+    smr_status comm_pull(const smr_input_frame *frames, const smr_input_frame *peer_frames, uint32_t n, const int32_t *roots,
+                         const uint64_t *consumers);
+    smr_status comm_tick_barrier();   // caller holds mu_
+    smr_status peer_pool_alloc(size_t bytes, void **dev_ptr, uint8_t handle[64]);
+    smr_status peer_pool_open(const uint8_t handle[64], void **dev_ptr);
+    smr_status peer_pool_close(void *dev_ptr);
+    smr_status peer_pool_free(void *dev_ptr);
     smr_status set_profiling(int enabled);
     void kernel_times(smr_kernel_times *out) { std::lock_guard<std::mutex> g(mu_); *out = prof_; }
 };
@@ -434,6 +445,9 @@ Renderer::~Renderer() {
             cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
         }
         for (auto &kv : lane_perms_) cudaFree(kv.second);
+        for (void *p : peer_opened_) cudaIpcCloseMemHandle(p);
+        for (void *p : peer_own_) cudaFree(p);
+        if (barrier_word_) cudaFree(barrier_word_);
         cudaStreamDestroy(stream_);
     }
 }
@@ -1771,6 +1785,15 @@ smr_status Renderer::comm_exchange(const smr_input_frame *frames, uint32_t n, co
     // Runs on its own stream so that it overlaps the kernels of the tick submitted last; it is ordered after every
     // EARLIER tick (whose buffers the caller may be recycling) and before the next smr_render_begin.
     if (tick_started_) CUDA_OK(cudaStreamWaitEvent(comm_stream_, tick_start_, 0));
+    if (flags & SMR_COMM_PEER_DIRECT) {
+        // nothing moves: the frames rooted elsewhere are read in place over NVLink by the tick's kernels (the TMA loads of the
+        // fused resample kernel); the step is the cross-rank ordering alone
+        smr_status st = comm_tick_barrier();
+        if (st != SMR_OK) return st;
+        CUDA_OK(cudaEventRecord(comm_done_, comm_stream_));
+        comm_pending_ = true;
+        return SMR_OK;
+    }
     const uint64_t all = comm_size_ >= 64 ? ~0ull : ((1ull << comm_size_) - 1ull);
     // SMR_COMM_POOLED: the caller declares that the planes are laid out identically on every rank (e.g. one frame pool
     // per ingest GPU), so consecutive planes with the same root and consumers that are contiguous HERE are contiguous
@@ -1815,6 +1838,113 @@ smr_status Renderer::comm_exchange(const smr_input_frame *frames, uint32_t n, co
     if (rc != 0) { set_error(std::string("NCCL exchange: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
     CUDA_OK(cudaEventRecord(comm_done_, comm_stream_));
     comm_pending_ = true;
+    return SMR_OK;
+}
+
+// A 4-byte all-reduce on the communication stream: when it completes here, every rank's communication stream has reached
+// the same tick, i.e. every rank has finished the ticks before its last submitted one and has its frames of this tick in
+// place.  The only cross-GPU traffic of SMR_COMM_PEER_DIRECT besides the tile loads themselves.
+smr_status Renderer::comm_tick_barrier() {
+    if (!barrier_word_) {
+        CUDA_OK(cudaMalloc(&barrier_word_, 256));
+        CUDA_OK(cudaMemsetAsync(barrier_word_, 0, 256, comm_stream_));
+    }
+    int rc = g_nccl.AllReduce(barrier_word_, barrier_word_, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, nccl_comm_, comm_stream_);
+    if (rc != 0) { set_error(std::string("NCCL barrier: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SMR_ERR_CUDA; }
+    return SMR_OK;
+}
+
+// Pull form of the exchange: after the tick barrier each consumer copies the frames rooted elsewhere out of the root's pool
+// (opened with smr_peer_pool_open) with the copy engines -- cudaMemcpyAsync over NVLink, no SM is spent on the transfer.
+smr_status Renderer::comm_pull(const smr_input_frame *frames, const smr_input_frame *peer_frames, uint32_t n, const int32_t *roots,
+                               const uint64_t *consumers) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!nccl_comm_) { set_error("smr_comm_init was not called"); return SMR_ERR_INVALID_ARGUMENT; }
+    if (n && (!frames || !peer_frames || !roots)) return SMR_ERR_INVALID_ARGUMENT;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    if (tick_started_) CUDA_OK(cudaStreamWaitEvent(comm_stream_, tick_start_, 0));
+    smr_status st = comm_tick_barrier();
+    if (st != SMR_OK) return st;
+    struct Run { uint8_t *dst; const uint8_t *src; size_t bytes; };
+    std::vector<Run> runs;
+    for (uint32_t i = 0; i < n; i++) {
+        const smr_input_frame &f = frames[i], &pf = peer_frames[i];
+        if (roots[i] < 0 || roots[i] >= comm_size_) return SMR_ERR_INVALID_ARGUMENT;
+        if (roots[i] == comm_rank_) continue;
+        if (consumers && !((consumers[i] >> comm_rank_) & 1ull)) continue;
+        if (f.mem_kind != SMR_MEM_DEVICE || pf.mem_kind != SMR_MEM_DEVICE) { set_error("the exchange needs device-resident planes"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (pf.format != f.format || pf.width != f.width || pf.height != f.height) { set_error("peer frame geometry differs"); return SMR_ERR_INVALID_ARGUMENT; }
+        for (int p = 0; p < 3; p++) {
+            size_t row_bytes = 0, rows = 0;
+            if (!plane_layout(f.format, f.width, f.height, p, row_bytes, rows)) continue;
+            if (!f.planes[p] || !pf.planes[p]) { set_error("input plane pointer is null"); return SMR_ERR_INVALID_ARGUMENT; }
+            const size_t pitch = f.pitch[p] ? f.pitch[p] : row_bytes, ppitch = pf.pitch[p] ? pf.pitch[p] : row_bytes;
+            if (pitch != ppitch || pitch < row_bytes) { set_error("peer frame pitch differs"); return SMR_ERR_INVALID_ARGUMENT; }
+            const size_t bytes = pitch * (rows - 1) + row_bytes;
+            uint8_t *d = (uint8_t *)f.planes[p];
+            const uint8_t *sp = (const uint8_t *)pf.planes[p];
+            if (!runs.empty() && runs.back().dst + runs.back().bytes == d && runs.back().src + runs.back().bytes == sp) runs.back().bytes += bytes;
+            else runs.push_back({d, sp, bytes});
+        }
+    }
+    for (const Run &R : runs) CUDA_OK(cudaMemcpyAsync(R.dst, R.src, R.bytes, cudaMemcpyDeviceToDevice, comm_stream_));
+    CUDA_OK(cudaEventRecord(comm_done_, comm_stream_));
+    comm_pending_ = true;
+    return SMR_OK;
+}
+
+smr_status Renderer::peer_pool_alloc(size_t bytes, void **dev_ptr, uint8_t handle[64]) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!dev_ptr || !handle || !bytes) return SMR_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size of the C ABI");
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));   // its own allocation: an IPC handle names a whole cudaMalloc block
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); set_error("cudaIpcGetMemHandle failed"); return SMR_ERR_CUDA; }
+    memcpy(handle, &h, 64);
+    peer_own_.push_back(p);
+    *dev_ptr = p;
+    return SMR_OK;
+}
+
+smr_status Renderer::peer_pool_open(const uint8_t handle[64], void **dev_ptr) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!dev_ptr || !handle) return SMR_ERR_INVALID_ARGUMENT;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return SMR_ERR_CUDA; }
+    peer_opened_.push_back(p);
+    *dev_ptr = p;
+    return SMR_OK;
+}
+
+smr_status Renderer::peer_pool_close(void *dev_ptr) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = std::find(peer_opened_.begin(), peer_opened_.end(), dev_ptr);
+    if (it == peer_opened_.end()) return SMR_ERR_INVALID_ARGUMENT;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    cudaStreamSynchronize(stream_);
+    if (comm_stream_) cudaStreamSynchronize(comm_stream_);
+    tmap_cache_.clear();   // descriptors of planes inside the mapping
+    cudaIpcCloseMemHandle(dev_ptr);
+    peer_opened_.erase(it);
+    return SMR_OK;
+}
+
+smr_status Renderer::peer_pool_free(void *dev_ptr) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = std::find(peer_own_.begin(), peer_own_.end(), dev_ptr);
+    if (it == peer_own_.end()) return SMR_ERR_INVALID_ARGUMENT;
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    cudaStreamSynchronize(stream_);
+    if (comm_stream_) cudaStreamSynchronize(comm_stream_);
+    tmap_cache_.clear();
+    cudaFree(dev_ptr);
+    peer_own_.erase(it);
     return SMR_OK;
 }
 
@@ -1981,6 +2111,12 @@ smr_status smr_comm_init(smr_renderer *r, const uint8_t id[128], int32_t rank, i
 smr_status smr_comm_broadcast_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks) { SMR_GUARD(r->impl.comm_exchange(frames, n, root_ranks, nullptr, 0)) }
 smr_status smr_comm_exchange_inputs(smr_renderer *r, const smr_input_frame *frames, uint32_t n, const int32_t *root_ranks,
                                     const uint64_t *consumer_masks, uint32_t flags) { SMR_GUARD(r->impl.comm_exchange(frames, n, root_ranks, consumer_masks, flags)) }
+smr_status smr_comm_pull_inputs(smr_renderer *r, const smr_input_frame *frames, const smr_input_frame *peer_frames, uint32_t n,
+                                const int32_t *root_ranks, const uint64_t *consumer_masks) { SMR_GUARD(r->impl.comm_pull(frames, peer_frames, n, root_ranks, consumer_masks)) }
+smr_status smr_peer_pool_alloc(smr_renderer *r, size_t bytes, void **dev_ptr, uint8_t handle[64]) { SMR_GUARD(r->impl.peer_pool_alloc(bytes, dev_ptr, handle)) }
+smr_status smr_peer_pool_open(smr_renderer *r, const uint8_t handle[64], void **dev_ptr) { SMR_GUARD(r->impl.peer_pool_open(handle, dev_ptr)) }
+smr_status smr_peer_pool_close(smr_renderer *r, void *dev_ptr) { SMR_GUARD(r->impl.peer_pool_close(dev_ptr)) }
+smr_status smr_peer_pool_free(smr_renderer *r, void *dev_ptr) { SMR_GUARD(r->impl.peer_pool_free(dev_ptr)) }
 smr_status smr_comm_destroy(smr_renderer *r) { SMR_GUARD(r->impl.comm_destroy()) }
 smr_status smr_set_profiling(smr_renderer *r, int32_t enabled) { SMR_GUARD(r->impl.set_profiling(enabled)) }
 smr_status smr_get_kernel_times(smr_renderer *r, smr_kernel_times *out) {

@@ -621,12 +621,42 @@ class Renderer:
 
     COMM_POOLED = 1
 
-    def comm_exchange_inputs(self, in_arr, n, roots, consumer_masks=None, pooled=False):
+    COMM_PEER_DIRECT = 2
+
+    def comm_exchange_inputs(self, in_arr, n, roots, consumer_masks=None, pooled=False, peer_direct=False):
         """selective replication: frame i goes from rank roots[i] to the ranks whose bit is set in consumer_masks[i]
-        (None: to every rank); pooled=True declares an identical plane layout on every rank (contiguous runs merge)"""
+        (None: to every rank); pooled=True declares an identical plane layout on every rank (contiguous runs merge);
+        peer_direct=True moves nothing (the tick's kernels read the roots' pools over NVLink): ordering step only"""
         arr = (C.c_int32 * max(1, n))(*roots)
         masks = None if consumer_masks is None else (C.c_uint64 * max(1, n))(*consumer_masks)
-        self._check(self._lib.smr_comm_exchange_inputs(self._h, in_arr, n, arr, masks, self.COMM_POOLED if pooled else 0))
+        flags = (self.COMM_POOLED if pooled else 0) | (self.COMM_PEER_DIRECT if peer_direct else 0)
+        self._check(self._lib.smr_comm_exchange_inputs(self._h, in_arr, n, arr, masks, flags))
+
+    def comm_pull_inputs(self, in_arr, peer_arr, n, roots, consumer_masks=None):
+        """copy-engine form: frames rooted elsewhere are copied from peer_arr[i] (planes in the root's opened pool)
+        to in_arr[i] (local planes) after the cross-rank ordering step"""
+        arr = (C.c_int32 * max(1, n))(*roots)
+        masks = None if consumer_masks is None else (C.c_uint64 * max(1, n))(*consumer_masks)
+        self._check(self._lib.smr_comm_pull_inputs(self._h, in_arr, peer_arr, n, arr, masks))
+
+    def peer_pool_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a frame pool other GPUs' handles can open"""
+        ptr = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        self._check(self._lib.smr_peer_pool_alloc(self._h, nbytes, C.byref(ptr), C.byref(h)))
+        return ptr.value, bytes(h)
+
+    def peer_pool_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        ptr = C.c_void_p()
+        self._check(self._lib.smr_peer_pool_open(self._h, C.byref(h), C.byref(ptr)))
+        return ptr.value
+
+    def peer_pool_close(self, ptr: int):
+        self._check(self._lib.smr_peer_pool_close(self._h, ptr))
+
+    def peer_pool_free(self, ptr: int):
+        self._check(self._lib.smr_peer_pool_free(self._h, ptr))
 
     def comm_destroy(self):
         self._check(self._lib.smr_comm_destroy(self._h))
