@@ -122,14 +122,18 @@ def synth_planes_torch(torch, dev, w, h, seed):
     return plane(w, h, 16, 235, 1), plane(w // 2, h // 2, 16, 240, 2)
 
 
+SETUP_SECONDS = 0.3   # untimed set-up ticks before the W warm-up steps (clock ramp, tables, descriptors)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        indices = list(indices)
+        self.index, self.rows, self.proc, self.n = ",".join(str(i) for i in indices), [], None, len(indices)
 
     def start(self):
         try:
@@ -152,19 +156,25 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         i1 = len(self.rows)
-        i0 = min(getattr(self, "i0", 0), max(i1 - 1, 0))   # a region shorter than one sampling period: the latest row
-        self.rows = self.rows[i0:i1] if i1 > i0 else self.rows[-1:]
+        i0 = min(getattr(self, "i0", 0), max(i1 - self.n, 0))   # a region shorter than one sampling period: the latest row per GPU
+        self.rows = self.rows[i0:i1] if i1 > i0 else self.rows[-self.n:]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        ok = [r for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        per_gpu = {}
+        for r in ok:
+            per_gpu.setdefault(r[0], []).append(float(r[1]))
+        med = {g: float(np.median(v)) for g, v in per_gpu.items()}
+        mx = [float(r[2]) for r in ok if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in ok for n, v in zip(names, r[5:9]) if v == "Active"})
+        # every GPU of the job is sampled; the reported clock is the slowest GPU's median under load
+        return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": min((len(v) for v in per_gpu.values()), default=0),
+                "per_gpu_sm_mhz": [med[g] for g in sorted(med, key=int)] if len(med) > 1 else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -351,8 +361,11 @@ def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, exchange="
                 r.comm_exchange_inputs(a, n, comm_roots, None, pooled=True, peer_direct=exchange == "peer_direct")
         r.render_raw(k * frame_ns, a, n, dev_out, n_out, wait=False)
 
-    for k in range(warmup):
+    setup = 200   # a fixed count (the exchange is collective): tables, descriptors, arenas, load clocks -- then the W warm-up steps
+    for k in range(setup + warmup):
         step(k)
+        if k % 16 == 15:
+            r.wait()
     r.wait()
     if dist is not None:
         dist.barrier()
@@ -360,7 +373,7 @@ def measure_cfg4(torch, dist, dev, rank, world, local, steps, warmup, exchange="
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(steps):
-        step(warmup + k)
+        step(setup + warmup + k)
     r.wait()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -437,7 +450,7 @@ def main():
     dev = torch.device("cuda", local)
     # nvidia-smi needs a few hundred ms before its first row: started now, it is streaming by the time the timed region
     # begins (rank 0 only -- its line is the one that is printed)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(range(world) if world > 1 else [local])
     if int(os.environ.get("RANK", "0")) == 0:
         clocks.start()
     dist = None
@@ -536,8 +549,13 @@ def main():
     # one that is printed, and N concurrent nvidia-smi loops would only contend for the driver lock
     # set-up, not warm-up: the first ticks of a handle compute the Lanczos weight tables, encode the TMA descriptors of
     # every frame buffer, size the arenas and take the clocks out of idle; the W warm-up steps follow
-    for k in range(-8, 0):
-        step_dev(k % nvar)
+    t_setup = time.perf_counter()
+    k = 0
+    while k < 8 or time.perf_counter() - t_setup < SETUP_SECONDS:   # every GPU of the job reaches its load clocks (a rank whose
+        step_dev(k % nvar)                                           # GPU ramps late would set the max over ranks)
+        k += 1
+        if k % 16 == 0:
+            r.wait()
     r.wait()
     for k in range(args.warmup):
         step_dev(k)
