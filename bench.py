@@ -650,7 +650,7 @@ def main():
             for a in host_in[k % hv]:
                 a.pts_ns = k * frame_ns          # fresh frames every tick (a frame older than the fallback timeout is dropped)
             r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=wait)
-        for k in range(3):
+        for k in range(max(args.warmup, 8)):   # every in-flight slot (SMR_TICKS_IN_FLIGHT = 4) has its staging buffers allocated
             step_host(k, True)
         barrier()
         st0 = r.stats()

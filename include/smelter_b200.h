@@ -233,10 +233,13 @@ smr_status smr_unregister_output(smr_renderer *r, const char *output_id);
 smr_status smr_render(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
                       smr_output_frame *outputs, uint32_t n_outputs);
 
-/* The same with the waits split off, so a caller can overlap ticks (at most two in flight):
+/* The same with the waits split off, so a caller can overlap ticks (at most SMR_TICKS_IN_FLIGHT in flight; one more
+ * smr_render_begin first waits for the oldest and retires it):
  * smr_render_begin enqueues uploads + kernels + downloads and returns; smr_render_end retires the OLDEST tick in
- * flight.  Host planes of a tick belong to the library from its smr_render_begin until the smr_render_end that
+ * flight.  The ticks execute in submission order on one stream; running the host a few ticks ahead keeps the GPU fed
+ * across host-side hiccups (the ticks of the benchmark configurations last 0.25 - 0.5 ms).  Host planes of a tick belong to the library from its smr_render_begin until the smr_render_end that
  * retires it.  A plane's pitch must be >= its row bytes (SMR_ERR_INVALID_ARGUMENT otherwise). */
+#define SMR_TICKS_IN_FLIGHT 4
 smr_status smr_render_begin(smr_renderer *r, uint64_t pts_ns, const smr_input_frame *inputs, uint32_t n_inputs,
                             smr_output_frame *outputs, uint32_t n_outputs);
 smr_status smr_render_end(smr_renderer *r);

@@ -46,6 +46,11 @@ static const float kPiF = 3.14159265359f;
 // ------------------------------------------------------------------------------------------------
 // resampler planning (transformations/layout/resampler.rs:43-145)
 // ------------------------------------------------------------------------------------------------
+// Ticks the host may have submitted ahead of the GPU (smr_render_begin without smr_render_end): each owns a parameter
+// block, an input staging set and its events.  Four absorb a host hiccup of some milliseconds at the 0.25-0.5 ms ticks of
+// the benchmark configurations; the kernels of all of them run in submission order on one stream.
+constexpr int kTicksInFlight = SMR_TICKS_IN_FLIGHT;
+
 struct AxisMapping {
     int axis;  // 0 horizontal, 1 vertical
     float crop_offset, crop_len;
@@ -270,7 +275,7 @@ class Renderer {
     struct Input {
         bool has_frame = false;
         dev::Tex tex;           // planes as they sit in HBM
-        DevBuf planes[2][3];    // owned copies of host frames, double-buffered by tick parity
+        DevBuf planes[kTicksInFlight][3];    // owned copies of host frames, one set per tick in flight
         Resolution res;
         int node_tex = -1;      // index in the tick's texture table of the materialised RGBA8 node texture
         int raw_tex = -1;       // index of the virtual (fused K1/K2) texture
@@ -371,16 +376,16 @@ class Renderer {
 
     std::vector<uint8_t> param_host_;  // built here, copied to pinned, then to device
     size_t param_used_ = 0;
-    PinnedBuf param_pinned_[2];   // double-buffered by tick parity: tick n+1 is prepared and uploaded
-    DevBuf param_dev_[2];         // while tick n is still executing
+    PinnedBuf param_pinned_[kTicksInFlight];   // one per tick in flight: tick n+1 .. n+3 are prepared and uploaded
+    DevBuf param_dev_[kTicksInFlight];         // while tick n is still executing
     size_t frame_used_ = 0;
     DevBuf frame_dev_;
     std::map<WeightKey, WeightEntry> weights_;
     // up to two ticks in flight: uploads of tick n+1 (copy stream) overlap the kernels of tick n
     cudaStream_t copy_stream_ = nullptr, copy_stream2_ = nullptr;   // uploads alternate between two streams (two DMA engines)
-    cudaEvent_t h2d_done2_[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done2_[kTicksInFlight] = {};
     int upload_rr_ = 0;
-    cudaEvent_t h2d_done_[2] = {nullptr, nullptr}, tick_done_[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done_[kTicksInFlight] = {}, tick_done_[kTicksInFlight] = {};
     // the tick's exchange step overlaps the previous tick's kernels: NCCL runs on its own stream, ordered after
     // everything submitted BEFORE the most recent tick and before the next one
     cudaStream_t comm_stream_ = nullptr;
@@ -435,11 +440,11 @@ Renderer::~Renderer() {
         cudaStreamSynchronize(stream_);
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
         if (copy_stream2_) { cudaStreamSynchronize(copy_stream2_); cudaStreamDestroy(copy_stream2_); }
-        for (int i = 0; i < 2; i++) if (h2d_done2_[i]) cudaEventDestroy(h2d_done2_[i]);
+        for (int i = 0; i < kTicksInFlight; i++) if (h2d_done2_[i]) cudaEventDestroy(h2d_done2_[i]);
         if (comm_stream_) { cudaStreamSynchronize(comm_stream_); cudaStreamDestroy(comm_stream_); }
         if (comm_done_) cudaEventDestroy(comm_done_);
         if (tick_start_) cudaEventDestroy(tick_start_);
-        for (int i = 0; i < 2; i++) { if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]); if (tick_done_[i]) cudaEventDestroy(tick_done_[i]); }
+        for (int i = 0; i < kTicksInFlight; i++) { if (h2d_done_[i]) cudaEventDestroy(h2d_done_[i]); if (tick_done_[i]) cudaEventDestroy(tick_done_[i]); }
         if (nccl_comm_) { g_nccl.CommDestroy(nccl_comm_); nccl_comm_ = nullptr; }
         for (auto &kv : weights_) {
             cudaFree(kv.second.weights); cudaFree(kv.second.inv); cudaFree(kv.second.first);
@@ -478,12 +483,12 @@ smr_status Renderer::init() {
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream2_, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) CUDA_OK(cudaEventCreateWithFlags(&h2d_done2_[i], cudaEventDisableTiming));
+    for (int i = 0; i < kTicksInFlight; i++) CUDA_OK(cudaEventCreateWithFlags(&h2d_done2_[i], cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&comm_done_, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&tick_start_, cudaEventDisableTiming));
     CUDA_OK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, opts_.cuda_device));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kTicksInFlight; i++) {
         CUDA_OK(cudaEventCreateWithFlags(&h2d_done_[i], cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&tick_done_[i], cudaEventDisableTiming));
     }
@@ -1466,11 +1471,11 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     CUDA_OK(cudaSetDevice(opts_.cuda_device));
     if (profiling_ && !inflight_.empty()) drain();   // per-kernel timing: one tick at a time
     tick_++;
-    slot_ = (int)(tick_ & 1);
-    // the slot's buffers (pinned params, input staging) belong to tick-2: wait for it (without retiring it)
+    slot_ = (int)(tick_ % kTicksInFlight);
+    // the slot's buffers (pinned params, input staging) belong to the tick kTicksInFlight ago: wait for it (without retiring it)
     for (int s : inflight_)
         if (s == slot_) CUDA_OK(cudaEventSynchronize(tick_done_[s]));
-    while (inflight_.size() >= 2) {   // never more than two in flight: the oldest is retired here
+    while ((int)inflight_.size() >= kTicksInFlight) {   // never more than kTicksInFlight in flight: the oldest is retired here
         CUDA_OK(cudaEventSynchronize(tick_done_[inflight_.front()]));
         inflight_.pop_front();
     }

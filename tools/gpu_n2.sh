@@ -2,7 +2,7 @@
 # 2-GPU session: the default bench line under torchrun (cfg3 + the cfg4 leg under every exchange mode).  Usage: gpu_n2.sh TAG [N]
 TAG=${1:-n2}; N=${2:-2}
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 60 --warmup 5 --no-e2e > gpurun_out/${TAG}.json 2> gpurun_out/${TAG}.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${STEPS:-100} --warmup 5 --no-e2e > gpurun_out/${TAG}.json 2> gpurun_out/${TAG}.err
 echo "rc=$?"
 python - <<PY
 import json
