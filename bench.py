@@ -633,12 +633,13 @@ def main():
         host_frames = [[(dev_frames[v][i][0].cpu().pin_memory(), dev_frames[v][i][1].cpu().pin_memory())
                         for i in range(n)] for v in range(hv)]
         host_in = [in_array(host_frames[v], F.MEM_HOST, lambda t: t.data_ptr()) for v in range(hv)]
-        # two sets of pinned output buffers: tick k+1 is submitted (smr_render_begin) before tick k is retired
-        # (smr_render_end), so its H2D copies overlap tick k's kernels -- the overlap the C ABI offers a caller
-        hys = [[torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(n_out)] for _ in range(2)]
-        huvs = [[torch.empty((H // 2, W // 2, 2), dtype=torch.uint8).pin_memory() for _ in range(n_out)] for _ in range(2)]
+        # DEPTH sets of pinned output buffers: ticks k+1 and k+2 are submitted (smr_render_begin) before tick k is retired
+        # (smr_render_end), so uploads, kernels and read-backs of neighbouring ticks overlap -- what the C ABI offers a caller
+        DEPTH = 3
+        hys = [[torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(n_out)] for _ in range(DEPTH)]
+        huvs = [[torch.empty((H // 2, W // 2, 2), dtype=torch.uint8).pin_memory() for _ in range(n_out)] for _ in range(DEPTH)]
         host_out = []
-        for b in range(2):
+        for b in range(DEPTH):
             arr = (F.OutputFrame * n_out)()
             for k in range(n_out):
                 arr[k].output_id = out_ids[k]
@@ -649,7 +650,7 @@ def main():
         def step_host(k, wait):
             for a in host_in[k % hv]:
                 a.pts_ns = k * frame_ns          # fresh frames every tick (a frame older than the fallback timeout is dropped)
-            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k & 1], n_out, wait=wait)
+            r.render_raw(k * frame_ns, host_in[k % hv], n, host_out[k % DEPTH], n_out, wait=wait)
         for k in range(max(args.warmup, 8)):   # every in-flight slot (SMR_TICKS_IN_FLIGHT = 4) has its staging buffers allocated
             step_host(k, True)
         barrier()
@@ -658,13 +659,14 @@ def main():
         t0 = time.perf_counter()
         ee0.record(stream)
         acc = 0
-        step_host(0, False)
-        for k in range(1, ke):
+        for k in range(ke):
             step_host(k, False)
-            r.wait()                                   # retires tick k-1
-            acc += int(hys[(k - 1) & 1][0][0, 0])      # the step's result is read on the host
-        r.wait()
-        acc += int(hys[(ke - 1) & 1][0][0, 0])
+            if k >= DEPTH - 1:
+                r.wait()                                             # retires tick k - (DEPTH - 1)
+                acc += int(hys[(k - DEPTH + 1) % DEPTH][0][0, 0])    # the step's result is read on the host
+        for k in range(ke - DEPTH + 1, ke):
+            r.wait()
+            acc += int(hys[k % DEPTH][0][0, 0])
         ee1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0

@@ -284,7 +284,8 @@ class Renderer {
         OutputNode node;
         int32_t format = 0;
         Resolution res;
-        DevBuf planes[3];       // device staging for host outputs
+        DevBuf planes[kTicksInFlight][3];       // device staging for host outputs, one set per tick in flight: the read-back of
+                                                // tick k runs on its own stream while tick k + 1 composes into the next set
         // smr_set_layouts: the caller flattened the scene itself (the reference's scene/** stays in Rust); used instead
         // of `node` until the next smr_update_scene of this output
         bool flat = false;
@@ -383,6 +384,8 @@ class Renderer {
     std::map<WeightKey, WeightEntry> weights_;
     // up to two ticks in flight: uploads of tick n+1 (copy stream) overlap the kernels of tick n
     cudaStream_t copy_stream_ = nullptr, copy_stream2_ = nullptr;   // uploads alternate between two streams (two DMA engines)
+    cudaStream_t d2h_stream_ = nullptr;      // read-back of host outputs: overlaps the next tick's kernels
+    cudaEvent_t kernels_done_[kTicksInFlight] = {};
     cudaEvent_t h2d_done2_[kTicksInFlight] = {};
     int upload_rr_ = 0;
     cudaEvent_t h2d_done_[kTicksInFlight] = {}, tick_done_[kTicksInFlight] = {};
@@ -399,6 +402,7 @@ class Renderer {
         if (stream_) cudaStreamSynchronize(stream_);
         if (copy_stream_) cudaStreamSynchronize(copy_stream_);
         if (copy_stream2_) cudaStreamSynchronize(copy_stream2_);
+        if (d2h_stream_) cudaStreamSynchronize(d2h_stream_);
         if (comm_stream_) cudaStreamSynchronize(comm_stream_);
         fold_profile();
         inflight_.clear();
@@ -440,6 +444,8 @@ Renderer::~Renderer() {
         cudaStreamSynchronize(stream_);
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
         if (copy_stream2_) { cudaStreamSynchronize(copy_stream2_); cudaStreamDestroy(copy_stream2_); }
+        if (d2h_stream_) { cudaStreamSynchronize(d2h_stream_); cudaStreamDestroy(d2h_stream_); }
+        for (int i = 0; i < kTicksInFlight; i++) if (kernels_done_[i]) cudaEventDestroy(kernels_done_[i]);
         for (int i = 0; i < kTicksInFlight; i++) if (h2d_done2_[i]) cudaEventDestroy(h2d_done2_[i]);
         if (comm_stream_) { cudaStreamSynchronize(comm_stream_); cudaStreamDestroy(comm_stream_); }
         if (comm_done_) cudaEventDestroy(comm_done_);
@@ -483,6 +489,8 @@ smr_status Renderer::init() {
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream2_, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < kTicksInFlight; i++) CUDA_OK(cudaEventCreateWithFlags(&kernels_done_[i], cudaEventDisableTiming));
     for (int i = 0; i < kTicksInFlight; i++) CUDA_OK(cudaEventCreateWithFlags(&h2d_done2_[i], cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&comm_done_, cudaEventDisableTiming));
@@ -1239,9 +1247,9 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
             pitch[p] = (int)user_pitch;
         } else {
             size_t dp = (row_bytes[p] + 15) & ~(size_t)15;  // 16-B rows: vector stores
-            if (dp * rows[p] > o.planes[p].cap && !inflight_.empty()) CUDA_OK(cudaStreamSynchronize(stream_));
-            CUDA_OK(o.planes[p].ensure(dp * rows[p]));
-            dst[p] = o.planes[p].p;
+            DevBuf &stage = o.planes[slot_][p];   // the slot's previous tick was waited for in render_begin
+            CUDA_OK(stage.ensure(dp * rows[p]));
+            dst[p] = stage.p;
             pitch[p] = (int)dp;
             d2h_.push_back({of.planes[p], user_pitch, dst[p], dp, row_bytes[p], rows[p]});
             stats_.d2h_bytes += row_bytes[p] * rows[p];
@@ -1488,6 +1496,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     fills_.clear(); d2h_.clear(); resample_cache_.clear();
     param_used_ = 0; frame_used_ = 0;
     uint64_t launches = 0;
+    cudaStream_t done_on = stream_;   // the stream the tick's last operation goes to
 
     // scene.register_render_event(pts, input_resolutions), state.rs:233-239
     std::map<std::string, Resolution> res_map;
@@ -1667,15 +1676,21 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
                                            f.yuv[0], f.yuv[1], f.yuv[2], stream_))) goto fail;
         prof_mark(SMR_KERNEL_FILL);
     }
+    // read-back on its own stream: the staging planes are per slot, so the next tick's kernels need not wait for it
+    if (!d2h_.empty() && !profiling_) {
+        CUDA_OK(cudaEventRecord(kernels_done_[slot_], stream_));
+        CUDA_OK(cudaStreamWaitEvent(d2h_stream_, kernels_done_[slot_], 0));
+        done_on = d2h_stream_;
+    }
     for (PendingCopy &c : d2h_)
         if (c.dpitch == c.width && c.spitch == c.width)
-            CUDA_OK(cudaMemcpyAsync(c.dst, c.src, c.width * c.height, cudaMemcpyDeviceToHost, stream_));
+            CUDA_OK(cudaMemcpyAsync(c.dst, c.src, c.width * c.height, cudaMemcpyDeviceToHost, done_on));
         else
-            CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, stream_));
+            CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, done_on));
     stats_.kernel_launches += launches;
     stats_.last_render_kernel_launches = launches;
     stats_.frames_rendered += n_out;
-    CUDA_OK(cudaEventRecord(tick_done_[slot_], stream_));
+    CUDA_OK(cudaEventRecord(tick_done_[slot_], done_on));
     inflight_.push_back(slot_);
     return SMR_OK;
 fail:
