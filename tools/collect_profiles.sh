@@ -2,7 +2,7 @@
 # Turns the gpurun_out/ evidence of tools/gpu_final.sh TAG into tracked text artefacts under profiles/.
 TAG=${1:-r02}
 O=profiles
-for w in cfg3 cfg3b cfg2 cfg4 cfg5 passthrough; do [ -s gpurun_out/${TAG}_bench_$w.json ] && tail -1 gpurun_out/${TAG}_bench_$w.json > $O/${TAG}_bench_$w.json; done
+for w in cfg3 cfg3b cfg2 cfg4 cfg5 grid25 passthrough; do [ -s gpurun_out/${TAG}_bench_$w.json ] && tail -1 gpurun_out/${TAG}_bench_$w.json > $O/${TAG}_bench_$w.json; done
 [ -s gpurun_out/${TAG}_reference_arm.json ] && tail -1 gpurun_out/${TAG}_reference_arm.json > $O/${TAG}_bench_cfg3_reference_arm.json
 cp gpurun_out/${TAG}_launches_cfg3.csv $O/${TAG}_launches_cfg3.csv 2>/dev/null
 for k in fused comp; do
@@ -13,6 +13,11 @@ for k in fused comp; do
 done
 python tools/ncu_lines.py gpurun_out/${TAG}_ncu_fused_cfg3.ncu-rep k_resample_tma 0.8 > $O/${TAG}_ncu_lines_fused_cfg3.txt 2>/dev/null
 python tools/ncu_lines.py gpurun_out/${TAG}_ncu_comp_cfg3.ncu-rep k_composite 0.8 > $O/${TAG}_ncu_lines_comp_cfg3.txt 2>/dev/null
+rep=gpurun_out/${TAG}_ncu_anyratio_cfg5.ncu-rep
+if [ -s $rep ]; then
+  { echo "==== ncu --set full --clock-control none, one launch of k_resample_tma0 inside bench.py --workload cfg5 (raw page) ===="; ncu -i $rep --page raw 2>/dev/null; } > $O/${TAG}_ncu_raw_anyratio_cfg5.txt
+  python tools/ncu_lines.py $rep k_resample_tma0 0.8 > $O/${TAG}_ncu_lines_anyratio_cfg5.txt 2>/dev/null
+fi
 for t in memcheck racecheck; do [ -s gpurun_out/${TAG}_$t.log ] && grep -v "^$" gpurun_out/${TAG}_$t.log | tail -12 > $O/${TAG}_sanitizer_$t.log; done
 tail -5 gpurun_out/${TAG}_pytest.log > $O/${TAG}_pytest_gpu_tail.log
 python - <<PY

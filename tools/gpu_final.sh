@@ -3,7 +3,7 @@
 TAG=${1:-final}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
-for w in cfg3 cfg3b cfg2 cfg4 cfg5 passthrough; do
+for w in cfg3 cfg3b cfg2 cfg4 cfg5 grid25 passthrough; do
   timeout 300 python bench.py --workload $w > gpurun_out/${TAG}_bench_$w.json 2> gpurun_out/${TAG}_bench_$w.err
   python - <<PY
 import json
@@ -18,6 +18,7 @@ tail -c 700 gpurun_out/${TAG}_reference_arm.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 24 -c 40 --csv --log-file gpurun_out/${TAG}_launches_cfg3.csv python bench.py --workload cfg3 --steps 6 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_resample_tma -s 12 -c 1 -o gpurun_out/${TAG}_ncu_fused_cfg3 -f python bench.py --workload cfg3 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_fused.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_composite -s 12 -c 1 -o gpurun_out/${TAG}_ncu_comp_cfg3 -f python bench.py --workload cfg3 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_comp.log 2>&1
-timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio or tiles_02 or nv12_input or full_range or random_noise" > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${TAG}_memcheck.log
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/${TAG}_racecheck.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_resample_tma0 -s 6 -c 1 -o gpurun_out/${TAG}_ncu_anyratio_cfg5 -f python bench.py --workload cfg5 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_anyratio.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio or tiles_02 or nv12_input or full_range or random_noise or transition_fractional or (box_reduced and 256)" > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${TAG}_memcheck.log
+timeout 500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio or (transition_fractional and 0.5) or (box_reduced and 384 and nv12)" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/${TAG}_racecheck.log
 echo done
