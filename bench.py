@@ -127,7 +127,7 @@ SETUP_SECONDS = 0.3   # untimed set-up ticks before the W warm-up steps (clock r
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,clocks.mem,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -138,7 +138,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20" if self.n == 1 else "50"],   # a query of 8 GPUs
+                                         stdout=subprocess.PIPE, text=True)                               # holds driver locks for longer
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
