@@ -815,7 +815,9 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm_in, const Axis
         const int max_span = box ? dev::kTma0MaxSpan / 2 : dev::kTma0MaxSpan;   // the row buffer holds 256 source pixels = 128 reduced ones
         while (cols > 2 && (int)std::ceil((cols - 1) * sh) + th + 3 > max_span) cols -= 2;
         // slots of a lane's window: taps + the widest distance of two adjacent columns' first taps + the pad slots crossed
-        const int gmax = sh == std::floor(sh) ? (int)sh : (int)std::floor(sh) + 1;
+        // (an integer ratio without offset is exact in f32: the distance is the ratio; otherwise floor + 1 bounds it, and the
+        // kernel traps rather than drop a tap should rounding ever exceed that)
+        const int gmax = (sh == std::floor(sh) && hm.crop_offset == 0.0f) ? (int)sh : (int)std::floor(sh) + 1;
         const int win = th + gmax, winp = win + ((7 + win - 1) >> 3);
         int bucket = 0;
         while (bucket < 4 && dev::kTma0Window[bucket] < winp) bucket++;
