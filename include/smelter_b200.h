@@ -258,6 +258,29 @@ smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *frame, u
  * smr_render are expected to hold.  Blocking; `rgba` has height rows of `pitch` bytes (0 = tightly packed). */
 smr_status smr_premultiply_rgba8(smr_renderer *r, const smr_input_frame *frame, void *rgba, uint32_t pitch, int32_t mem_kind);
 
+/* Text nodes: TextRendererNode::render (transformations/text_renderer.rs:72-167).  Shaping and glyph
+ * rasterisation (cosmic-text / swash inside glyphon, CPU code in the reference too) stay on the caller's side; what the
+ * reference does on the GPU -- clear the node texture to the component's background colour (:141-150) and draw glyphon's
+ * prepared glyph quads over it (`text_renderer.render`, :163) -- happens here: `glyphs` is glyphon's GlyphToRender list
+ * after its clipping to TextBounds (quad origin, size, atlas origin, colour, content type), the atlases are its mask
+ * (R8) and colour (RGBA8) atlas pages.  Quads are alpha-blended in list order (wgpu::BlendState::ALPHA_BLENDING) through
+ * the node texture's view.  color_mode: glyphon ColorMode, 0 = Accurate (TextAtlas::new, :95-100), 1 = Web.  The
+ * result (width x height RGBA8, premultiplied by construction) is the text node's texture: hand it to smr_render as a
+ * SMR_FRAME_RGBA8 input (device memory: zero copy) -- like the reference, render it once per scene update
+ * (`was_rendered`, :73-75), not per frame.  glyphs and atlases are HOST memory; `rgba` per mem_kind.  Blocking. */
+typedef enum { SMR_GLYPH_COLOR = 0, SMR_GLYPH_MASK = 1 } smr_glyph_content;      /* glyphon ContentType */
+typedef struct {
+    int32_t x, y;                  /* top-left pixel of the quad in the text texture */
+    uint16_t width, height;
+    uint16_t atlas_x, atlas_y;     /* top-left texel in the atlas `content` names */
+    smr_rgba color;                /* glyphon::Color: straight alpha, sRGB */
+    int32_t content;               /* smr_glyph_content */
+} smr_glyph;
+typedef struct { const void *data; uint32_t width, height, pitch; } smr_atlas;   /* pitch 0 = tightly packed */
+smr_status smr_render_text(smr_renderer *r, uint32_t width, uint32_t height, smr_rgba background, const smr_glyph *glyphs,
+                           uint32_t n_glyphs, const smr_atlas *mask_atlas, const smr_atlas *color_atlas, int32_t color_mode,
+                           void *rgba, uint32_t pitch, int32_t mem_kind);
+
 /* inspection (no device needed): the balanced row partition the fused resample launch uses for jobs of
  * dst_w[i] x dst_h[i] output pixels on `max_blocks` resident blocks.  pieces: 4 ints each {job, strip, row_begin,
  * row_end}; block b owns pieces [begin[b], begin[b + 1]). */
@@ -277,7 +300,7 @@ smr_status smr_debug_layouts(smr_renderer *r, const char *output_id, uint64_t pt
                              smr_render_layout *out, uint32_t capacity, uint32_t *n_out,
                              uint32_t *root_width, uint32_t *root_height);
 
-/* The FLATTENED form of the boundary: a host that keeps the reference's scene/** (Component tree,
+/* The FLATTENED form of the boundary: a host that keeps the reference's scene/ tree (Component tree,
  * transitions, NestedLayout::flatten -- all Rust) hands over, per output and whenever they change, the RenderLayout[]
  * that transformations/layout/params.rs:169-333 would pack into uniform blocks: same fields, same units (pixels of
  * the root_width x root_height layout node texture), painter's order.  child_ids[k] is the input id of the node's

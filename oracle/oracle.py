@@ -59,6 +59,9 @@ def lib():
         build()
         _lib = C.CDLL(_LIB_PATH)
         _lib.orc_srgb_decode_u8.restype = C.c_float
+        _lib.orc_render_text.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_render_text.restype = None
         _lib.orc_srgb_decode_u8.argtypes = [C.c_uint8]
         _lib.orc_srgb_encode_u8.restype = C.c_uint8
         _lib.orc_srgb_encode_u8.argtypes = [C.c_float]
@@ -175,6 +178,26 @@ def add_premultiplied_alpha(rgba, mode=0):
     h, w = rgba.shape[:2]
     out = np.empty((h, w, 4), np.uint8)
     lib().orc_add_premultiplied_alpha(_p(rgba), w, h, int(mode), _p(out))
+    return out
+
+
+GLYPH_DTYPE = [("x", "<i4"), ("y", "<i4"), ("width", "<u2"), ("height", "<u2"), ("atlas_x", "<u2"), ("atlas_y", "<u2"),
+               ("color", "u1", (4,)), ("content", "<i4")]   # orc_glyph
+
+
+def render_text(width, height, background, glyphs, mask_atlas=None, color_atlas=None, color_mode=0, mode=0):
+    """TextRendererNode::render: clear + glyph quads (orc_render_text).  background: 4 bytes; glyphs: GLYPH_DTYPE records."""
+    if width == 0 or height == 0:
+        return np.zeros((1, 1, 4), np.uint8)
+    g = np.ascontiguousarray(glyphs, dtype=np.dtype(GLYPH_DTYPE))
+    bg = (C.c_uint8 * 4)(*[int(v) for v in background])
+    m = _u8(mask_atlas) if mask_atlas is not None else None
+    c = _u8(color_atlas) if color_atlas is not None else None
+    out = np.empty((height, width, 4), np.uint8)
+    lib().orc_render_text(int(width), int(height), bg, g.ctypes.data_as(C.c_void_p) if len(g) else None, len(g),
+                          _p(m) if m is not None else None, m.shape[1] if m is not None else 0, m.shape[0] if m is not None else 0,
+                          _p(c) if c is not None else None, c.shape[1] if c is not None else 0, c.shape[0] if c is not None else 0,
+                          int(color_mode), int(mode), _p(out))
     return out
 
 

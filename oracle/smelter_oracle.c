@@ -692,6 +692,70 @@ void orc_add_premultiplied_alpha(const uint8_t *rgba, int w, int h, int mode, ui
     }
 }
 
+/* TextRendererNode::render (transformations/text_renderer.rs:72-167): the node texture is cleared to the component's
+ * background colour (`LoadOp::Clear(convert_to_shader_color(..))`, :141-150, stored through the target view) and
+ * glyphon's TextRenderer draws one quad per prepared glyph over it.  glyphon is an un-vendored git dependency
+ * (0.11.0 @ smelter-labs rev c784922, Cargo.lock:2298); what is restated here is its published shader + pipeline:
+ *   vertex:   quad = pos + {0, dim}, uv = atlas origin + {0, dim} in integer texels (so every covered pixel centre hits
+ *             the centre of exactly one atlas texel: a plain texel fetch, whatever the sampler's filter);
+ *             glyph colour -> linear (srgb_to_linear per channel, alpha untouched) in ColorMode::Accurate -- the mode
+ *             TextAtlas::new selects (:95-100) -- or left as it is in ColorMode::Web;
+ *   fragment: mask glyph:  (colour.rgb, colour.a * mask)      mask atlas = R8Unorm
+ *             colour glyph: the colour-atlas texel             colour atlas = Rgba8UnormSrgb (Accurate) / Rgba8Unorm (Web)
+ *   blend:    wgpu::BlendState::ALPHA_BLENDING -- rgb: src * src.a + dst * (1 - src.a); a: src.a + dst.a * (1 - src.a),
+ *             on the clamped source, destination read and result stored through the node texture's view
+ *             (sRGB in GpuOptimized, plain UNORM8 in CpuOptimized).
+ * The glyph list is glyphon's `GlyphToRender` after its CPU-side clipping to TextBounds; shaping and rasterisation
+ * (cosmic-text / swash) stay on the CPU side of the boundary.  PARITY UNPINNED: render_tests/text.rs holds snapshots only. */
+void orc_render_text(int w, int h, const uint8_t background[4], const orc_glyph *glyphs, int n_glyphs, const uint8_t *mask_atlas,
+                     int mask_w, int mask_h, const uint8_t *color_atlas, int color_w, int color_h, int color_mode, int mode,
+                     uint8_t *out) {
+    orc_init();
+    float bg[4];
+    shader_color(background, mode, bg);
+    for (int i = 0; i < w * h; i++) {
+        uint8_t *o = out + (size_t)i * 4;
+        for (int c = 0; c < 3; c++) o[c] = mode == ORC_MODE_GPU_OPTIMIZED ? orc_srgb_encode_u8(bg[c]) : orc_unorm8(bg[c]);
+        o[3] = orc_unorm8(bg[3]);
+    }
+    const int accurate = color_mode == 0;
+    for (int gi = 0; gi < n_glyphs; gi++) {
+        const orc_glyph *G = &glyphs[gi];
+        float col[4];
+        for (int c = 0; c < 3; c++) col[c] = accurate ? g_dec[G->color[c]] : g_u8n[G->color[c]];
+        col[3] = g_u8n[G->color[3]];
+        for (int dy = 0; dy < (int)G->height; dy++) {
+            const int py = G->y + dy;
+            if (py < 0 || py >= h) continue;
+            for (int dx = 0; dx < (int)G->width; dx++) {
+                const int px = G->x + dx;
+                if (px < 0 || px >= w) continue;
+                const int ax = (int)G->atlas_x + dx, ay = (int)G->atlas_y + dy;
+                float s[4];
+                if (G->content == 1) {   /* ContentType::Mask */
+                    /* texel outside the atlas: ClampToEdge of glyphon's sampler */
+                    const int cx = ax < mask_w ? ax : mask_w - 1, cy = ay < mask_h ? ay : mask_h - 1;
+                    const float cov = mask_atlas ? g_u8n[mask_atlas[(size_t)cy * mask_w + cx]] : 0.0f;
+                    s[0] = col[0]; s[1] = col[1]; s[2] = col[2]; s[3] = col[3] * cov;
+                } else {                 /* ContentType::Color */
+                    const int cx = ax < color_w ? ax : color_w - 1, cy = ay < color_h ? ay : color_h - 1;
+                    const uint8_t *t = color_atlas ? color_atlas + ((size_t)cy * color_w + cx) * 4 : NULL;
+                    for (int c = 0; c < 3; c++) s[c] = t ? (accurate ? g_dec[t[c]] : g_u8n[t[c]]) : 0.0f;
+                    s[3] = t ? g_u8n[t[3]] : 0.0f;
+                }
+                for (int c = 0; c < 4; c++) s[c] = clamp01(s[c]);
+                const float a = s[3], ia = 1.0f - a;
+                uint8_t *d = out + ((size_t)py * w + px) * 4;
+                for (int c = 0; c < 3; c++) {
+                    if (mode == ORC_MODE_GPU_OPTIMIZED) d[c] = orc_srgb_encode_u8(fmaf(g_dec[d[c]], ia, s[c] * a));
+                    else d[c] = orc_unorm8(fmaf(g_u8n[d[c]], ia, s[c] * a));
+                }
+                d[3] = orc_unorm8(fmaf(g_u8n[d[3]], ia, a));
+            }
+        }
+    }
+}
+
 void orc_rescale_rgba(const uint8_t *rgba, int sw, int sh, int ow, int oh, int mode, uint8_t *out) {
     orc_texture t = {sw, sh, rgba};
 #pragma omp parallel for schedule(static)

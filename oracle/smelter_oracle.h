@@ -134,6 +134,20 @@ void orc_render_layout_node(int out_w, int out_h, const orc_layout *layouts, int
 void orc_rescale_rgba(const uint8_t *rgba, int sw, int sh, int ow, int oh, int mode, uint8_t *out);
 /* add_premultiplied_alpha.wgsl:24-35: straight alpha -> premultiplied through the mode's texture views */
 void orc_add_premultiplied_alpha(const uint8_t *rgba, int w, int h, int mode, uint8_t *out);
+/* glyphon GlyphToRender after clipping (un-vendored dependency glyphon 0.11.0 @ smelter-labs c784922): quad origin in
+ * the text texture, size, atlas origin, straight-alpha sRGB colour, content (0 = colour atlas, 1 = mask atlas) */
+typedef struct {
+    int32_t x, y;
+    uint16_t width, height;
+    uint16_t atlas_x, atlas_y;
+    uint8_t color[4];
+    int32_t content;
+} orc_glyph;
+/* TextRendererNode::render (text_renderer.rs:72-167): clear to background, alpha-blend the glyph quads in order.
+ * mask_atlas: R8 (mask_w x mask_h), color_atlas: RGBA8; color_mode 0 = glyphon ColorMode::Accurate, 1 = Web. */
+void orc_render_text(int w, int h, const uint8_t background[4], const orc_glyph *glyphs, int n_glyphs, const uint8_t *mask_atlas,
+                     int mask_w, int mask_h, const uint8_t *color_atlas, int color_w, int color_h, int color_mode, int mode,
+                     uint8_t *out);
 void orc_harness_yuv420_to_rgba(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w,
                                 int h, uint8_t *rgba);
 

@@ -101,6 +101,20 @@ class RenderLayout(C.Structure):
                 ("masks", Mask * MAX_MASKS)]
 
 
+class Rgba(C.Structure):
+    _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8), ("a", C.c_uint8)]
+
+
+class Atlas(C.Structure):       # smr_atlas
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32)]
+
+
+GLYPH_COLOR, GLYPH_MASK = 0, 1
+# smr_glyph as a numpy record (24 bytes, the C layout): glyphon's GlyphToRender after clipping
+GLYPH_DTYPE = [("x", "<i4"), ("y", "<i4"), ("width", "<u2"), ("height", "<u2"), ("atlas_x", "<u2"), ("atlas_y", "<u2"),
+               ("color", "u1", (4,)), ("content", "<i4")]
+
+
 class Stats(C.Structure):
     _fields_ = [("frames_rendered", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("last_render_kernel_launches", C.c_uint64)]
@@ -116,7 +130,7 @@ class KernelTimes(C.Structure):
 
 EXPORTS = [
     "smr_create", "smr_destroy", "smr_register_input", "smr_unregister_input", "smr_update_scene",
-    "smr_unregister_output", "smr_set_layouts", "smr_render", "smr_render_begin", "smr_render_end", "smr_preprocess_frame", "smr_premultiply_rgba8", "smr_debug_partition", "smr_output_plane_sizes",
+    "smr_unregister_output", "smr_set_layouts", "smr_render", "smr_render_begin", "smr_render_end", "smr_preprocess_frame", "smr_premultiply_rgba8", "smr_render_text", "smr_debug_partition", "smr_output_plane_sizes",
     "smr_component_default", "smr_debug_layouts", "smr_debug_set_inputs", "smr_get_stats", "smr_set_profiling", "smr_get_kernel_times",
     "smr_comm_get_unique_id", "smr_comm_init", "smr_comm_broadcast_inputs", "smr_comm_exchange_inputs", "smr_comm_pull_inputs", "smr_peer_pool_alloc", "smr_peer_pool_open", "smr_peer_pool_close", "smr_peer_pool_free", "smr_comm_destroy", "smr_host_register", "smr_host_unregister", "smr_cuda_stream", "smr_last_error",
     "smr_version",
@@ -150,6 +164,9 @@ def lib():
     L.smr_preprocess_frame.restype = C.c_int32
     L.smr_premultiply_rgba8.argtypes = [vp, C.POINTER(InputFrame), C.c_void_p, C.c_uint32, C.c_int32]
     L.smr_premultiply_rgba8.restype = C.c_int32
+    L.smr_render_text.argtypes = [vp, C.c_uint32, C.c_uint32, Rgba, C.c_void_p, C.c_uint32, C.POINTER(Atlas), C.POINTER(Atlas),
+                                  C.c_int32, C.c_void_p, C.c_uint32, C.c_int32]
+    L.smr_render_text.restype = C.c_int32
     L.smr_debug_partition.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint32, C.c_uint32, C.POINTER(C.c_int32),
                                       C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_uint32)]
     L.smr_debug_partition.restype = C.c_int32

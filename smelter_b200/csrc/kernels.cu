@@ -1843,6 +1843,77 @@ int launch_preprocess(const Tex &src, int mode, int rescale, uint8_t *out, int o
 }
 
 // ------------------------------------------------------------------------------------------------
+// Text node texture (transformations/text_renderer.rs:72-167 + glyphon's glyph pipeline): LoadOp::Clear(background), then
+// one quad per prepared glyph, wgpu::BlendState::ALPHA_BLENDING through the node texture's view, in list order.
+// One thread per pixel of a 32 x 8 tile; the block walks the glyph list 256 entries at a time, keeps (in order) the
+// ones whose quad touches the tile, and every pixel blends those that cover it.  Quads sit on whole pixels and whole
+// atlas texels, so a covered pixel reads exactly one texel.  Rendered once per scene update, not per frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_text(const __grid_constant__ TextJob J) {
+    __shared__ Tables T;
+    __shared__ int s_list[256];
+    __shared__ int s_wc[8];
+    load_tables(T);
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, px = x0 + lane, py = y0 + warp;
+    uchar4 d;
+    if (J.mode == 0) d = make_uchar4((unsigned char)srgb_encode(T, J.bg[0]), (unsigned char)srgb_encode(T, J.bg[1]), (unsigned char)srgb_encode(T, J.bg[2]), (unsigned char)unorm8(J.bg[3]));
+    else d = make_uchar4((unsigned char)unorm8(J.bg[0]), (unsigned char)unorm8(J.bg[1]), (unsigned char)unorm8(J.bg[2]), (unsigned char)unorm8(J.bg[3]));
+    const float *clut = J.color_mode == 0 ? T.dec : T.u8n;   // ColorMode::Accurate: glyph colours and colour-atlas texels -> linear
+    const float *dlut = J.mode == 0 ? T.dec : T.u8n;         // the node texture's view
+    for (int base = 0; base < J.n_glyphs; base += 256) {
+        const int gi = base + tid;
+        bool hit = false;
+        if (gi < J.n_glyphs) {
+            const GlyphDev G = J.glyphs[gi];
+            hit = G.w > 0 && G.h > 0 && G.x < x0 + 32 && G.x + (int)G.w > x0 && G.y < y0 + 8 && G.y + (int)G.h > y0;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_wc[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const int c = s_wc[w]; before += w < warp ? c : 0; total += c; }
+        if (hit) s_list[before + __popc(b & ((1u << lane) - 1u))] = gi;   // list order is painter's order
+        __syncthreads();
+        for (int k = 0; k < total; k++) {
+            const GlyphDev G = J.glyphs[s_list[k]];
+            const int dx = px - G.x, dy = py - G.y;
+            if ((unsigned)dx >= (unsigned)G.w || (unsigned)dy >= (unsigned)G.h) continue;
+            const int ax = (int)G.ax + dx, ay = (int)G.ay + dy;
+            float s0, s1, s2, a;
+            if (G.content == 1) {      // ContentType::Mask: (colour.rgb, colour.a * coverage)
+                const int cx = min(ax, J.mask_w - 1), cy = min(ay, J.mask_h - 1);
+                const float cov = J.mask ? T.u8n[__ldg(J.mask + (size_t)cy * J.mask_pitch + cx)] : 0.0f;
+                s0 = clut[G.color[0]]; s1 = clut[G.color[1]]; s2 = clut[G.color[2]];
+                a = T.u8n[G.color[3]] * cov;
+            } else {                   // ContentType::Color: the atlas texel
+                if (J.color) {
+                    const int cx = min(ax, J.color_w - 1), cy = min(ay, J.color_h - 1);
+                    const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(J.color + (size_t)cy * J.color_pitch) + cx);
+                    s0 = clut[t.x]; s1 = clut[t.y]; s2 = clut[t.z]; a = T.u8n[t.w];
+                } else { s0 = s1 = s2 = a = 0.0f; }
+            }
+            s0 = clamp01(s0); s1 = clamp01(s1); s2 = clamp01(s2); a = clamp01(a);
+            if (a == 0.0f) continue;   // dst * 1 + src * 0: encode(decode(b)) == b, unorm8(b / 255) == b
+            const float ia = 1.0f - a;
+            const float r0 = fmaf(dlut[d.x], ia, s0 * a), r1 = fmaf(dlut[d.y], ia, s1 * a), r2 = fmaf(dlut[d.z], ia, s2 * a);
+            if (J.mode == 0) { d.x = (unsigned char)srgb_encode(T, r0); d.y = (unsigned char)srgb_encode(T, r1); d.z = (unsigned char)srgb_encode(T, r2); }
+            else { d.x = (unsigned char)unorm8(r0); d.y = (unsigned char)unorm8(r1); d.z = (unsigned char)unorm8(r2); }
+            d.w = (unsigned char)unorm8(fmaf(T.u8n[d.w], ia, a));
+        }
+        __syncthreads();   // s_list / s_wc are rewritten by the next batch
+    }
+    if (px < J.width && py < J.height) reinterpret_cast<uchar4 *>(J.out + (size_t)py * J.out_pitch)[px] = d;
+}
+
+int launch_text(const TextJob &job, Stream s) {
+    dim3 b(32, 8), g((job.width + 31) / 32, (job.height + 7) / 8);
+    k_text<<<g, b, 0, (cudaStream_t)s>>>(job);
+    return check_launch("k_text") ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: black frame (render_loop.rs:127-173)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill(uint8_t *p0, uint8_t *p1, uint8_t *p2, int pitch0, int pitch1, int pitch2, int w, int h,

@@ -166,6 +166,25 @@ struct OutputJob {          // K10/K11 stand-alone (root size != output size, or
     int32_t out_pitch0, out_pitch1, out_pitch2;
 };
 
+// TextRendererNode::render (text_renderer.rs:72-167): glyphon's prepared glyph quads, same layout as smr_glyph
+struct GlyphDev {
+    int32_t x, y;                 // quad origin in the text texture (may be negative / beyond the edge: clipped per pixel)
+    uint16_t w, h, ax, ay;        // quad size; origin in the atlas its `content` names
+    uint8_t color[4];             // straight-alpha sRGB colour
+    int32_t content;              // 0 colour atlas (RGBA8), 1 mask atlas (R8)
+};
+struct TextJob {
+    int32_t width, height;
+    int32_t mode;                 // 0 GpuOptimized (sRGB node texture), 1 CpuOptimized
+    int32_t color_mode;           // glyphon ColorMode: 0 Accurate (colours -> linear, colour atlas sRGB), 1 Web
+    int32_t n_glyphs;
+    float bg[4];                  // premultiplied shader colour of the clear (wgpu/utils.rs:51-71)
+    const GlyphDev *glyphs;
+    const uint8_t *mask; int32_t mask_w, mask_h, mask_pitch;
+    const uint8_t *color; int32_t color_w, color_h, color_pitch;
+    uint8_t *out; int32_t out_pitch;
+};
+
 // host tables pushed once per device (numeric contract NC-1/3/4)
 void upload_tables(const float *u8n, const float *srgb_dec, const float *srgb_enc_thr);
 
@@ -181,6 +200,8 @@ inline int fused_source_class(int tex_kind) {
 }
 // FramePreProcessor: node texture of `src` (rescale = 0) or its linear-filtered rescale to out_w x out_h
 int launch_preprocess(const Tex &src, int mode, int rescale, uint8_t *out, int out_pitch, int out_w, int out_h, Stream s);
+// text node texture: clear + glyph quads alpha-blended in list order
+int launch_text(const TextJob &job, Stream s);
 int launch_resample_fused(int variant, int src, const FusedJob *jobs_dev, const FusedPiece *pieces_dev,
                           const int *piece_begin_dev, int nblocks, Stream s);
 // integer-ratio variant: the (single-phase) weight row of ratio S goes to constant memory, once per mapping

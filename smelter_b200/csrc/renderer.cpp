@@ -262,6 +262,8 @@ class Renderer {
     smr_status render_end_all();
     smr_status preprocess_frame(const smr_input_frame *f, uint32_t ow, uint32_t oh, void *rgba, uint32_t pitch, int32_t mem_kind,
                                 bool premultiply = false);
+    smr_status render_text(uint32_t w, uint32_t h, smr_rgba bg, const smr_glyph *glyphs, uint32_t n, const smr_atlas *mask,
+                           const smr_atlas *color, int32_t color_mode, void *rgba, uint32_t pitch, int32_t mem_kind);
     smr_status debug_set_inputs(uint64_t pts, const smr_input_frame *in, uint32_t n_in);
     smr_status debug_layouts(const char *output_id, uint64_t pts, smr_render_layout *out, uint32_t cap, uint32_t *n,
                              uint32_t *rw, uint32_t *rh);
@@ -1164,6 +1166,73 @@ smr_status Renderer::preprocess_frame(const smr_input_frame *f, uint32_t ow, uin
         stats_.d2h_bytes += row * oh;
     }
     CUDA_OK(cudaStreamSynchronize(stream_));   // the reference blocks in device.poll (frame_pre_processor.rs:171-176)
+    return SMR_OK;
+}
+
+// TextRendererNode::render (transformations/text_renderer.rs:72-167): clear + glyphon's glyph quads
+smr_status Renderer::render_text(uint32_t w, uint32_t h, smr_rgba bg, const smr_glyph *glyphs, uint32_t n, const smr_atlas *mask,
+                                 const smr_atlas *color, int32_t color_mode, void *rgba, uint32_t pitch, int32_t mem_kind) {
+    static_assert(sizeof(smr_glyph) == sizeof(dev::GlyphDev), "smr_glyph is copied to the device as it is");
+    if (!rgba || (n && !glyphs) || (color_mode != 0 && color_mode != 1)) return SMR_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(mu_);
+    if (host_only_) { set_error("host-only handle (cuda_device = -1) has no device: no CPU fallback"); return SMR_ERR_CUDA; }
+    CUDA_OK(cudaSetDevice(opts_.cuda_device));
+    // a zero-sized text texture is a transparent 1x1 one in the reference (text_renderer.rs:77-85); here the caller skips it
+    if (w == 0 || h == 0 || w > 16384 || h > 16384) { set_error("text texture resolution out of range"); return SMR_ERR_INVALID_ARGUMENT; }
+    if (n > (1u << 22)) { set_error("too many glyphs"); return SMR_ERR_INVALID_ARGUMENT; }
+    bool need_mask = false, need_color = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if (glyphs[i].content == SMR_GLYPH_MASK) need_mask = true;
+        else if (glyphs[i].content == SMR_GLYPH_COLOR) need_color = true;
+        else { set_error("glyph content type must be SMR_GLYPH_COLOR or SMR_GLYPH_MASK"); return SMR_ERR_INVALID_ARGUMENT; }
+    }
+    dev::TextJob J = {};
+    J.width = (int)w; J.height = (int)h; J.mode = opts_.rendering_mode; J.color_mode = color_mode; J.n_glyphs = (int)n;
+    shader_color(RGBA{bg.r, bg.g, bg.b, bg.a}, J.bg);
+    const smr_atlas *atl[2] = {mask, color};
+    const bool need[2] = {need_mask, need_color};
+    for (int k = 0; k < 2; k++) {
+        if (!need[k]) continue;
+        const smr_atlas *a = atl[k];
+        const size_t texel = k == 0 ? 1 : 4;
+        if (!a || !a->data || a->width == 0 || a->height == 0 || a->width > 16384 || a->height > 16384) {
+            set_error(k == 0 ? "mask glyphs need a mask atlas" : "colour glyphs need a colour atlas");
+            return SMR_ERR_INVALID_ARGUMENT;
+        }
+        const size_t row = (size_t)a->width * texel, sp = a->pitch ? a->pitch : row;
+        if (sp < row) { set_error("atlas pitch smaller than a row"); return SMR_ERR_INVALID_ARGUMENT; }
+        if (row * a->height > pre_planes_[k].cap) CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(pre_planes_[k].ensure(row * a->height));
+        CUDA_OK(cudaMemcpy2DAsync(pre_planes_[k].p, row, a->data, sp, row, a->height, cudaMemcpyHostToDevice, stream_));
+        stats_.h2d_bytes += row * a->height;
+        if (k == 0) { J.mask = pre_planes_[0].p; J.mask_w = (int)a->width; J.mask_h = (int)a->height; J.mask_pitch = (int)row; }
+        else { J.color = pre_planes_[1].p; J.color_w = (int)a->width; J.color_h = (int)a->height; J.color_pitch = (int)row; }
+    }
+    if (n) {
+        const size_t bytes = sizeof(smr_glyph) * (size_t)n;
+        if (bytes > pre_planes_[2].cap) CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(pre_planes_[2].ensure(bytes));
+        CUDA_OK(cudaMemcpyAsync(pre_planes_[2].p, glyphs, bytes, cudaMemcpyHostToDevice, stream_));
+        stats_.h2d_bytes += bytes;
+        J.glyphs = reinterpret_cast<const dev::GlyphDev *>(pre_planes_[2].p);
+    }
+    const size_t row = (size_t)w * 4, user_pitch = pitch ? pitch : row;
+    if (user_pitch < row) { set_error("output pitch smaller than a row"); return SMR_ERR_BUFFER_TOO_SMALL; }
+    uint8_t *dst = (uint8_t *)rgba;
+    size_t dpitch = user_pitch;
+    if (mem_kind != SMR_MEM_DEVICE) {
+        if (row * h > pre_out_.cap) CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(pre_out_.ensure(row * h));
+        dst = pre_out_.p; dpitch = row;
+    } else if ((dpitch & 3) || ((size_t)dst & 3)) { set_error("device RGBA8 planes are 4-byte aligned"); return SMR_ERR_INVALID_ARGUMENT; }
+    J.out = dst; J.out_pitch = (int)dpitch;
+    if (dev::launch_text(J, stream_) < 0) { set_error(dev::last_launch_error()); return SMR_ERR_CUDA; }
+    stats_.kernel_launches++;
+    if (mem_kind != SMR_MEM_DEVICE) {
+        CUDA_OK(cudaMemcpy2DAsync(rgba, user_pitch, dst, dpitch, row, h, cudaMemcpyDeviceToHost, stream_));
+        stats_.d2h_bytes += row * h;
+    }
+    CUDA_OK(cudaStreamSynchronize(stream_));   // the glyph list and the atlases are borrowed for the call only
     return SMR_OK;
 }
 
@@ -2109,6 +2178,10 @@ smr_status smr_preprocess_frame(smr_renderer *r, const smr_input_frame *f, uint3
                                 int32_t mem_kind) { SMR_GUARD(r->impl.preprocess_frame(f, ow, oh, rgba, pitch, mem_kind)) }
 smr_status smr_premultiply_rgba8(smr_renderer *r, const smr_input_frame *f, void *rgba, uint32_t pitch, int32_t mem_kind) {
     SMR_GUARD(r->impl.preprocess_frame(f, 0, 0, rgba, pitch, mem_kind, true))
+}
+smr_status smr_render_text(smr_renderer *r, uint32_t w, uint32_t h, smr_rgba bg, const smr_glyph *glyphs, uint32_t n,
+                           const smr_atlas *mask, const smr_atlas *color, int32_t color_mode, void *rgba, uint32_t pitch, int32_t mem_kind) {
+    SMR_GUARD(r->impl.render_text(w, h, bg, glyphs, n, mask, color, color_mode, rgba, pitch, mem_kind))
 }
 smr_status smr_render(smr_renderer *r, uint64_t pts, const smr_input_frame *in, uint32_t n_in, smr_output_frame *out,
                       uint32_t n_out) {

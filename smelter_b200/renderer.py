@@ -563,6 +563,33 @@ class Renderer:
         self._check(self._lib.smr_premultiply_rgba8(self._h, arr, out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
         return out
 
+    def render_text(self, width: int, height: int, background: "RGBAColor", glyphs: np.ndarray,
+                    mask_atlas: Optional[np.ndarray] = None, color_atlas: Optional[np.ndarray] = None,
+                    color_mode: int = 0) -> np.ndarray:
+        """TextRendererNode::render (transformations/text_renderer.rs:72-167): clear to the text component's background
+        colour, then glyphon's prepared glyph quads (records of _ffi.GLYPH_DTYPE, painter's order) alpha-blended from
+        the mask atlas ((h, w) uint8) / colour atlas ((h, w, 4) uint8).  Returns the (height, width, 4) node texture --
+        a valid FrameData.Rgba8 input.  A zero-sized text texture is one transparent pixel (text_renderer.rs:77-85)."""
+        if width == 0 or height == 0:
+            return np.zeros((1, 1, 4), np.uint8)
+        g = np.ascontiguousarray(glyphs, dtype=np.dtype(F.GLYPH_DTYPE))
+        keep, atl = [], []
+        for a, ch in ((mask_atlas, 1), (color_atlas, 4)):
+            if a is None:
+                atl.append(None)
+                continue
+            a = np.ascontiguousarray(a, np.uint8)
+            assert a.ndim == (2 if ch == 1 else 3) and (ch == 1 or a.shape[2] == 4)
+            keep.append(a)
+            atl.append(F.Atlas(a.ctypes.data, a.shape[1], a.shape[0], 0))
+        out = np.empty((height, width, 4), np.uint8)
+        bg = F.Rgba(background.r, background.g, background.b, background.a)
+        self._check(self._lib.smr_render_text(self._h, width, height, bg, g.ctypes.data if len(g) else None, len(g),
+                                              C.byref(atl[0]) if atl[0] is not None else None,
+                                              C.byref(atl[1]) if atl[1] is not None else None, int(color_mode),
+                                              out.ctypes.data, 0, F.MEM_HOST), RenderSceneError)
+        return out
+
     # -- zero-copy path (device pointers in and out; used by bench.py's `value` leg) ---------------
     def render_raw(self, pts_ns, in_arr, n_in, out_arr, n_out, wait=True):
         st = self._lib.smr_render_begin(self._h, pts_ns, in_arr, n_in, out_arr, n_out)

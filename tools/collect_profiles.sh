@@ -1,7 +1,8 @@
 #!/bin/bash
 # Turns the gpurun_out/ evidence of tools/gpu_final.sh TAG into tracked text artefacts under profiles/.
 TAG=${1:-r02}
-O=profiles
+O=${O:-profiles}   # on the GPU box: O=gpurun_out/profiles (the .ncu-rep files are too big to travel back)
+mkdir -p $O
 for w in cfg3 cfg3b cfg2 cfg4 cfg5 grid25 passthrough; do [ -s gpurun_out/${TAG}_bench_$w.json ] && tail -1 gpurun_out/${TAG}_bench_$w.json > $O/${TAG}_bench_$w.json; done
 [ -s gpurun_out/${TAG}_reference_arm.json ] && tail -1 gpurun_out/${TAG}_reference_arm.json > $O/${TAG}_bench_cfg3_reference_arm.json
 cp gpurun_out/${TAG}_launches_cfg3.csv $O/${TAG}_launches_cfg3.csv 2>/dev/null
@@ -36,10 +37,9 @@ for k, cls in (("fused", "resample_fused"), ("comp", "composite")):
         tr[cls] = int(bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum"))
     except Exception as e:
         print("traffic", k, e)
-p = "profiles/traffic.json"
-d = json.load(open(p))
+d = json.load(open("profiles/traffic.json"))
 d.setdefault("cfg3", {}).update(tr)
-json.dump(d, open(p, "w"), indent=1, sort_keys=True)
+json.dump(d, open("$O/traffic.json", "w"), indent=1, sort_keys=True)
 print("traffic", tr)
 PY
 ls -la $O | grep ${TAG} | awk '{print $5, $9}'

@@ -21,4 +21,8 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_co
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_resample_tma0 -s 6 -c 1 -o gpurun_out/${TAG}_ncu_anyratio_cfg5 -f python bench.py --workload cfg5 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_anyratio.log 2>&1
 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio or tiles_02 or nv12_input or full_range or random_noise or transition_fractional or (box_reduced and 256)" > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${TAG}_memcheck.log
 timeout 500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "integer_ratio or (transition_fractional and 0.5) or (box_reduced and 384 and nv12)" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/${TAG}_racecheck.log
+# the reports are tens of MB each and gpurun_out/ travels back only below 64 MiB: turn them into text here, keep the text
+O=gpurun_out/profiles bash tools/collect_profiles.sh $TAG > gpurun_out/${TAG}_collect.log 2>&1
+rm -f gpurun_out/*.ncu-rep
+du -sh gpurun_out
 echo done
