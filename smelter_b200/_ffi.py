@@ -101,10 +101,6 @@ class RenderLayout(C.Structure):
                 ("masks", Mask * MAX_MASKS)]
 
 
-class Rgba(C.Structure):
-    _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8), ("a", C.c_uint8)]
-
-
 class Atlas(C.Structure):       # smr_atlas
     _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32)]
 
