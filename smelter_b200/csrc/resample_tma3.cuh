@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                     const uint32_t ywd = yw[p >> 1];
                     float2 ny = v5::add2(make_float2(__uint_as_float(__byte_perm(ywd, 0x4B000000u, (p & 1) ? 0x7642 : 0x7640)),
                                                  __uint_as_float(__byte_perm(ywd, 0x4B000000u, (p & 1) ? 0x7643 : 0x7641))), v5::splat(m23));
+#ifdef SMR_EXP_NO_CONV   // what-if build: no K1/K2 arithmetic (bytes -> float only), no decode
+                    prg[2 * p] = make_float2(ny.x, nu.x); prg[2 * p + 1] = make_float2(ny.y, nu.y); pb[2 * p] = nv.x; pb[2 * p + 1] = nv.y;
+                    continue;
+#endif
                     // exact n / 255 and n / (255 * 16): fma(n, c, n * lo)
                     const float c1 = __uint_as_float(0x3b808081u), lo1 = __uint_as_float(0xaf7efeffu);
                     const float c16 = __uint_as_float(0x39808081u), lo16 = __uint_as_float(0xad7efeffu);
@@ -335,16 +339,28 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                     const float2 qr = v5::add2_after_mul(v5::mul2(rr, v5::splat(255.0f)), v5::splat(kMagicRound));
                     const float2 qg = v5::add2_after_mul(v5::mul2(gg, v5::splat(255.0f)), v5::splat(kMagicRound));
                     const float2 qb = v5::add2_after_mul(v5::mul2(bb, v5::splat(255.0f)), v5::splat(kMagicRound));
+#ifdef SMR_EXP_NO_DEC    // what-if build: no sRGB decode lookups
+                    prg[2 * p] = make_float2(qr.x, qg.x); prg[2 * p + 1] = make_float2(qr.y, qg.y); pb[2 * p] = qb.x; pb[2 * p + 1] = qb.y;
+#else
                     prg[2 * p] = make_float2(v5::lds_tab((__float_as_uint(qr.x) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.x) << 7) + kaddr));
                     prg[2 * p + 1] = make_float2(v5::lds_tab((__float_as_uint(qr.y) << 7) + kaddr), v5::lds_tab((__float_as_uint(qg.y) << 7) + kaddr));
                     pb[2 * p] = v5::lds_tab((__float_as_uint(qb.x) << 7) + kaddr);
                     pb[2 * p + 1] = v5::lds_tab((__float_as_uint(qb.y) << 7) + kaddr);
+#endif
                 }
                 // A2: horizontal Lanczos along the warp.  acc j of the lane that owns tap 0 of output OUT * lane + j
                 float2 arg[OUT];          // (r, g)
                 float ab[OUT];            // b
 #pragma unroll
                 for (int j = 0; j < OUT; j++) { arg[j] = make_float2(0.f, 0.f); ab[j] = 0.f; }
+#ifdef SMR_EXP_NO_A2     // what-if build: no horizontal taps -- measures the systolic pass
+#pragma unroll
+                for (int j = 0; j < OUT; j++) {   // every converted pixel stays live, at one add each
+                    arg[j] = prg[j]; ab[j] = pb[j];
+#pragma unroll
+                    for (int i = OUT + j; i < P; i += OUT) { arg[j] = v5::add2(arg[j], prg[i]); ab[j] += pb[i]; }
+                }
+#else
 #pragma unroll
                 for (int s = 0; s < NST; s++) {
 #pragma unroll
@@ -378,6 +394,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                             }
                     }
                 }
+#endif
                 // normalise, quantise to f16 (NC-5) and park the row in the ring: [row][lane][channel][j]
                 {
                     const float inv = c_winv[S];
@@ -399,7 +416,11 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
         // loads refill the stage while the vertical pass runs
         group_sync(grp);
         if (tid == 0) issue(parked->nxt);
+#ifdef SMR_EXP_NO_B      // what-if build (tools/exp_variants.sh): no vertical pass -- measures what phase B costs; output is garbage
+        if (false) {
+#else
         if (cur.last) {
+#endif
             // ---- phase B: vertical pass ------------------------------------------------------------------------------
             const int tv = J.taps_v;
             const float *lbase = ring + lane * 3 * OUT;
