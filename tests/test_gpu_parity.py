@@ -670,3 +670,54 @@ def test_set_layouts_renders_like_the_scene():
     b.set_layouts(OUTPUT_ID, RES, YUV, root, [f"input_{i}" for i in range(1, 4)], ls)
     out = b.render(s.FrameSet(frames=fr, pts=0.0))
     assert_identical([np.asarray(p) for p in out.frames[OUTPUT_ID].data.planes], exp, "flattened path")
+
+
+def test_codec_shaped_device_surfaces():
+    """SURVEY 8f-4 hand-off: NV12 frames as a hardware decoder maps them -- device memory, pitch wider than
+    the row, the interleaved chroma plane `pitch x aligned_height` bytes below the luma plane -- go in as SMR_MEM_DEVICE
+    planes, and the output is written into an encoder-style surface of the same shape.  No host copies (h2d / d2h byte
+    counters stay zero); bytes against the oracle on the same frames."""
+    import ctypes as C
+    import torch
+    from smelter_b200 import _ffi as F
+    from tests.parity import oracle_output
+    w, h, pitch, ah = 1920, 1080, 2048, 1088            # NVDEC: pitch and surface height aligned
+    ow, oh, opitch, oah = 1280, 720, 1536, 736
+    dev = torch.device("cuda:0")
+    fr, surfaces = {}, []
+    arr = (F.InputFrame * 2)()
+    keep = []
+    for i in (1, 2):
+        y, u, v = harness.test_input(i, w, h)
+        fr[f"input_{i}"] = nv12_frame((y, u, v), w, h)
+        surf = torch.zeros((ah * 3 // 2, pitch), dtype=torch.uint8, device=dev)
+        surf[:h, :w] = torch.from_numpy(np.ascontiguousarray(y)).to(dev)
+        surf[ah:ah + h // 2, :w] = torch.from_numpy(np.stack([u, v], axis=-1).reshape(h // 2, w)).to(dev)
+        surfaces.append(surf)
+        b = f"input_{i}".encode()
+        keep.append(b)
+        a = arr[i - 1]
+        a.input_id, a.format, a.width, a.height, a.pts_ns, a.mem_kind = b, F.FRAME_NV12, w, h, 0, F.MEM_DEVICE
+        a.planes[0], a.planes[1] = surf.data_ptr(), surf.data_ptr() + pitch * ah
+        a.pitch[0], a.pitch[1] = pitch, pitch
+    scene = s.TilesComponent(children=streams(2), background_color=BG, margin=4.0)
+    r = TrackedRenderer()
+    for iid in fr:
+        r.register_input(iid)
+    res = s.Resolution(ow, oh)
+    r.update_scene(OUTPUT_ID, res, NV12, scene)
+    osurf = torch.zeros((oah * 3 // 2, opitch), dtype=torch.uint8, device=dev)
+    out = (F.OutputFrame * 1)()
+    ob = OUTPUT_ID.encode()
+    out[0].output_id, out[0].mem_kind = ob, F.MEM_DEVICE
+    out[0].planes[0], out[0].planes[1] = osurf.data_ptr(), osurf.data_ptr() + opitch * oah
+    out[0].pitch[0], out[0].pitch[1] = opitch, opitch
+    torch.cuda.synchronize()
+    r.render_raw(0, arr, 2, out, 1)
+    st = r.stats()
+    assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0, st
+    got_y = osurf[:oh, :ow].cpu().numpy()
+    got_uv = osurf[oah:oah + oh // 2, :ow].cpu().numpy().reshape(oh // 2, ow // 2, 2)
+    exp = oracle_output(r, scene, fr, res, NV12, 0, 0.0)
+    assert_identical((got_y, got_uv), exp, "codec-shaped surfaces")
+    assert not osurf[:oh, ow:].any() and not osurf[oh:oah].any(), "bytes outside the visible planes were written"
