@@ -191,6 +191,8 @@ typedef struct {
     uint64_t kernel_launches;       /* CUDA kernels launched by this handle */
     uint64_t h2d_bytes, d2h_bytes;  /* bytes copied across PCIe by smr_render */
     uint64_t last_render_kernel_launches;
+    uint64_t last_render_direct_tiles;   /* 128 x 16 output tiles of the last tick whose Y / chroma bytes the fused resample
+                                            kernel wrote itself (1:1 opaque child interiors), skipped by the composite */
 } smr_stats;
 
 /* per-kernel-class device time, measured with cudaEvents on the launching stream when profiling is on

@@ -866,6 +866,42 @@ static bool launch_fused_src(int src, const FusedJob *jobs_dev, const FusedPiece
 }  // namespace smr
 namespace smr {
 namespace dev {
+// rgba_to_yuv.wgsl:26-54 on raw stored bytes
+__device__ __forceinline__ float to_y(float r, float g, float b) {
+    float y = fmaf(b, 0.0722f, fmaf(g, 0.7152f, r * 0.2126f));
+    return fmaf(y, 0.85882352941f, K16);
+}
+__device__ __forceinline__ float to_u(float r, float g, float b) {
+    float u = fmaf(b, 0.5f, fmaf(g, -0.3854f, r * -0.1146f));
+    return fmaf(u + 0.5f, 0.87843137254f, K16);
+}
+__device__ __forceinline__ float to_v(float r, float g, float b) {
+    float v = fmaf(b, -0.0458f, fmaf(g, -0.4542f, r * 0.5f));
+    return fmaf(v + 0.5f, 0.87843137254f, K16);
+}
+
+// K10 / K11 of one 2 x 2 block of final target bytes (little-endian RGBA8 words; rgba_to_yuv.wgsl / rgba_to_nv12.wgsl), the
+// very operations of the composite's fused output stage: Y per pixel from the raw bytes, chroma from the exact mean of
+// the four bytes (NC-6u at the .5 / .5 taps of an even-sized target).  (X, Y) even: frame position of the block.
+__device__ __forceinline__ void emit_yuv_2x2(const FusedJob &J, int X, int Y, uint32_t p00, uint32_t p10, uint32_t p01, uint32_t p11) {
+    auto lum = [](uint32_t p) -> unsigned char {
+        return (unsigned char)unorm8(to_y(div255((float)(p & 0xffu), 1.0f), div255((float)((p >> 8) & 0xffu), 1.0f),
+                                          div255((float)((p >> 16) & 0xffu), 1.0f)));
+    };
+    *reinterpret_cast<uchar2 *>(J.out0 + (size_t)Y * J.out_pitch0 + X) = make_uchar2(lum(p00), lum(p10));
+    *reinterpret_cast<uchar2 *>(J.out0 + (size_t)(Y + 1) * J.out_pitch0 + X) = make_uchar2(lum(p01), lum(p11));
+    const float r = div255((float)((p00 & 0xffu) + (p10 & 0xffu) + (p01 & 0xffu) + (p11 & 0xffu)), 0.25f);
+    const float g = div255((float)(((p00 >> 8) & 0xffu) + ((p10 >> 8) & 0xffu) + ((p01 >> 8) & 0xffu) + ((p11 >> 8) & 0xffu)), 0.25f);
+    const float b = div255((float)(((p00 >> 16) & 0xffu) + ((p10 >> 16) & 0xffu) + ((p01 >> 16) & 0xffu) + ((p11 >> 16) & 0xffu)), 0.25f);
+    const unsigned char u = (unsigned char)unorm8(to_u(r, g, b)), v = (unsigned char)unorm8(to_v(r, g, b));
+    if (J.out_format == 4) {   // NV12: texel (X / 2, Y / 2) of the interleaved plane sits at byte X
+        *reinterpret_cast<uchar2 *>(J.out1 + (size_t)(Y >> 1) * J.out_pitch1 + X) = make_uchar2(u, v);
+    } else {
+        J.out1[(size_t)(Y >> 1) * J.out_pitch1 + (X >> 1)] = u;
+        J.out2[(size_t)(Y >> 1) * J.out_pitch2 + (X >> 1)] = v;
+    }
+}
+
 #include "resample_tma.cuh"
 #include "resample_tma3.cuh"
 #include "resample_tma0.cuh"
@@ -1228,20 +1264,6 @@ __device__ __forceinline__ uchar4 blend(const Tables &T, int mode, uchar4 dst, f
     return o;
 }
 
-// rgba_to_yuv.wgsl:26-54 on raw stored bytes
-__device__ __forceinline__ float to_y(float r, float g, float b) {
-    float y = fmaf(b, 0.0722f, fmaf(g, 0.7152f, r * 0.2126f));
-    return fmaf(y, 0.85882352941f, K16);
-}
-__device__ __forceinline__ float to_u(float r, float g, float b) {
-    float u = fmaf(b, 0.5f, fmaf(g, -0.3854f, r * -0.1146f));
-    return fmaf(u + 0.5f, 0.87843137254f, K16);
-}
-__device__ __forceinline__ float to_v(float r, float g, float b) {
-    float v = fmaf(b, -0.0458f, fmaf(g, -0.4542f, r * 0.5f));
-    return fmaf(v + 0.5f, 0.87843137254f, K16);
-}
-
 // general per-pixel path: full fragment shader + fixed-function blend.  Kept out of line: the fast paths of
 // k_composite cover almost every pixel and the instruction cache matters more than the call.
 // true when the rounded-rect alpha of fs_main is provably exactly 1 at this pixel centre: at least `shr`
@@ -1323,6 +1345,9 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     __shared__ unsigned short s_list[MAX_TILE_LAYERS];
     __shared__ int s_count;
     __shared__ LayerDev s_layers[PARAM ? 1 : SM_LAYERS];
+    static_assert(CB_X * CT_W == kDirectTileW && CB_Y * CT_H * CT_ITERS == kDirectTileH, "direct tiles are the block tiles");
+    // the fused resample kernel has written this tile's output bytes already (block-uniform, before any barrier)
+    if (J.direct_map != nullptr && __ldg(J.direct_map + blockIdx.y * J.map_w + blockIdx.x)) return;
     load_tables(T);
     const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H * CT_ITERS);
     const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H * CT_ITERS, J.height);

@@ -93,7 +93,13 @@ struct CompositeJob {
     int32_t out_format;              // smr_output_format, or -1: RGBA8 node texture only
     uint8_t *out0, *out1, *out2;
     int32_t out_pitch0, out_pitch1, out_pitch2;
+    // direct tiles (fused K10/K11 outputs only): direct_map[ty * map_w + tx] != 0 says that tile (128 x 16 pixels) lies
+    // wholly inside the exact 1:1 interior of ONE opaque resampled child with nothing painted over it -- the fused
+    // resample kernel has already written its Y / chroma bytes (FusedJob.direct_map), the composite skips the tile
+    const uint8_t *direct_map;
+    int32_t map_w;
 };
+constexpr int kDirectTileW = 128, kDirectTileH = 16;   // = the composite's block tile (CB_X * CT_W x CB_Y * CT_H)
 
 // one Lanczos pass (resample.wgsl) or box pass (downsample.wgsl)
 struct ResampleJob {
@@ -132,6 +138,16 @@ struct FusedJob {
     int32_t v_same;         // TMA variants: the vertical mapping is the same integer ratio with zero offset (weights = c_wint[S])
     int32_t strip_cols;     // variants 30..33 (any-ratio TMA kernel): output columns per strip of THIS job (<= 64, even)
     const uint8_t *lane_perm;   // variants 30..33: [strip][32] which pair of the strip's columns each lane owns (nullptr: lane l owns pair l)
+    // variants 22 / 24 with v_same: K10 / K11 straight out of the vertical pass.  Where the child is shown 1:1, opaque and
+    // uncovered (the composite's direct tiles, CompositeJob.direct_map), a resampled pixel IS the output frame's pixel:
+    // its Y and the chroma of its 2 x 2 block are written here, from the registers that hold the encoded bytes, and
+    // the composite never reads them back.  (fx, fy): frame position of dst (0, 0), both even; dst_w, dst_h even.
+    const uint8_t *direct_map;  // nullptr: no direct output for this job
+    int32_t map_w;
+    int32_t fx, fy;
+    int32_t out_format;         // 0 planar 4:2:0 (out0 / out1 / out2), 4 NV12 (out0 / out1)
+    uint8_t *out0, *out1, *out2;
+    int32_t out_pitch0, out_pitch1, out_pitch2;
 };
 // a contiguous run of output rows of one 64-column strip of one job; each block of the persistent grid gets an
 // equal share of the launch's rows as a short list of pieces (renderer.cpp: partition_fused)

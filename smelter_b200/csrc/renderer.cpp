@@ -339,8 +339,13 @@ class Renderer {
     uint64_t tick_ = 0;
 
     // per-tick build state (host mirrors; device addresses = base + offset, fixed up before launch)
-    struct PendingComposite { dev::CompositeJob job; size_t layers_off, masks_off; };
+    struct PendingComposite {
+        dev::CompositeJob job; size_t layers_off, masks_off;
+        size_t direct_off = SIZE_MAX;     // param-arena offset of the direct-tile map (SIZE_MAX: none)
+        std::vector<int> direct_owner;    // per tile: the fused job that writes its output bytes, or -1
+    };
     struct PendingCopy { void *dst; size_t dpitch; const void *src; size_t spitch; size_t width, height; };
+    void classify_direct_tiles(PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H);
     std::vector<dev::Tex> tex_table_;
     std::vector<uint8_t> tex_opaque_;  // per table entry: every texel's alpha is 255 by construction
     std::vector<size_t> tex_frame_off_;       // for textures living in the frame arena: offset of p0 (else SIZE_MAX)
@@ -363,6 +368,9 @@ class Renderer {
     bool plane_tmap(const uint8_t *p, int pitch, int w, int h, int kind, CUtensorMap *out);
     std::vector<CUtensorMap> tick_tmaps_;      // three per TMA job
     std::vector<int> fused_tmap_idx_;          // per fused job: first of its three entries in tick_tmaps_, or -1
+    std::vector<size_t> fused_direct_off_;     // per fused job: param-arena offset of the direct-tile map it writes for (SIZE_MAX: none)
+    std::map<int, int> tex_fused_job_;         // texture-table index of a fused resample's output -> its index in fused_jobs_
+    bool direct_k11_ = true;                   // SMR_DIRECT_K11=0: A/B switch, every tile goes through the composite
     bool disable_tma_ = false;                 // SMR_DISABLE_TMA=1: A/B switch back to the LDG-staged kernels
     bool tma_grouped_ = true;                  // SMR_TMA_GROUPED=0: the three-blocks-per-SM form of the TMA kernel
     std::vector<dev::FusedJob> fused_jobs_;
@@ -476,6 +484,7 @@ smr_status Renderer::init() {
     if (opts_.max_layouts_count > 1024) opts_.max_layouts_count = 1024;
     if (opts_.cuda_device == -1) { host_only_ = true; return SMR_OK; }  // scene/layout inspection only
     if (const char *e = getenv("SMR_DISABLE_TMA")) disable_tma_ = e[0] == '1';
+    if (const char *e = getenv("SMR_DIRECT_K11")) direct_k11_ = e[0] != '0';
     if (const char *e = getenv("SMR_TMA_GROUPED")) tma_grouped_ = e[0] != '0';
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -841,10 +850,12 @@ int Renderer::try_fused_resample(Input &in, const AxisMapping &hm_in, const Axis
     if (box && j.variant < 40) return -1;   // no other fused kernel reduces (the arena bytes stay unused this tick): generic passes
     fused_jobs_.push_back(j);
     fused_tmap_idx_.push_back(tmap_idx);
+    fused_direct_off_.push_back(SIZE_MAX);
     fused_src_dst_.push_back({in.raw_tex, dst_off});
     dev::Tex out;
     out.kind = dev::TEX_RGBA8; out.width = dw; out.height = dh; out.pitch0 = dw * 4;
     int idx = (int)tex_table_.size();
+    tex_fused_job_[idx] = (int)fused_jobs_.size() - 1;
     tex_table_.push_back(out);
     tex_opaque_.push_back(1);   // the fused kernel reads YUV and writes alpha 255
     tex_frame_off_.push_back(dst_off);
@@ -1298,6 +1309,78 @@ static void out_plane_layout(int fmt, uint32_t w, uint32_t h, size_t row_bytes[3
 }
 
 // LayoutNode::render (transformations/layout.rs:169-278) + read_outputs (render_loop.rs:59-230) for one output
+// Direct tiles: a composite tile (128 x 16 output pixels) whose TOPMOST intersecting layer is the exact 1:1, opaque
+// interior of a resampled child (FAST_IDENT | FAST_OPAQUE: host-proved, every alpha factor exactly 1) and covers the
+// whole tile shows nothing but that child's texels -- whatever lies below is replaced, nothing lies above.  For such a
+// tile K10 / K11 need only the child's encoded bytes, which the fused resample kernel still holds in registers at the end
+// of its vertical pass: it writes the tile's Y / chroma bytes itself (FusedJob.direct_map) and the composite skips the
+// tile (CompositeJob.direct_map).  Conditions on the job: the grouped TMA kernel with the integer vertical ratio (rows
+// come out in pairs), even frame position and size (chroma blocks), one direct target per job (the first claimant).
+void Renderer::classify_direct_tiles(PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H) {
+    const int TW = dev::kDirectTileW, TH = dev::kDirectTileH;
+    const int tx_n = (W + TW - 1) / TW, ty_n = (H + TH - 1) / TH;
+    const dev::CompositeJob &cj = pc.job;
+    if (cj.out_format != SMR_OUT_NV12 && cj.out_format != SMR_OUT_PLANAR_YUV420) return;
+    if ((cj.out_pitch0 & 1) || ((uintptr_t)cj.out0 & 1) || (cj.out_format == SMR_OUT_NV12 && ((cj.out_pitch1 & 1) || ((uintptr_t)cj.out1 & 1)))) return;
+    // candidate layers: which fused job could serve them
+    std::vector<int> job_of(layers.size(), -1);
+    bool any = false;
+    for (size_t li = 0; li < layers.size(); li++) {
+        const dev::LayerDev &L = layers[li];
+        if (L.type != 0 || (L.fast & (dev::FAST_IDENT | dev::FAST_OPAQUE)) != (dev::FAST_IDENT | dev::FAST_OPAQUE)) continue;
+        auto it = tex_fused_job_.find(L.tex);
+        if (it == tex_fused_job_.end()) continue;
+        const dev::FusedJob &fj = fused_jobs_[it->second];
+        if ((fj.variant != 22 && fj.variant != 24) || !fj.v_same || ((fj.dst_w | fj.dst_h) & 1)) continue;
+        if ((L.tx_off & 1) || (L.ty_off & 1)) continue;   // frame position of texel (0, 0) = (-tx_off, -ty_off)
+        const size_t claimed = fused_direct_off_[it->second];
+        if (claimed != SIZE_MAX && claimed != pc.direct_off) continue;   // serves another output (or an earlier layer) already
+        job_of[li] = it->second;
+        any = true;
+    }
+    if (!any) return;
+    std::vector<int> owner((size_t)tx_n * ty_n, -1);
+    std::vector<int> owner_layer((size_t)tx_n * ty_n, -1);
+    size_t n_direct = 0;
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++) {
+            const int x0 = tx * TW, y0 = ty * TH, x1 = std::min(x0 + TW, W), y1 = std::min(y0 + TH, H);
+            for (int li = (int)layers.size() - 1; li >= 0; li--) {
+                const dev::LayerDev &L = layers[li];
+                if (L.px0 >= x1 || L.px1 <= x0 || L.py0 >= y1 || L.py1 <= y0) continue;   // the composite's own culling test
+                if (job_of[li] >= 0 &&
+                    ((x0 >= L.ix0 && x1 <= L.ix1 && y0 >= L.iy0 && y1 <= L.iy1) || (x0 >= L.jx0 && x1 <= L.jx1 && y0 >= L.jy0 && y1 <= L.jy1))) {
+                    owner[(size_t)ty * tx_n + tx] = job_of[li];
+                    owner_layer[(size_t)ty * tx_n + tx] = li;
+                    n_direct++;
+                }
+                break;   // topmost intersecting layer decides
+            }
+        }
+    if (!n_direct) return;
+    // one layer per job (a texture shown twice 1:1 in the same output would need two frame positions)
+    std::map<int, int> layer_of_job;
+    for (size_t t = 0; t < owner.size(); t++) {
+        if (owner[t] < 0) continue;
+        auto ins = layer_of_job.emplace(owner[t], owner_layer[t]);
+        if (ins.first->second != owner_layer[t]) { owner[t] = -1; n_direct--; }
+    }
+    if (!n_direct) return;
+    pc.direct_off = param_alloc((size_t)tx_n * ty_n);
+    pc.direct_owner = owner;
+    pc.job.map_w = tx_n;
+    for (auto &jl : layer_of_job) {
+        dev::FusedJob &fj = fused_jobs_[jl.first];
+        const dev::LayerDev &L = layers[jl.second];
+        fused_direct_off_[jl.first] = pc.direct_off;
+        fj.map_w = tx_n;
+        fj.fx = -L.tx_off; fj.fy = -L.ty_off;
+        fj.out_format = cj.out_format;
+        fj.out0 = cj.out0; fj.out1 = cj.out1; fj.out2 = cj.out2;
+        fj.out_pitch0 = cj.out_pitch0; fj.out_pitch1 = cj.out_pitch1; fj.out_pitch2 = cj.out_pitch2;
+    }
+}
+
 smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) {
     const int mode = opts_.rendering_mode;
     of.width = (uint32_t)o.res.width; of.height = (uint32_t)o.res.height;
@@ -1522,6 +1605,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
         pc.job.out_format = o.format;
         pc.job.out0 = dst[0]; pc.job.out1 = dst[1]; pc.job.out2 = dst[2];
         pc.job.out_pitch0 = pitch[0]; pc.job.out_pitch1 = pitch[1]; pc.job.out_pitch2 = pitch[2];
+        if (fused_fmt && direct_k11_) classify_direct_tiles(pc, layers, W, H);
         composites_.push_back(pc);
     } else {
         if (o.format == SMR_OUT_RGBA8) { set_error("RGBA output must match the root layout resolution"); return SMR_ERR_UNSUPPORTED; }
@@ -1562,6 +1646,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     tex_table_.clear(); tex_opaque_.clear(); tex_frame_off_.clear();
     for (int s = 0; s < 3; s++) { stage_jobs_[s].clear(); stage_frame_off_[s].clear(); stage_src_tex_[s].clear(); }
     fused_jobs_.clear(); fused_src_dst_.clear(); fused_tmap_idx_.clear(); tick_tmaps_.clear();
+    fused_direct_off_.clear(); tex_fused_job_.clear();
     rollback_weights();   // leftovers of a tick that failed before its weight launch (normally empty)
     weight_jobs_.clear(); convert_jobs_.clear(); composites_.clear(); output_jobs_.clear(); output_src_tex_.clear();
     fills_.clear(); d2h_.clear(); resample_cache_.clear();
@@ -1654,6 +1739,14 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(),
                                  sm_count_ * (v.first >= 30 ? dev::kTma0Groups : 3), pieces, begin, dev::kFusedStripCols, cols.data());
             if (pieces.empty()) continue;
+            // direct tiles: the vertical pass emits K10 / K11 per PAIR of output rows, so a job's pieces must hold whole pairs
+            // (they do whenever every job of the launch has an even height); a job cut at an odd row writes nothing directly
+            for (const dev::FusedPiece &pp : pieces)
+                if (fused_direct_off_[pp.job] != SIZE_MAX && ((pp.oy_begin | pp.oy_end) & 1)) {
+                    fused_direct_off_[pp.job] = SIZE_MAX;
+                    for (PendingComposite &pc : composites_)
+                        for (int &ow : pc.direct_owner) if (ow == pp.job) ow = -1;
+                }
             FusedLaunch fl;
             fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
             fl.pieces_off = param_alloc(sizeof(dev::FusedPiece) * pieces.size());
@@ -1682,6 +1775,19 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             const uint8_t *m = param_dev_[slot_].p + tm_off + sizeof(CUtensorMap) * (size_t)fused_tmap_idx_[i];
             fused_jobs_[i].tm0 = m; fused_jobs_[i].tm1 = m + sizeof(CUtensorMap); fused_jobs_[i].tm2 = m + 2 * sizeof(CUtensorMap);
         }
+    uint64_t direct_tiles = 0;
+    for (PendingComposite &pc : composites_) {   // direct-tile maps: one byte per composite tile
+        if (pc.direct_off == SIZE_MAX) continue;
+        bool any = false;
+        for (int ow : pc.direct_owner) direct_tiles += ow >= 0 ? 1 : 0;
+        for (size_t t = 0; t < pc.direct_owner.size(); t++) {
+            param_host_[pc.direct_off + t] = pc.direct_owner[t] >= 0 ? 1 : 0;
+            any = any || pc.direct_owner[t] >= 0;
+        }
+        pc.job.direct_map = any ? param_dev_[slot_].p + pc.direct_off : nullptr;
+    }
+    for (size_t i = 0; i < fused_jobs_.size(); i++)
+        fused_jobs_[i].direct_map = fused_direct_off_[i] != SIZE_MAX ? param_dev_[slot_].p + fused_direct_off_[i] : nullptr;
     if (!fused_jobs_.empty()) memcpy(param_host_.data() + fj_off, fused_jobs_.data(), sizeof(dev::FusedJob) * fused_jobs_.size());
     {
         uint8_t *pd0 = param_dev_[slot_].p;
@@ -1760,6 +1866,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             CUDA_OK(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, cudaMemcpyDeviceToHost, done_on));
     stats_.kernel_launches += launches;
     stats_.last_render_kernel_launches = launches;
+    stats_.last_render_direct_tiles = direct_tiles;
     stats_.frames_rendered += n_out;
     CUDA_OK(cudaEventRecord(tick_done_[slot_], done_on));
     inflight_.push_back(slot_);

@@ -427,9 +427,8 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
             constexpr int ROWF = K::RROW_BYTES / 4;
             const int row_end = min(cur.o0 + kWarps, cur.oy_end);
             // one output row: encode (NC-4) and store this lane's OUT columns
-            auto finish = [&](const float2 *acc, int oy) {
+            auto finish = [&](const float2 *acc, int oy, uint32_t *px) {
                 const float inv_v = __ldg(J.inv_v + oy);
-                uint32_t px[OUT];
 #pragma unroll
                 for (int j = 0; j < OUT; j++) {
                     const float rv = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
@@ -455,8 +454,22 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                     }
                 }
             };
+            // direct tiles (FusedJob.direct_map): rows oa, oa + 1 are final rows of the output frame -- K10 / K11 of this lane's
+            // 2 x 2 blocks from the encoded bytes still in registers; frame position and sizes are even (host)
+            auto emit = [&](const uint32_t *pa, const uint32_t *pb, int oa) {
+                if (J.direct_map == nullptr) return;
+                const int ncols = min(K::NOUT, J.dst_w - cur.ox0);
+#pragma unroll
+                for (int j = 0; j < OUT; j += 2) {
+                    const int col = OUT * (lane - K::last_stage(j)) + j;
+                    if (col < 0 || col >= ncols) continue;
+                    const int X = J.fx + cur.ox0 + col, Y = J.fy + oa;
+                    if (!__ldg(J.direct_map + (Y / kDirectTileH) * J.map_w + X / kDirectTileW)) continue;
+                    emit_yuv_2x2(J, X, Y, pa[j], pa[j + 1], pb[j], pb[j + 1]);
+                }
+            };
             // one output row the general way: weights from global memory, tap rows clamped to the image
-            auto one_row = [&](int oy) {
+            auto one_row = [&](int oy, uint32_t *px) {
                 const int fv = __ldg(J.first_v + oy);
                 const float *wv = J.w_v + (size_t)oy * tv;
                 float2 acc[3 * OUT / 2];
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
 #pragma unroll
                     for (int k = 0; k < 3 * OUT / 2; k++) acc[k] = v5::fma2(*reinterpret_cast<const float2 *>(p + 2 * k), v5::splat(wt), acc[k]);
                 }
-                finish(acc, oy);
+                finish(acc, oy, px);
             };
             if (J.v_same) {
                 // same integer ratio vertically: rows o and o + 1 share TAPS - S of their TAPS ring rows.  Four warps (one
@@ -499,16 +512,20 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                                 for (int k = 0; k < 3 * OUT / 2; k++) bb2[k] = v5::fma2(v[k], v5::splat(c_wint[S][u >= S ? u - S : 0]), bb2[k]);
                             }
                         }
-                        finish(aa, oa);
-                        finish(bb2, ob);
+                        uint32_t pa[OUT], pb[OUT];
+                        finish(aa, oa, pa);
+                        finish(bb2, ob, pb);
+                        emit(pa, pb, oa);
                     } else {
-                        if (oa < row_end) one_row(oa);
-                        if (ob < row_end) one_row(ob);
+                        uint32_t pa[OUT], pb[OUT];
+                        if (oa < row_end) one_row(oa, pa);
+                        if (ob < row_end) { one_row(ob, pb); emit(pa, pb, oa); }   // pieces of a direct job hold whole row pairs
                     }
                 }
             } else {
                 const int oy = cur.o0 + warp;
-                if (oy < row_end) one_row(oy);
+                uint32_t pz[OUT];
+                if (oy < row_end) one_row(oy, pz);   // no direct output without the integer vertical ratio (host)
             }
             group_sync(grp);   // the ring rows this pass read may be overwritten by the next step's horizontal pass
         }

@@ -721,3 +721,43 @@ def test_codec_shaped_device_surfaces():
     exp = oracle_output(r, scene, fr, res, NV12, 0, 0.0)
     assert_identical((got_y, got_uv), exp, "codec-shaped surfaces")
     assert not osurf[:oh, ow:].any() and not osurf[oh:oah].any(), "bytes outside the visible planes were written"
+
+
+@pytest.mark.parametrize("fmt", [NV12, YUV])
+@pytest.mark.parametrize("ratio", [2, 4])
+def test_direct_tiles_match_the_composite_path(fmt, ratio, monkeypatch):
+    """Output tiles that lie wholly inside the 1:1 opaque interior of ONE resampled child (nothing painted over them) get
+    their Y / chroma bytes straight from the vertical pass of the fused resample kernel (FusedJob.direct_map) and are
+    skipped by the composite.  Same scene with SMR_DIRECT_K11=0 (every tile through the composite): identical planes;
+    both equal the oracle.  Rounded corners, a translucent overlay and a second, scaled-down showing of an input keep
+    plenty of tiles on the composite path next to the direct ones."""
+    ow, oh = 1280, 720
+    iw, ih = ow // 2 * ratio, oh // 2 * ratio
+    fr = {f"input_{i}": (nv12_frame if i % 2 else yuv_frame)(harness.test_input(i, iw, ih), iw, ih) for i in range(1, 5)}
+    kids = [s.RescalerComponent(child=c, border_radius=s.BorderRadius.new_with_radius(20.0)) for c in streams(4)]
+    overlay = V(position=s.Position.Absolute(width=500.0, height=90.0, left=390.0, bottom=40.0),
+                background_color=s.RGBAColor(16, 32, 160, 112), border_radius=s.BorderRadius.new_with_radius(24.0))
+    pip = s.RescalerComponent(position=s.Position.Absolute(width=160.0, height=90.0, right=16.0, top=16.0),
+                              child=s.InputStreamComponent(input_id="input_2"))
+    scene = V(background_color=BG, children=[s.TilesComponent(children=kids, background_color=BG), overlay, pip])
+    res = s.Resolution(ow, oh)
+    got, exp, r = run_case(scene, fr, resolution=res, out_format=fmt)
+    assert_identical(got, exp, "direct tiles")
+    n_direct = r.stats()["last_render_direct_tiles"]
+    assert n_direct > 100, n_direct                     # 1280 x 720 = 10 x 45 tiles, most of them inside a child
+    monkeypatch.setenv("SMR_DIRECT_K11", "0")
+    got0, _, r0 = run_case(scene, fr, resolution=res, out_format=fmt)
+    assert r0.stats()["last_render_direct_tiles"] == 0
+    assert_identical(got0, got, "composite path vs direct tiles")
+
+
+def test_direct_tiles_need_even_positions():
+    """a child at an odd frame position cannot share 2 x 2 chroma blocks with the frame: its tiles stay with the composite,
+    the child at an even position next to it is written directly; bytes as the oracle's either way"""
+    fr = inputs(2, 1280, 720)
+    a = s.RescalerComponent(position=s.Position.Absolute(width=640.0, height=360.0, left=3.0, top=5.0), child=streams(2)[0])
+    b = s.RescalerComponent(position=s.Position.Absolute(width=640.0, height=360.0, left=644.0, top=366.0), child=streams(2)[1])
+    got, exp, r = run_case(V(background_color=BG, children=[a, b]), fr, resolution=s.Resolution(1286, 730))
+    assert_identical(got, exp, "odd and even positions")
+    n = r.stats()["last_render_direct_tiles"]
+    assert 40 <= n <= 5 * 23, n                         # only b's interior: at most 640 / 128 x 360 / 16 tiles
