@@ -884,16 +884,24 @@ __device__ __forceinline__ float to_v(float r, float g, float b) {
 // very operations of the composite's fused output stage: Y per pixel from the raw bytes, chroma from the exact mean of
 // the four bytes (NC-6u at the .5 / .5 taps of an even-sized target).  (X, Y) even: frame position of the block.
 __device__ __forceinline__ void emit_yuv_2x2(const FusedJob &J, int X, int Y, uint32_t p00, uint32_t p10, uint32_t p01, uint32_t p11) {
-    auto lum = [](uint32_t p) -> unsigned char {
-        return (unsigned char)unorm8(to_y(div255((float)(p & 0xffu), 1.0f), div255((float)((p >> 8) & 0xffu), 1.0f),
-                                          div255((float)((p >> 16) & 0xffu), 1.0f)));
+    // no conversion unit (I2F / F2I run at a fraction of the FP32 rate): a byte or 16-bit field goes under the exponent of
+    // 2^23 by PRMT and 2^23 is subtracted (exact); the UNORM8 store rounds by the magic add (== __float2int_rn below 2^22)
+    auto byte_f = [](uint32_t p, uint32_t sel) { return __uint_as_float(__byte_perm(p, 0x4B000000u, sel)) - 8388608.0f; };
+    auto store8 = [](float x) -> unsigned char {   // unorm8(): rint(clamp01(x) * 255)
+        const float t = __saturatef(x) * 255.0f;
+        return (unsigned char)(__float_as_uint(t + 12582912.0f) & 0xffu);
+    };
+    auto lum = [&](uint32_t p) -> unsigned char {
+        return store8(to_y(div255(byte_f(p, 0x7540u), 1.0f), div255(byte_f(p, 0x7541u), 1.0f), div255(byte_f(p, 0x7542u), 1.0f)));
     };
     *reinterpret_cast<uchar2 *>(J.out0 + (size_t)Y * J.out_pitch0 + X) = make_uchar2(lum(p00), lum(p10));
     *reinterpret_cast<uchar2 *>(J.out0 + (size_t)(Y + 1) * J.out_pitch0 + X) = make_uchar2(lum(p01), lum(p11));
-    const float r = div255((float)((p00 & 0xffu) + (p10 & 0xffu) + (p01 & 0xffu) + (p11 & 0xffu)), 0.25f);
-    const float g = div255((float)(((p00 >> 8) & 0xffu) + ((p10 >> 8) & 0xffu) + ((p01 >> 8) & 0xffu) + ((p11 >> 8) & 0xffu)), 0.25f);
-    const float b = div255((float)(((p00 >> 16) & 0xffu) + ((p10 >> 16) & 0xffu) + ((p01 >> 16) & 0xffu) + ((p11 >> 16) & 0xffu)), 0.25f);
-    const unsigned char u = (unsigned char)unorm8(to_u(r, g, b)), v = (unsigned char)unorm8(to_v(r, g, b));
+    // sums of the four bytes per channel, two channels per word: (r, b) in the 16-bit halves of one, (g, a) of the other
+    const uint32_t m = 0x00ff00ffu;
+    const uint32_t srb = (p00 & m) + (p10 & m) + (p01 & m) + (p11 & m);
+    const uint32_t sga = ((p00 >> 8) & m) + ((p10 >> 8) & m) + ((p01 >> 8) & m) + ((p11 >> 8) & m);
+    const float r = div255(byte_f(srb, 0x7610u), 0.25f), g = div255(byte_f(sga, 0x7610u), 0.25f), b = div255(byte_f(srb, 0x7632u), 0.25f);
+    const unsigned char u = store8(to_u(r, g, b)), v = store8(to_v(r, g, b));
     if (J.out_format == 4) {   // NV12: texel (X / 2, Y / 2) of the interleaved plane sits at byte X
         *reinterpret_cast<uchar2 *>(J.out1 + (size_t)(Y >> 1) * J.out_pitch1 + X) = make_uchar2(u, v);
     } else {
@@ -1347,9 +1355,14 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     __shared__ LayerDev s_layers[PARAM ? 1 : SM_LAYERS];
     static_assert(CB_X * CT_W == kDirectTileW && CB_Y * CT_H * CT_ITERS == kDirectTileH, "direct tiles are the block tiles");
     // the fused resample kernel has written this tile's output bytes already (block-uniform, before any barrier)
-    if (J.direct_map != nullptr && __ldg(J.direct_map + blockIdx.y * J.map_w + blockIdx.x)) return;
+    int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    if (J.tile_list != nullptr) {   // compacted launch: the direct tiles have no block at all
+        if ((int)blockIdx.x >= J.n_tiles || blockIdx.y != 0) return;
+        const uint32_t t = __ldg(J.tile_list + blockIdx.x);
+        tile_x = (int)(t & 0xffffu); tile_y = (int)(t >> 16);
+    } else if (J.direct_map != nullptr && __ldg(J.direct_map + tile_y * J.map_w + tile_x)) return;
     load_tables(T);
-    const int tile_x0 = blockIdx.x * (CB_X * CT_W), tile_y0 = blockIdx.y * (CB_Y * CT_H * CT_ITERS);
+    const int tile_x0 = tile_x * (CB_X * CT_W), tile_y0 = tile_y * (CB_Y * CT_H * CT_ITERS);
     const int tile_x1 = min(tile_x0 + CB_X * CT_W, J.width), tile_y1 = min(tile_y0 + CB_Y * CT_H * CT_ITERS, J.height);
     // per-tile layer culling, painter's order preserved.  One layer per thread (a serial loop over the layer
     // list costs one dependent global-load latency per layer while the whole block waits), ordered compaction
@@ -1753,7 +1766,8 @@ __global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_multi(const Composi
         if (tid < (int)(sizeof(CompositeJob) / 4)) reinterpret_cast<unsigned int *>(&J)[tid] = __ldg(src + tid);
     }
     __syncthreads();
-    if ((int)blockIdx.x * (CB_X * CT_W) >= J.width || (int)blockIdx.y * (CB_Y * CT_H * CT_ITERS) >= J.height) return;
+    if (J.tile_list == nullptr &&
+        ((int)blockIdx.x * (CB_X * CT_W) >= J.width || (int)blockIdx.y * (CB_Y * CT_H * CT_ITERS) >= J.height)) return;
     composite_body<false>(J, J.layers);
 }
 
@@ -1761,6 +1775,7 @@ int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *job
     static_assert(sizeof(CompositeJob) % 4 == 0 && sizeof(CompositeJob) / 4 <= CB_X * CB_Y, "job copied by one block pass");
     int gx = 0, gy = 0;
     for (int i = 0; i < n; i++) {
+        if (jobs_host[i].tile_list != nullptr) { gx = max(gx, jobs_host[i].n_tiles); gy = max(gy, jobs_host[i].n_tiles > 0 ? 1 : 0); continue; }
         gx = max(gx, (jobs_host[i].width + CB_X * CT_W - 1) / (CB_X * CT_W));
         gy = max(gy, (jobs_host[i].height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
     }
@@ -1771,6 +1786,10 @@ int launch_composite_multi(const CompositeJob *jobs_dev, const CompositeJob *job
 
 int launch_composite(const CompositeJob &job, Stream s) {
     dim3 b(CB_X, CB_Y), g((job.width + CB_X * CT_W - 1) / (CB_X * CT_W), (job.height + CB_Y * CT_H * CT_ITERS - 1) / (CB_Y * CT_H * CT_ITERS));
+    if (job.tile_list != nullptr) {
+        if (job.n_tiles <= 0) return 0;   // every tile of the frame was written by the resample kernel
+        g = dim3(job.n_tiles, 1);
+    }
     if (job.n_layers <= PARAM_LAYERS && job.layers_host != nullptr) {
         CompositeParams P;   // ~26 KB on the host stack; the driver copies the parameter block at launch
         P.job = job;

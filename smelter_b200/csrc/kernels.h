@@ -93,11 +93,15 @@ struct CompositeJob {
     int32_t out_format;              // smr_output_format, or -1: RGBA8 node texture only
     uint8_t *out0, *out1, *out2;
     int32_t out_pitch0, out_pitch1, out_pitch2;
-    // direct tiles (fused K10/K11 outputs only): direct_map[ty * map_w + tx] != 0 says that tile (128 x 16 pixels) lies
+    // direct tiles (fused K10/K11 outputs only): direct_map[ty * map_w + tx] != 0 (the owner's FusedJob.direct_id) says that tile (128 x 16 pixels) lies
     // wholly inside the exact 1:1 interior of ONE opaque resampled child with nothing painted over it -- the fused
     // resample kernel has already written its Y / chroma bytes (FusedJob.direct_map), the composite skips the tile
     const uint8_t *direct_map;
     int32_t map_w;
+    // with direct tiles in the tick the launch covers only the tiles that are left: block b works on tile
+    // (tile_list[b] & 0xffff, tile_list[b] >> 16), row-major order; nullptr: block (x, y) = tile (x, y)
+    const uint32_t *tile_list;
+    int32_t n_tiles;
 };
 constexpr int kDirectTileW = 128, kDirectTileH = 16;   // = the composite's block tile (CB_X * CT_W x CB_Y * CT_H)
 
@@ -142,7 +146,8 @@ struct FusedJob {
     // uncovered (the composite's direct tiles, CompositeJob.direct_map), a resampled pixel IS the output frame's pixel:
     // its Y and the chroma of its 2 x 2 block are written here, from the registers that hold the encoded bytes, and
     // the composite never reads them back.  (fx, fy): frame position of dst (0, 0), both even; dst_w, dst_h even.
-    const uint8_t *direct_map;  // nullptr: no direct output for this job
+    const uint8_t *direct_map;  // nullptr: no direct output for this job; else tile (tx, ty) is this job's iff the byte == direct_id
+    int32_t direct_id;          // 1 .. 255 (children may overlap in the frame: a tile belongs to the topmost one only)
     int32_t map_w;
     int32_t fx, fy;
     int32_t out_format;         // 0 planar 4:2:0 (out0 / out1 / out2), 4 NV12 (out0 / out1)

@@ -1333,6 +1333,7 @@ void Renderer::classify_direct_tiles(PendingComposite &pc, const std::vector<dev
         const dev::FusedJob &fj = fused_jobs_[it->second];
         if ((fj.variant != 22 && fj.variant != 24) || !fj.v_same || ((fj.dst_w | fj.dst_h) & 1)) continue;
         if ((L.tx_off & 1) || (L.ty_off & 1)) continue;   // frame position of texel (0, 0) = (-tx_off, -ty_off)
+        if (it->second >= 255) continue;   // the map holds the owner as one byte
         const size_t claimed = fused_direct_off_[it->second];
         if (claimed != SIZE_MAX && claimed != pc.direct_off) continue;   // serves another output (or an earlier layer) already
         job_of[li] = it->second;
@@ -1374,6 +1375,7 @@ void Renderer::classify_direct_tiles(PendingComposite &pc, const std::vector<dev
         const dev::LayerDev &L = layers[jl.second];
         fused_direct_off_[jl.first] = pc.direct_off;
         fj.map_w = tx_n;
+        fj.direct_id = jl.first + 1;
         fj.fx = -L.tx_off; fj.fy = -L.ty_off;
         fj.out_format = cj.out_format;
         fj.out0 = cj.out0; fj.out1 = cj.out1; fj.out2 = cj.out2;
@@ -1764,6 +1766,34 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             memcpy(param_host_.data() + stage_off[s], stage_jobs_[s].data(), sizeof(dev::ResampleJob) * stage_jobs_[s].size());
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
     if (!tick_tmaps_.empty()) memcpy(param_host_.data() + tm_off, tick_tmaps_.data(), sizeof(CUtensorMap) * tick_tmaps_.size());
+    uint64_t direct_tiles = 0;
+    for (PendingComposite &pc : composites_) {   // direct-tile maps: one byte per composite tile
+        if (pc.direct_off == SIZE_MAX) continue;
+        bool any = false;
+        for (int ow : pc.direct_owner) direct_tiles += ow >= 0 ? 1 : 0;
+        for (size_t t = 0; t < pc.direct_owner.size(); t++) {
+            param_host_[pc.direct_off + t] = pc.direct_owner[t] >= 0 ? (uint8_t)(pc.direct_owner[t] + 1) : 0;
+            any = any || pc.direct_owner[t] >= 0;
+        }
+        if (!any) pc.direct_off = SIZE_MAX;
+    }
+    if (direct_tiles) {
+        // compacted composite launch: one block per tile that is left (row-major), for every output of the tick (they share
+        // one launch); a direct tile costs nothing, not even an empty block
+        for (PendingComposite &pc : composites_) {
+            const int tx_n = (pc.job.width + dev::kDirectTileW - 1) / dev::kDirectTileW, ty_n = (pc.job.height + dev::kDirectTileH - 1) / dev::kDirectTileH;
+            std::vector<uint32_t> list;
+            list.reserve((size_t)tx_n * ty_n);
+            for (int ty = 0; ty < ty_n; ty++)
+                for (int tx = 0; tx < tx_n; tx++)
+                    if (pc.direct_off == SIZE_MAX || pc.direct_owner[(size_t)ty * tx_n + tx] < 0) list.push_back((uint32_t)tx | ((uint32_t)ty << 16));
+            const size_t off = param_alloc(sizeof(uint32_t) * std::max<size_t>(list.size(), 1));
+            if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
+            if (!list.empty()) memcpy(param_host_.data() + off, list.data(), sizeof(uint32_t) * list.size());
+            pc.job.tile_list = (const uint32_t *)(uintptr_t)off;   // arena offset for now: the arena may still grow
+            pc.job.n_tiles = (int)list.size();
+        }
+    }
     // composite jobs: their device pointers are known once the arena is sized; with two or more outputs in the tick
     // the jobs travel in the arena and run as ONE launch
     const size_t cj_off = param_alloc(sizeof(dev::CompositeJob) * std::max<size_t>(composites_.size(), 1));
@@ -1775,16 +1805,9 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             const uint8_t *m = param_dev_[slot_].p + tm_off + sizeof(CUtensorMap) * (size_t)fused_tmap_idx_[i];
             fused_jobs_[i].tm0 = m; fused_jobs_[i].tm1 = m + sizeof(CUtensorMap); fused_jobs_[i].tm2 = m + 2 * sizeof(CUtensorMap);
         }
-    uint64_t direct_tiles = 0;
-    for (PendingComposite &pc : composites_) {   // direct-tile maps: one byte per composite tile
-        if (pc.direct_off == SIZE_MAX) continue;
-        bool any = false;
-        for (int ow : pc.direct_owner) direct_tiles += ow >= 0 ? 1 : 0;
-        for (size_t t = 0; t < pc.direct_owner.size(); t++) {
-            param_host_[pc.direct_off + t] = pc.direct_owner[t] >= 0 ? 1 : 0;
-            any = any || pc.direct_owner[t] >= 0;
-        }
-        pc.job.direct_map = any ? param_dev_[slot_].p + pc.direct_off : nullptr;
+    for (PendingComposite &pc : composites_) {   // arena offsets -> device pointers
+        pc.job.direct_map = pc.direct_off != SIZE_MAX ? param_dev_[slot_].p + pc.direct_off : nullptr;
+        if (direct_tiles) pc.job.tile_list = (const uint32_t *)(param_dev_[slot_].p + (size_t)(uintptr_t)pc.job.tile_list);
     }
     for (size_t i = 0; i < fused_jobs_.size(); i++)
         fused_jobs_[i].direct_map = fused_direct_off_[i] != SIZE_MAX ? param_dev_[slot_].p + fused_direct_off_[i] : nullptr;

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                     const int col = OUT * (lane - K::last_stage(j)) + j;
                     if (col < 0 || col >= ncols) continue;
                     const int X = J.fx + cur.ox0 + col, Y = J.fy + oa;
-                    if (!__ldg(J.direct_map + (Y / kDirectTileH) * J.map_w + X / kDirectTileW)) continue;
+                    if ((int)__ldg(J.direct_map + (Y / kDirectTileH) * J.map_w + X / kDirectTileW) != J.direct_id) continue;
                     emit_yuv_2x2(J, X, Y, pa[j], pa[j + 1], pb[j], pb[j + 1]);
                 }
             };
