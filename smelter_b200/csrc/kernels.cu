@@ -1330,6 +1330,9 @@ __device__ __noinline__ uchar4 shade_blend(const Tables &T, const CompositeJob &
     return pass ? texel : blend(T, J.mode, dst, src);
 }
 
+#ifndef SMR_COMPOSITE_BLOCKS
+#define SMR_COMPOSITE_BLOCKS 3   // resident blocks per SM the composite kernels are compiled for
+#endif
 #define CT_W 4           // pixels per thread, x
 #define CT_H 2           // pixels per thread, y
 #define CB_X 32          // threads per block, x
@@ -1751,14 +1754,14 @@ __device__ __forceinline__ void composite_body(const CompositeJob &J, const Laye
     }  // it
 }
 
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_p(const __grid_constant__ CompositeParams P) {
+__global__ void __launch_bounds__(CB_X *CB_Y, SMR_COMPOSITE_BLOCKS) k_composite(CompositeJob J) { composite_body<false>(J, J.layers); }
+__global__ void __launch_bounds__(CB_X *CB_Y, SMR_COMPOSITE_BLOCKS) k_composite_p(const __grid_constant__ CompositeParams P) {
     composite_body<true>(P.job, P.layers);
 }
 
 // all outputs of a tick in one launch (blockIdx.z = output): a 1080p frame alone is 2.3 waves of 444 resident
 // blocks, eight of them back to back are 18.4 -- the per-launch tails disappear
-__global__ void __launch_bounds__(CB_X *CB_Y, 3) k_composite_multi(const CompositeJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(CB_X *CB_Y, SMR_COMPOSITE_BLOCKS) k_composite_multi(const CompositeJob *__restrict__ jobs) {
     __shared__ CompositeJob J;
     {
         const int tid = threadIdx.y * CB_X + threadIdx.x;

@@ -290,6 +290,12 @@ class Renderer {
                                                 // tick k runs on its own stream while tick k + 1 composes into the next set
         // smr_set_layouts: the caller flattened the scene itself (the reference's scene/** stays in Rust); used instead
         // of `node` until the next smr_update_scene of this output
+        // tile plan of the composite (direct-tile owners + cost-sorted list of the tiles that are left), kept while the
+        // flattened layers and the resamples feeding them stay the same (a static scene plans once)
+        uint64_t tile_key = 0;
+        bool tile_key_valid = false;
+        std::vector<int> tile_owner_layer;       // per tile: index of the layer whose child is shown there 1:1 and alone, or -1
+        std::vector<uint32_t> tile_list;         // tiles that are left for the composite, most expensive first
         bool flat = false;
         Resolution flat_root;
         std::vector<std::string> flat_children;
@@ -343,9 +349,11 @@ class Renderer {
         dev::CompositeJob job; size_t layers_off, masks_off;
         size_t direct_off = SIZE_MAX;     // param-arena offset of the direct-tile map (SIZE_MAX: none)
         std::vector<int> direct_owner;    // per tile: the fused job that writes its output bytes, or -1
+        bool use_list = false;            // compacted launch over `list` (tiles left for the composite, most expensive first)
+        std::vector<uint32_t> list;
     };
     struct PendingCopy { void *dst; size_t dpitch; const void *src; size_t spitch; size_t width, height; };
-    void classify_direct_tiles(PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H);
+    void plan_tiles(Output &o, PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H);
     std::vector<dev::Tex> tex_table_;
     std::vector<uint8_t> tex_opaque_;  // per table entry: every texel's alpha is 255 by construction
     std::vector<size_t> tex_frame_off_;       // for textures living in the frame arena: offset of p0 (else SIZE_MAX)
@@ -371,6 +379,7 @@ class Renderer {
     std::vector<size_t> fused_direct_off_;     // per fused job: param-arena offset of the direct-tile map it writes for (SIZE_MAX: none)
     std::map<int, int> tex_fused_job_;         // texture-table index of a fused resample's output -> its index in fused_jobs_
     bool direct_k11_ = true;                   // SMR_DIRECT_K11=0: A/B switch, every tile goes through the composite
+    bool tile_sort_ = true;                    // SMR_TILE_SORT=0: the compacted composite launch keeps row-major order
     bool disable_tma_ = false;                 // SMR_DISABLE_TMA=1: A/B switch back to the LDG-staged kernels
     bool tma_grouped_ = true;                  // SMR_TMA_GROUPED=0: the three-blocks-per-SM form of the TMA kernel
     std::vector<dev::FusedJob> fused_jobs_;
@@ -485,6 +494,7 @@ smr_status Renderer::init() {
     if (opts_.cuda_device == -1) { host_only_ = true; return SMR_OK; }  // scene/layout inspection only
     if (const char *e = getenv("SMR_DISABLE_TMA")) disable_tma_ = e[0] == '1';
     if (const char *e = getenv("SMR_DIRECT_K11")) direct_k11_ = e[0] != '0';
+    if (const char *e = getenv("SMR_TILE_SORT")) tile_sort_ = e[0] != '0';
     if (const char *e = getenv("SMR_TMA_GROUPED")) tma_grouped_ = e[0] != '0';
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -1309,68 +1319,104 @@ static void out_plane_layout(int fmt, uint32_t w, uint32_t h, size_t row_bytes[3
 }
 
 // LayoutNode::render (transformations/layout.rs:169-278) + read_outputs (render_loop.rs:59-230) for one output
+// Tile plan of a composite with fused K10 / K11 output.
+//
 // Direct tiles: a composite tile (128 x 16 output pixels) whose TOPMOST intersecting layer is the exact 1:1, opaque
 // interior of a resampled child (FAST_IDENT | FAST_OPAQUE: host-proved, every alpha factor exactly 1) and covers the
 // whole tile shows nothing but that child's texels -- whatever lies below is replaced, nothing lies above.  For such a
 // tile K10 / K11 need only the child's encoded bytes, which the fused resample kernel still holds in registers at the end
 // of its vertical pass: it writes the tile's Y / chroma bytes itself (FusedJob.direct_map) and the composite skips the
-// tile (CompositeJob.direct_map).  Conditions on the job: the grouped TMA kernel with the integer vertical ratio (rows
-// come out in pairs), even frame position and size (chroma blocks), one direct target per job (the first claimant).
-void Renderer::classify_direct_tiles(PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H) {
+// tile.  Conditions on the job: the grouped TMA kernel with the integer vertical ratio (rows come out in pairs), even
+// frame position and size (chroma blocks), one direct target per job (the first claimant).
+//
+// Tile list: the composite is launched over the tiles that are left, one block each, MOST EXPENSIVE FIRST.  Those tiles are
+// few (2 - 3 waves of resident blocks in the BASELINE grids) and uneven -- edges, corners, overlays and shadows take the
+// general fragment path, interiors do not -- so in row-major order the launch ends on whatever heavy tiles come last while
+// most SMs idle; longest-first leaves a tail of cheap tiles.  Cost estimate per intersecting layer: 1 when the tile lies
+// in one of the layer's exact-interior bars, 8 when some of its pixels run the fragment path.
+//
+// The plan depends only on the flattened layers and on which fused job feeds each of them: it is cached per output.
+static inline void fnv1a(uint64_t &h, const void *p, size_t n) {
+    const uint8_t *b = (const uint8_t *)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+}
+void Renderer::plan_tiles(Output &o, PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H) {
     const int TW = dev::kDirectTileW, TH = dev::kDirectTileH;
     const int tx_n = (W + TW - 1) / TW, ty_n = (H + TH - 1) / TH;
+    if (tx_n > 0xffff || ty_n > 0xffff) return;
     const dev::CompositeJob &cj = pc.job;
-    if (cj.out_format != SMR_OUT_NV12 && cj.out_format != SMR_OUT_PLANAR_YUV420) return;
-    if ((cj.out_pitch0 & 1) || ((uintptr_t)cj.out0 & 1) || (cj.out_format == SMR_OUT_NV12 && ((cj.out_pitch1 & 1) || ((uintptr_t)cj.out1 & 1)))) return;
-    // candidate layers: which fused job could serve them
+    bool direct_ok = direct_k11_ && (cj.out_format == SMR_OUT_NV12 || cj.out_format == SMR_OUT_PLANAR_YUV420);
+    if ((cj.out_pitch0 & 1) || ((uintptr_t)cj.out0 & 1) || (cj.out_format == SMR_OUT_NV12 && ((cj.out_pitch1 & 1) || ((uintptr_t)cj.out1 & 1)))) direct_ok = false;
+    // which fused job could serve each layer
     std::vector<int> job_of(layers.size(), -1);
+    if (direct_ok)
+        for (size_t li = 0; li < layers.size(); li++) {
+            const dev::LayerDev &L = layers[li];
+            if (L.type != 0 || (L.fast & (dev::FAST_IDENT | dev::FAST_OPAQUE)) != (dev::FAST_IDENT | dev::FAST_OPAQUE)) continue;
+            auto it = tex_fused_job_.find(L.tex);
+            if (it == tex_fused_job_.end() || it->second >= 255) continue;   // the map holds the owner as one byte
+            const dev::FusedJob &fj = fused_jobs_[it->second];
+            if ((fj.variant != 22 && fj.variant != 24) || !fj.v_same || ((fj.dst_w | fj.dst_h) & 1)) continue;
+            if ((L.tx_off & 1) || (L.ty_off & 1)) continue;   // frame position of texel (0, 0) = (-tx_off, -ty_off)
+            if (fused_direct_off_[it->second] != SIZE_MAX) continue;   // serves another output (or an earlier layer) already
+            job_of[li] = it->second;
+        }
+    uint64_t key = 1469598103934665603ull;
+    fnv1a(key, &W, sizeof(W)); fnv1a(key, &H, sizeof(H));
+    if (!layers.empty()) fnv1a(key, layers.data(), sizeof(dev::LayerDev) * layers.size());
+    if (!job_of.empty()) fnv1a(key, job_of.data(), sizeof(int) * job_of.size());
+    const size_t n_tiles = (size_t)tx_n * ty_n;
+    if (!(o.tile_key_valid && o.tile_key == key && o.tile_owner_layer.size() == n_tiles)) {
+        o.tile_owner_layer.assign(n_tiles, -1);
+        std::vector<std::pair<int, uint32_t>> keyed;
+        keyed.reserve(n_tiles);
+        std::map<int, int> layer_of_job;   // one layer per job (a texture shown twice 1:1 would need two frame positions)
+        for (int ty = 0; ty < ty_n; ty++)
+            for (int tx = 0; tx < tx_n; tx++) {
+                const int x0 = tx * TW, y0 = ty * TH, x1 = std::min(x0 + TW, W), y1 = std::min(y0 + TH, H);
+                int cost = 0;
+                bool top = true;
+                int owner = -1;
+                for (int li = (int)layers.size() - 1; li >= 0; li--) {
+                    const dev::LayerDev &L = layers[li];
+                    if (L.px0 >= x1 || L.px1 <= x0 || L.py0 >= y1 || L.py1 <= y0) continue;   // the composite's own culling test
+                    const bool in = (x0 >= L.ix0 && x1 <= L.ix1 && y0 >= L.iy0 && y1 <= L.iy1) || (x0 >= L.jx0 && x1 <= L.jx1 && y0 >= L.jy0 && y1 <= L.jy1);
+                    if (top) {   // the topmost intersecting layer decides about a direct tile
+                        top = false;
+                        if (in && job_of[li] >= 0) {
+                            auto ins = layer_of_job.emplace(job_of[li], li);
+                            if (ins.first->second == li) { owner = li; break; }
+                        }
+                    }
+                    cost += in ? 1 : 8;
+                    if (in && (L.fast & dev::FAST_OPAQUE)) break;   // the kernel's occlusion start: nothing below is evaluated
+                }
+                if (owner >= 0) o.tile_owner_layer[(size_t)ty * tx_n + tx] = owner;
+                else keyed.push_back({-cost, (uint32_t)tx | ((uint32_t)ty << 16)});
+            }
+        if (tile_sort_)
+            std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, uint32_t> &a, const std::pair<int, uint32_t> &b) { return a.first < b.first; });
+        o.tile_list.resize(keyed.size());
+        for (size_t k = 0; k < keyed.size(); k++) o.tile_list[k] = keyed[k].second;
+        o.tile_key = key; o.tile_key_valid = true;
+    }
+    pc.use_list = true;
+    pc.list = o.tile_list;
+    pc.job.map_w = tx_n;
+    // claim the fused jobs of the direct tiles
+    std::map<int, int> claimed;   // job -> layer
     bool any = false;
-    for (size_t li = 0; li < layers.size(); li++) {
-        const dev::LayerDev &L = layers[li];
-        if (L.type != 0 || (L.fast & (dev::FAST_IDENT | dev::FAST_OPAQUE)) != (dev::FAST_IDENT | dev::FAST_OPAQUE)) continue;
-        auto it = tex_fused_job_.find(L.tex);
-        if (it == tex_fused_job_.end()) continue;
-        const dev::FusedJob &fj = fused_jobs_[it->second];
-        if ((fj.variant != 22 && fj.variant != 24) || !fj.v_same || ((fj.dst_w | fj.dst_h) & 1)) continue;
-        if ((L.tx_off & 1) || (L.ty_off & 1)) continue;   // frame position of texel (0, 0) = (-tx_off, -ty_off)
-        if (it->second >= 255) continue;   // the map holds the owner as one byte
-        const size_t claimed = fused_direct_off_[it->second];
-        if (claimed != SIZE_MAX && claimed != pc.direct_off) continue;   // serves another output (or an earlier layer) already
-        job_of[li] = it->second;
+    pc.direct_owner.assign(n_tiles, -1);
+    for (size_t t = 0; t < n_tiles; t++) {
+        const int li = o.tile_owner_layer[t];
+        if (li < 0) continue;
+        pc.direct_owner[t] = job_of[li];
+        claimed[job_of[li]] = li;
         any = true;
     }
-    if (!any) return;
-    std::vector<int> owner((size_t)tx_n * ty_n, -1);
-    std::vector<int> owner_layer((size_t)tx_n * ty_n, -1);
-    size_t n_direct = 0;
-    for (int ty = 0; ty < ty_n; ty++)
-        for (int tx = 0; tx < tx_n; tx++) {
-            const int x0 = tx * TW, y0 = ty * TH, x1 = std::min(x0 + TW, W), y1 = std::min(y0 + TH, H);
-            for (int li = (int)layers.size() - 1; li >= 0; li--) {
-                const dev::LayerDev &L = layers[li];
-                if (L.px0 >= x1 || L.px1 <= x0 || L.py0 >= y1 || L.py1 <= y0) continue;   // the composite's own culling test
-                if (job_of[li] >= 0 &&
-                    ((x0 >= L.ix0 && x1 <= L.ix1 && y0 >= L.iy0 && y1 <= L.iy1) || (x0 >= L.jx0 && x1 <= L.jx1 && y0 >= L.jy0 && y1 <= L.jy1))) {
-                    owner[(size_t)ty * tx_n + tx] = job_of[li];
-                    owner_layer[(size_t)ty * tx_n + tx] = li;
-                    n_direct++;
-                }
-                break;   // topmost intersecting layer decides
-            }
-        }
-    if (!n_direct) return;
-    // one layer per job (a texture shown twice 1:1 in the same output would need two frame positions)
-    std::map<int, int> layer_of_job;
-    for (size_t t = 0; t < owner.size(); t++) {
-        if (owner[t] < 0) continue;
-        auto ins = layer_of_job.emplace(owner[t], owner_layer[t]);
-        if (ins.first->second != owner_layer[t]) { owner[t] = -1; n_direct--; }
-    }
-    if (!n_direct) return;
-    pc.direct_off = param_alloc((size_t)tx_n * ty_n);
-    pc.direct_owner = owner;
-    pc.job.map_w = tx_n;
-    for (auto &jl : layer_of_job) {
+    if (!any) { pc.direct_owner.clear(); return; }
+    pc.direct_off = param_alloc(n_tiles);
+    for (auto &jl : claimed) {
         dev::FusedJob &fj = fused_jobs_[jl.first];
         const dev::LayerDev &L = layers[jl.second];
         fused_direct_off_[jl.first] = pc.direct_off;
@@ -1607,7 +1653,7 @@ smr_status Renderer::plan_output(Output &o, smr_output_frame &of, uint64_t pts) 
         pc.job.out_format = o.format;
         pc.job.out0 = dst[0]; pc.job.out1 = dst[1]; pc.job.out2 = dst[2];
         pc.job.out_pitch0 = pitch[0]; pc.job.out_pitch1 = pitch[1]; pc.job.out_pitch2 = pitch[2];
-        if (fused_fmt && direct_k11_) classify_direct_tiles(pc, layers, W, H);
+        if (fused_fmt && (direct_k11_ || tile_sort_)) plan_tiles(o, pc, layers, W, H);
         composites_.push_back(pc);
     } else {
         if (o.format == SMR_OUT_RGBA8) { set_error("RGBA output must match the root layout resolution"); return SMR_ERR_UNSUPPORTED; }
@@ -1747,7 +1793,11 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
                 if (fused_direct_off_[pp.job] != SIZE_MAX && ((pp.oy_begin | pp.oy_end) & 1)) {
                     fused_direct_off_[pp.job] = SIZE_MAX;
                     for (PendingComposite &pc : composites_)
-                        for (int &ow : pc.direct_owner) if (ow == pp.job) ow = -1;
+                        for (size_t t = 0; t < pc.direct_owner.size(); t++)
+                            if (pc.direct_owner[t] == pp.job) {   // back to the composite (cheap interior tiles: at the end of the list)
+                                pc.direct_owner[t] = -1;
+                                pc.list.push_back((uint32_t)(t % (size_t)pc.job.map_w) | ((uint32_t)(t / (size_t)pc.job.map_w) << 16));
+                            }
                 }
             FusedLaunch fl;
             fl.variant = v.first; fl.src = v.second; fl.nblocks = (int)begin.size() - 1;
@@ -1767,31 +1817,22 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
     if (!weight_jobs_.empty()) memcpy(param_host_.data() + wj_off, weight_jobs_.data(), sizeof(dev::WeightJob) * weight_jobs_.size());
     if (!tick_tmaps_.empty()) memcpy(param_host_.data() + tm_off, tick_tmaps_.data(), sizeof(CUtensorMap) * tick_tmaps_.size());
     uint64_t direct_tiles = 0;
-    for (PendingComposite &pc : composites_) {   // direct-tile maps: one byte per composite tile
-        if (pc.direct_off == SIZE_MAX) continue;
-        bool any = false;
-        for (int ow : pc.direct_owner) direct_tiles += ow >= 0 ? 1 : 0;
-        for (size_t t = 0; t < pc.direct_owner.size(); t++) {
-            param_host_[pc.direct_off + t] = pc.direct_owner[t] >= 0 ? (uint8_t)(pc.direct_owner[t] + 1) : 0;
-            any = any || pc.direct_owner[t] >= 0;
+    for (PendingComposite &pc : composites_) {   // direct-tile maps (one byte per tile: the owner's id) and tile lists
+        if (pc.direct_off != SIZE_MAX) {
+            bool any = false;
+            for (size_t t = 0; t < pc.direct_owner.size(); t++) {
+                param_host_[pc.direct_off + t] = pc.direct_owner[t] >= 0 ? (uint8_t)(pc.direct_owner[t] + 1) : 0;
+                any = any || pc.direct_owner[t] >= 0;
+                direct_tiles += pc.direct_owner[t] >= 0 ? 1 : 0;
+            }
+            if (!any) pc.direct_off = SIZE_MAX;
         }
-        if (!any) pc.direct_off = SIZE_MAX;
-    }
-    if (direct_tiles) {
-        // compacted composite launch: one block per tile that is left (row-major), for every output of the tick (they share
-        // one launch); a direct tile costs nothing, not even an empty block
-        for (PendingComposite &pc : composites_) {
-            const int tx_n = (pc.job.width + dev::kDirectTileW - 1) / dev::kDirectTileW, ty_n = (pc.job.height + dev::kDirectTileH - 1) / dev::kDirectTileH;
-            std::vector<uint32_t> list;
-            list.reserve((size_t)tx_n * ty_n);
-            for (int ty = 0; ty < ty_n; ty++)
-                for (int tx = 0; tx < tx_n; tx++)
-                    if (pc.direct_off == SIZE_MAX || pc.direct_owner[(size_t)ty * tx_n + tx] < 0) list.push_back((uint32_t)tx | ((uint32_t)ty << 16));
-            const size_t off = param_alloc(sizeof(uint32_t) * std::max<size_t>(list.size(), 1));
+        if (pc.use_list) {
+            const size_t off = param_alloc(sizeof(uint32_t) * std::max<size_t>(pc.list.size(), 1));
             if (param_host_.size() < param_used_) param_host_.resize(param_used_ * 2);
-            if (!list.empty()) memcpy(param_host_.data() + off, list.data(), sizeof(uint32_t) * list.size());
+            if (!pc.list.empty()) memcpy(param_host_.data() + off, pc.list.data(), sizeof(uint32_t) * pc.list.size());
             pc.job.tile_list = (const uint32_t *)(uintptr_t)off;   // arena offset for now: the arena may still grow
-            pc.job.n_tiles = (int)list.size();
+            pc.job.n_tiles = (int)pc.list.size();
         }
     }
     // composite jobs: their device pointers are known once the arena is sized; with two or more outputs in the tick
@@ -1807,7 +1848,7 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
         }
     for (PendingComposite &pc : composites_) {   // arena offsets -> device pointers
         pc.job.direct_map = pc.direct_off != SIZE_MAX ? param_dev_[slot_].p + pc.direct_off : nullptr;
-        if (direct_tiles) pc.job.tile_list = (const uint32_t *)(param_dev_[slot_].p + (size_t)(uintptr_t)pc.job.tile_list);
+        if (pc.use_list) pc.job.tile_list = (const uint32_t *)(param_dev_[slot_].p + (size_t)(uintptr_t)pc.job.tile_list);
     }
     for (size_t i = 0; i < fused_jobs_.size(); i++)
         fused_jobs_[i].direct_map = fused_direct_off_[i] != SIZE_MAX ? param_dev_[slot_].p + fused_direct_off_[i] : nullptr;
