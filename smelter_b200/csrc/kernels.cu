@@ -884,29 +884,48 @@ __device__ __forceinline__ float to_v(float r, float g, float b) {
 // very operations of the composite's fused output stage: Y per pixel from the raw bytes, chroma from the exact mean of
 // the four bytes (NC-6u at the .5 / .5 taps of an even-sized target).  (X, Y) even: frame position of the block.
 __device__ __forceinline__ void emit_yuv_2x2(const FusedJob &J, int X, int Y, uint32_t p00, uint32_t p10, uint32_t p01, uint32_t p11) {
-    // no conversion unit (I2F / F2I run at a fraction of the FP32 rate): a byte or 16-bit field goes under the exponent of
-    // 2^23 by PRMT and 2^23 is subtracted (exact); the UNORM8 store rounds by the magic add (== __float2int_rn below 2^22)
-    auto byte_f = [](uint32_t p, uint32_t sel) { return __uint_as_float(__byte_perm(p, 0x4B000000u, sel)) - 8388608.0f; };
-    auto store8 = [](float x) -> unsigned char {   // unorm8(): rint(clamp01(x) * 255)
-        const float t = __saturatef(x) * 255.0f;
-        return (unsigned char)(__float_as_uint(t + 12582912.0f) & 0xffu);
+    using namespace v5;
+    // The arithmetic of the composite's output stage, operation for operation, two values per instruction (packed FP32) and
+    // without the conversion unit (I2F / F2I run at a fraction of the FP32 rate): a byte or 16-bit field goes under the
+    // exponent of 2^23 by PRMT and 2^23 is subtracted (exact); the UNORM8 store rounds by the magic add (== __float2int_rn
+    // below 2^22); clamp01 is the .SAT of the producing fma.
+    const float2 m23 = splat(-8388608.0f);
+    const float2 c = splat(__uint_as_float(0x3b808081u)), lo = splat(__uint_as_float(0xaf7efeffu));   // div255(n, 1): fma(n, c, n * lo)
+    auto pairf = [&](uint32_t a, uint32_t b, uint32_t sel) {   // exact floats of one byte of a and of b
+        return add2(make_float2(__uint_as_float(__byte_perm(a, 0x4B000000u, sel)), __uint_as_float(__byte_perm(b, 0x4B000000u, sel))), m23);
     };
-    auto lum = [&](uint32_t p) -> unsigned char {
-        return store8(to_y(div255(byte_f(p, 0x7540u), 1.0f), div255(byte_f(p, 0x7541u), 1.0f), div255(byte_f(p, 0x7542u), 1.0f)));
+    auto unit = [&](float2 n) { return fma2(n, c, mul2(n, lo)); };                                      // T.u8n[] of two bytes
+    auto store2 = [&](float2 x01) -> uint32_t {   // two unorm8(): x01 already clamped to [0, 1]; bytes in bits 0..7 and 8..15
+        const float2 q = add2_after_mul(mul2(x01, splat(255.0f)), splat(12582912.0f));
+        return (__float_as_uint(q.x) & 0xffu) | ((__float_as_uint(q.y) & 0xffu) << 8);
     };
-    *reinterpret_cast<uchar2 *>(J.out0 + (size_t)Y * J.out_pitch0 + X) = make_uchar2(lum(p00), lum(p10));
-    *reinterpret_cast<uchar2 *>(J.out0 + (size_t)(Y + 1) * J.out_pitch0 + X) = make_uchar2(lum(p01), lum(p11));
+    auto lum2 = [&](uint32_t a, uint32_t b) -> uint32_t {   // to_y() of two pixels
+        const float2 r = unit(pairf(a, b, 0x7540u)), g = unit(pairf(a, b, 0x7541u)), bl = unit(pairf(a, b, 0x7542u));
+        const float2 y = fma2(bl, splat(0.0722f), fma2(g, splat(0.7152f), mul2(r, splat(0.2126f))));
+        return store2(make_float2(__saturatef(fmaf(y.x, 0.85882352941f, K16)), __saturatef(fmaf(y.y, 0.85882352941f, K16))));
+    };
+    *reinterpret_cast<unsigned short *>(J.out0 + (size_t)Y * J.out_pitch0 + X) = (unsigned short)lum2(p00, p10);
+    *reinterpret_cast<unsigned short *>(J.out0 + (size_t)(Y + 1) * J.out_pitch0 + X) = (unsigned short)lum2(p01, p11);
     // sums of the four bytes per channel, two channels per word: (r, b) in the 16-bit halves of one, (g, a) of the other
     const uint32_t m = 0x00ff00ffu;
     const uint32_t srb = (p00 & m) + (p10 & m) + (p01 & m) + (p11 & m);
     const uint32_t sga = ((p00 >> 8) & m) + ((p10 >> 8) & m) + ((p01 >> 8) & m) + ((p11 >> 8) & m);
-    const float r = div255(byte_f(srb, 0x7610u), 0.25f), g = div255(byte_f(sga, 0x7610u), 0.25f), b = div255(byte_f(srb, 0x7632u), 0.25f);
-    const unsigned char u = store8(to_u(r, g, b)), v = store8(to_v(r, g, b));
+    const float2 c4 = splat(__uint_as_float(0x3b808081u) * 0.25f), lo4 = splat(__uint_as_float(0xaf7efeffu) * 0.25f);   // div255(n, 0.25)
+    const float2 nrg = add2(make_float2(__uint_as_float(__byte_perm(srb, 0x4B000000u, 0x7610u)), __uint_as_float(__byte_perm(sga, 0x4B000000u, 0x7610u))), m23);
+    const float nb = __uint_as_float(__byte_perm(srb, 0x4B000000u, 0x7632u)) - 8388608.0f;
+    const float2 rg = fma2(nrg, c4, mul2(nrg, lo4));
+    const float b = fmaf(nb, c4.x, nb * lo4.x);
+    // (to_u, to_v) as one packed chain: the two matrix rows side by side
+    float2 uv = mul2(splat(rg.x), make_float2(-0.1146f, 0.5f));
+    uv = fma2(splat(rg.y), make_float2(-0.3854f, -0.4542f), uv);
+    uv = fma2(splat(b), make_float2(0.5f, -0.0458f), uv);
+    uv = add2(uv, splat(0.5f));
+    const uint32_t cuv = store2(make_float2(__saturatef(fmaf(uv.x, 0.87843137254f, K16)), __saturatef(fmaf(uv.y, 0.87843137254f, K16))));
     if (J.out_format == 4) {   // NV12: texel (X / 2, Y / 2) of the interleaved plane sits at byte X
-        *reinterpret_cast<uchar2 *>(J.out1 + (size_t)(Y >> 1) * J.out_pitch1 + X) = make_uchar2(u, v);
+        *reinterpret_cast<unsigned short *>(J.out1 + (size_t)(Y >> 1) * J.out_pitch1 + X) = (unsigned short)cuv;
     } else {
-        J.out1[(size_t)(Y >> 1) * J.out_pitch1 + (X >> 1)] = u;
-        J.out2[(size_t)(Y >> 1) * J.out_pitch2 + (X >> 1)] = v;
+        J.out1[(size_t)(Y >> 1) * J.out_pitch1 + (X >> 1)] = (unsigned char)(cuv & 0xffu);
+        J.out2[(size_t)(Y >> 1) * J.out_pitch2 + (X >> 1)] = (unsigned char)(cuv >> 8);
     }
 }
 
