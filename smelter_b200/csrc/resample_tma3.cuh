@@ -456,16 +456,25 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
             };
             // direct tiles (FusedJob.direct_map): rows oa, oa + 1 are final rows of the output frame -- K10 / K11 of this lane's
             // 2 x 2 blocks from the encoded bytes still in registers; frame position and sizes are even (host)
-            auto emit = [&](const uint32_t *pa, const uint32_t *pb, int oa) {
-                if (J.direct_map == nullptr) return;
+            // does this lane's 2 x 2 block (columns j, j + 1 of rows oa, oa + 1) lie in a direct tile of this job?  Asked BEFORE the
+            // tap loop: the map byte is a global load, and the vertical pass is the latency-bound leg of the step
+            auto owned = [&](int oa, bool *own) {
                 const int ncols = min(K::NOUT, J.dst_w - cur.ox0);
 #pragma unroll
                 for (int j = 0; j < OUT; j += 2) {
                     const int col = OUT * (lane - K::last_stage(j)) + j;
-                    if (col < 0 || col >= ncols) continue;
+                    own[j / 2] = false;
+                    if (J.direct_map == nullptr || col < 0 || col >= ncols || oa >= row_end) continue;
                     const int X = J.fx + cur.ox0 + col, Y = J.fy + oa;
-                    if ((int)__ldg(J.direct_map + (Y / kDirectTileH) * J.map_w + X / kDirectTileW) != J.direct_id) continue;
-                    emit_yuv_2x2(J, X, Y, pa[j], pa[j + 1], pb[j], pb[j + 1]);
+                    own[j / 2] = (int)__ldg(J.direct_map + (Y / kDirectTileH) * J.map_w + X / kDirectTileW) == J.direct_id;
+                }
+            };
+            auto emit = [&](const uint32_t *pa, const uint32_t *pb, int oa, const bool *own) {
+#pragma unroll
+                for (int j = 0; j < OUT; j += 2) {
+                    if (!own[j / 2]) continue;
+                    const int col = OUT * (lane - K::last_stage(j)) + j;
+                    emit_yuv_2x2(J, J.fx + cur.ox0 + col, J.fy + oa, pa[j], pa[j + 1], pb[j], pb[j + 1]);
                 }
             };
             // one output row the general way: weights from global memory, tap rows clamped to the image
@@ -491,6 +500,8 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                 if (warp < kWarps / 2) {
                     const int oa = cur.o0 + 2 * warp, ob = oa + 1;
                     const int fa = __ldg(J.first_v) + S * oa;               // first_v(oa); first_v(ob) = fa + S
+                    bool own[OUT / 2];
+                    owned(oa, own);
                     if (ob < row_end && fa >= 0 && fa + S + TAPS - 1 <= H - 1) {
                         float2 aa[3 * OUT / 2], bb2[3 * OUT / 2];
 #pragma unroll
@@ -515,11 +526,11 @@ __global__ void __launch_bounds__(32 * kWarps * kGroups, 1) k_resample_tma3(cons
                         uint32_t pa[OUT], pb[OUT];
                         finish(aa, oa, pa);
                         finish(bb2, ob, pb);
-                        emit(pa, pb, oa);
+                        emit(pa, pb, oa, own);
                     } else {
                         uint32_t pa[OUT], pb[OUT];
                         if (oa < row_end) one_row(oa, pa);
-                        if (ob < row_end) { one_row(ob, pb); emit(pa, pb, oa); }   // pieces of a direct job hold whole row pairs
+                        if (ob < row_end) { one_row(ob, pb); emit(pa, pb, oa, own); }   // pieces of a direct job hold whole row pairs
                     }
                 }
             } else {
