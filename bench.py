@@ -709,7 +709,10 @@ def main():
     secondary = None
     if world > 1 and wl["name"] == "cfg3" and not args.no_secondary:
         modes = ["nccl", "peer_copy", "peer_direct"] if args.exchange == "all" else [args.exchange]
-        secondary = measure_cfg4_modes(torch, dist, dev, rank, world, local, max(args.steps, 20), args.warmup, modes)
+        try:
+            secondary = measure_cfg4_modes(torch, dist, dev, rank, world, local, max(args.steps, 20), args.warmup, modes)
+        except Exception as e:   # the primary line stands on its own; say what happened to the exchange leg
+            secondary = {"workload": "cfg4", "error": repr(e)[:300]}
     if rank == 0:
         line = {"metric": metric_name(wl),
                 "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

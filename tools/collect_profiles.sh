@@ -4,6 +4,7 @@ TAG=${1:-r02}
 O=${O:-profiles}   # on the GPU box: O=gpurun_out/profiles (the .ncu-rep files are too big to travel back)
 mkdir -p $O
 for w in cfg3 cfg3b cfg2 cfg4 cfg5 grid25 passthrough; do [ -s gpurun_out/${TAG}_bench_$w.json ] && tail -1 gpurun_out/${TAG}_bench_$w.json > $O/${TAG}_bench_$w.json; done
+for n in nodirect nodirect_nosort; do [ -s gpurun_out/${TAG}_bench_cfg3_$n.json ] && tail -1 gpurun_out/${TAG}_bench_cfg3_$n.json > $O/${TAG}_bench_cfg3_$n.json; done
 [ -s gpurun_out/${TAG}_reference_arm.json ] && tail -1 gpurun_out/${TAG}_reference_arm.json > $O/${TAG}_bench_cfg3_reference_arm.json
 cp gpurun_out/${TAG}_launches_cfg3.csv $O/${TAG}_launches_cfg3.csv 2>/dev/null
 for k in fused comp; do

@@ -13,6 +13,17 @@ try:
 except Exception as e: print("$w FAILED", e)
 PY
 done
+# A/B switches of the tile plan on the headline workload (device-timed only)
+SMR_DIRECT_K11=0 timeout 300 python bench.py --workload cfg3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_cfg3_nodirect.json 2>/dev/null
+SMR_DIRECT_K11=0 SMR_TILE_SORT=0 timeout 300 python bench.py --workload cfg3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_cfg3_nodirect_nosort.json 2>/dev/null
+python - <<PY
+import json
+for n in ("nodirect", "nodirect_nosort"):
+    try:
+        d=json.loads(open("gpurun_out/${TAG}_bench_cfg3_%s.json" % n).read().strip().splitlines()[-1])
+        print("cfg3", n, round(d["value"],1), {k: round(v["ms_per_frame"],4) for k,v in d["roofline"]["kernels"].items()})
+    except Exception as e: print("cfg3", n, "FAILED", e)
+PY
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_reference_arm.json 2> gpurun_out/${TAG}_reference_arm.err
 tail -c 700 gpurun_out/${TAG}_reference_arm.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 24 -c 40 --csv --log-file gpurun_out/${TAG}_launches_cfg3.csv python bench.py --workload cfg3 --steps 6 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
