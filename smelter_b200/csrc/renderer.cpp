@@ -111,7 +111,7 @@ static int resample_taps(float scale) {  // resample.wgsl:43-48
 // strip belongs to exactly one piece.
 void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst_h, int n_jobs, int max_blocks,
                           std::vector<dev::FusedPiece> &pieces, std::vector<int> &begin, int strip_cols_all = dev::kFusedStripCols,
-                          const int *strip_cols_per_job = nullptr) {
+                          const int *strip_cols_per_job = nullptr, int gran = 8) {
     pieces.clear(); begin.clear();
     long long total = 0;
     auto cols_of = [&](int i) { return strip_cols_per_job ? strip_cols_per_job[i] : strip_cols_all; };
@@ -119,7 +119,11 @@ void partition_fused_rows(const int *job_index, const int *dst_w, const int *dst
         if (dst_w[i] > 0 && dst_h[i] > 0) total += (long long)((dst_w[i] + cols_of(i) - 1) / cols_of(i)) * dst_h[i];
     if (total <= 0 || max_blocks <= 0) return;
     const int nblocks = (int)std::min<long long>((long long)max_blocks, (total + 7) / 8);
-    const long long per_block = ((total + nblocks - 1) / nblocks + 7) & ~7LL;
+    // share per block: a multiple of `gran` rows.  8 = whole steps of the kernels; the grouped TMA kernel takes 2 (whole row
+    // pairs): with 444 groups a share of 330.8 rows rounds to 332 instead of 336 -- every SM gets work (336 left two idle) and
+    // the critical path is half a step shorter
+    const long long g = gran > 0 ? gran : 8;
+    const long long per_block = ((total + nblocks - 1) / nblocks + g - 1) / g * g;
     begin.push_back(0);
     long long room = per_block;
     for (int i = 0; i < n_jobs; i++) {
@@ -1788,7 +1792,8 @@ smr_status Renderer::render_begin(uint64_t pts, const smr_input_frame *in, uint3
             std::vector<dev::FusedPiece> pieces;
             std::vector<int> begin;
             partition_fused_rows(idx.data(), widths.data(), heights.data(), (int)idx.size(),
-                                 sm_count_ * (v.first >= 30 ? dev::kTma0Groups : 3), pieces, begin, dev::kFusedStripCols, cols.data());
+                                 sm_count_ * (v.first >= 30 ? dev::kTma0Groups : 3), pieces, begin, dev::kFusedStripCols, cols.data(),
+                                 (v.first == 22 || v.first == 24) ? 2 : 8);
             if (pieces.empty()) continue;
             // direct tiles: the vertical pass emits K10 / K11 per PAIR of output rows, so a job's pieces must hold whole pairs
             // (they do whenever every job of the launch has an even height); a job cut at an odd row writes nothing directly
