@@ -1365,6 +1365,9 @@ void Renderer::plan_tiles(Output &o, PendingComposite &pc, const std::vector<dev
             // warps) becomes the longer leg -- measured: 4:1 grid +4 %, 2:1 grid -2 %
             if (fj.variant != 24 || !fj.v_same || ((fj.dst_w | fj.dst_h) & 1)) continue;
             if ((L.tx_off & 1) || (L.ty_off & 1)) continue;   // frame position of texel (0, 0) = (-tx_off, -ty_off)
+            // the whole child inside the frame: the kernel maps EVERY pixel of the job to a tile of the map, so a child hanging
+            // over an edge (overflow: visible, absolute positions) would index tiles that do not exist
+            if (L.tx_off > 0 || L.ty_off > 0 || -L.tx_off + fj.dst_w > W || -L.ty_off + fj.dst_h > H) continue;
             if (fused_direct_off_[it->second] != SIZE_MAX) continue;   // serves another output (or an earlier layer) already
             job_of[li] = it->second;
         }

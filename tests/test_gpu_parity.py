@@ -764,3 +764,16 @@ def test_direct_tiles_need_even_positions():
     assert_identical(got, exp, "odd and even positions")
     n = r.stats()["last_render_direct_tiles"]
     assert 40 <= n <= 5 * 23, n                         # only b's interior: at most 640 / 128 x 360 / 16 tiles
+
+
+def test_direct_tiles_not_for_a_child_hanging_over_the_frame_edge():
+    """a 4:1 child at an even position whose rectangle leaves the frame (View overflow: visible by position) is composed
+    the ordinary way: the resample kernel maps every pixel of a direct job to a tile of the frame, so only children wholly
+    inside the frame qualify; the child inside the frame next to it is written directly"""
+    fr = inputs(2, 2560, 1440)
+    a = s.RescalerComponent(position=s.Position.Absolute(width=640.0, height=360.0, left=960.0, top=-120.0), child=streams(2)[0])
+    b = s.RescalerComponent(position=s.Position.Absolute(width=640.0, height=360.0, left=128.0, top=320.0), child=streams(2)[1])
+    got, exp, r = run_case(V(background_color=BG, children=[a, b]), fr, resolution=s.Resolution(1280, 720))
+    assert_identical(got, exp, "child over the edge")
+    n = r.stats()["last_render_direct_tiles"]
+    assert 40 <= n <= 5 * 23, n                         # b's interior only
