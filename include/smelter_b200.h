@@ -290,6 +290,15 @@ smr_status smr_debug_partition(const int32_t *dst_w, const int32_t *dst_h, uint3
                                int32_t *pieces, uint32_t pieces_cap, uint32_t *n_pieces, int32_t *begin,
                                uint32_t begin_cap, uint32_t *n_blocks);
 
+/* inspection (no device needed): the tile plan of a composite with fused K10 / K11 output (Renderer::plan_tiles).  The
+ * width x height frame is cut into 128 x 16 tiles (row-major, tiles_x = ceil(width / 128)).  boxes: 14 ints per layer in
+ * painter's order {px0, px1, py0, py1 (pixel bounding box), ix0, ix1, iy0, iy1, jx0, jx1, jy0, jy1 (the two exact-interior
+ * bars), opaque (the interior replaces the target), job (fused resample job that could write the layer's tiles itself, -1:
+ * none)}.  owner_layer[t]: the layer whose job finishes tile t directly, or -1; tiles[]: the tiles left for the composite
+ * ((ty << 16) | tx), most expensive first when `sorted` != 0, row-major otherwise. */
+smr_status smr_debug_tile_plan(const int32_t *boxes, uint32_t n_layers, uint32_t width, uint32_t height, int32_t sorted,
+                               int32_t *owner_layer, uint32_t owner_cap, uint32_t *tiles, uint32_t tiles_cap, uint32_t *n_tiles);
+
 /* byte sizes of the planes smr_render writes for an output (0 for unused planes) */
 smr_status smr_output_plane_sizes(uint32_t width, uint32_t height, int32_t output_format, size_t sizes[3]);
 

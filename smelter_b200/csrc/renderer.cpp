@@ -1344,6 +1344,48 @@ static inline void fnv1a(uint64_t &h, const void *p, size_t n) {
     const uint8_t *b = (const uint8_t *)p;
     for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
 }
+// The geometric core of the plan as a free function (device-free; smr_debug_tile_plan and the CPU tests call it too).
+// boxes[i] = what the plan needs of layer i, painter's order: its pixel bounding box, its two exact-interior bars, whether
+// the interior replaces the target (FAST_OPAQUE), and the fused job that could write its tiles directly (-1: none).
+struct TileLayerBox { int32_t px0, px1, py0, py1, ix0, ix1, iy0, iy1, jx0, jx1, jy0, jy1, opaque, job; };
+void plan_tiles_core(const TileLayerBox *boxes, int n_layers, int W, int H, bool sort, std::vector<int> &owner_layer,
+                     std::vector<uint32_t> &list) {
+    const int TW = dev::kDirectTileW, TH = dev::kDirectTileH;
+    const int tx_n = (W + TW - 1) / TW, ty_n = (H + TH - 1) / TH;
+    const size_t n_tiles = (size_t)tx_n * ty_n;
+    owner_layer.assign(n_tiles, -1);
+    std::vector<std::pair<int, uint32_t>> keyed;
+    keyed.reserve(n_tiles);
+    std::map<int, int> layer_of_job;   // one layer per job (a texture shown twice 1:1 would need two frame positions)
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++) {
+            const int x0 = tx * TW, y0 = ty * TH, x1 = std::min(x0 + TW, W), y1 = std::min(y0 + TH, H);
+            int cost = 0;
+            bool top = true;
+            int owner = -1;
+            for (int li = n_layers - 1; li >= 0; li--) {
+                const TileLayerBox &L = boxes[li];
+                if (L.px0 >= x1 || L.px1 <= x0 || L.py0 >= y1 || L.py1 <= y0) continue;   // the composite's own culling test
+                const bool in = (x0 >= L.ix0 && x1 <= L.ix1 && y0 >= L.iy0 && y1 <= L.iy1) || (x0 >= L.jx0 && x1 <= L.jx1 && y0 >= L.jy0 && y1 <= L.jy1);
+                if (top) {   // the topmost intersecting layer decides about a direct tile
+                    top = false;
+                    if (in && L.job >= 0) {
+                        auto ins = layer_of_job.emplace(L.job, li);
+                        if (ins.first->second == li) { owner = li; break; }
+                    }
+                }
+                cost += in ? 1 : 8;
+                if (in && L.opaque) break;   // the kernel's occlusion start: nothing below is evaluated
+            }
+            if (owner >= 0) owner_layer[(size_t)ty * tx_n + tx] = owner;
+            else keyed.push_back({-cost, (uint32_t)tx | ((uint32_t)ty << 16)});
+        }
+    if (sort)
+        std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, uint32_t> &a, const std::pair<int, uint32_t> &b) { return a.first < b.first; });
+    list.resize(keyed.size());
+    for (size_t k = 0; k < keyed.size(); k++) list[k] = keyed[k].second;
+}
+
 void Renderer::plan_tiles(Output &o, PendingComposite &pc, const std::vector<dev::LayerDev> &layers, int W, int H) {
     const int TW = dev::kDirectTileW, TH = dev::kDirectTileH;
     const int tx_n = (W + TW - 1) / TW, ty_n = (H + TH - 1) / TH;
@@ -1377,37 +1419,13 @@ void Renderer::plan_tiles(Output &o, PendingComposite &pc, const std::vector<dev
     if (!job_of.empty()) fnv1a(key, job_of.data(), sizeof(int) * job_of.size());
     const size_t n_tiles = (size_t)tx_n * ty_n;
     if (!(o.tile_key_valid && o.tile_key == key && o.tile_owner_layer.size() == n_tiles)) {
-        o.tile_owner_layer.assign(n_tiles, -1);
-        std::vector<std::pair<int, uint32_t>> keyed;
-        keyed.reserve(n_tiles);
-        std::map<int, int> layer_of_job;   // one layer per job (a texture shown twice 1:1 would need two frame positions)
-        for (int ty = 0; ty < ty_n; ty++)
-            for (int tx = 0; tx < tx_n; tx++) {
-                const int x0 = tx * TW, y0 = ty * TH, x1 = std::min(x0 + TW, W), y1 = std::min(y0 + TH, H);
-                int cost = 0;
-                bool top = true;
-                int owner = -1;
-                for (int li = (int)layers.size() - 1; li >= 0; li--) {
-                    const dev::LayerDev &L = layers[li];
-                    if (L.px0 >= x1 || L.px1 <= x0 || L.py0 >= y1 || L.py1 <= y0) continue;   // the composite's own culling test
-                    const bool in = (x0 >= L.ix0 && x1 <= L.ix1 && y0 >= L.iy0 && y1 <= L.iy1) || (x0 >= L.jx0 && x1 <= L.jx1 && y0 >= L.jy0 && y1 <= L.jy1);
-                    if (top) {   // the topmost intersecting layer decides about a direct tile
-                        top = false;
-                        if (in && job_of[li] >= 0) {
-                            auto ins = layer_of_job.emplace(job_of[li], li);
-                            if (ins.first->second == li) { owner = li; break; }
-                        }
-                    }
-                    cost += in ? 1 : 8;
-                    if (in && (L.fast & dev::FAST_OPAQUE)) break;   // the kernel's occlusion start: nothing below is evaluated
-                }
-                if (owner >= 0) o.tile_owner_layer[(size_t)ty * tx_n + tx] = owner;
-                else keyed.push_back({-cost, (uint32_t)tx | ((uint32_t)ty << 16)});
-            }
-        if (tile_sort_)
-            std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, uint32_t> &a, const std::pair<int, uint32_t> &b) { return a.first < b.first; });
-        o.tile_list.resize(keyed.size());
-        for (size_t k = 0; k < keyed.size(); k++) o.tile_list[k] = keyed[k].second;
+        std::vector<TileLayerBox> boxes(layers.size());
+        for (size_t li = 0; li < layers.size(); li++) {
+            const dev::LayerDev &L = layers[li];
+            boxes[li] = {L.px0, L.px1, L.py0, L.py1, L.ix0, L.ix1, L.iy0, L.iy1, L.jx0, L.jx1, L.jy0, L.jy1,
+                         (L.fast & dev::FAST_OPAQUE) ? 1 : 0, job_of[li]};
+        }
+        plan_tiles_core(boxes.data(), (int)boxes.size(), W, H, tile_sort_, o.tile_owner_layer, o.tile_list);
         o.tile_key = key; o.tile_key_valid = true;
     }
     pc.use_list = true;
@@ -2423,6 +2441,26 @@ smr_status smr_host_unregister(void *ptr) {
 const char *smr_last_error(smr_renderer *r) { return r ? r->impl.last_error() : g_create_error.c_str(); }
 const char *smr_version(void) { return "smelter_b200 0.1 (sm_100a)"; }
 
+smr_status smr_debug_tile_plan(const int32_t *boxes, uint32_t n_layers, uint32_t width, uint32_t height, int32_t sorted,
+                               int32_t *owner_layer, uint32_t owner_cap, uint32_t *tiles, uint32_t tiles_cap, uint32_t *n_tiles) {
+    static_assert(sizeof(smr::TileLayerBox) == 14 * sizeof(int32_t), "14 ints per layer");
+    if ((n_layers && !boxes) || !n_tiles || width == 0 || height == 0 || width > 16384 * 4 || height > 16384 * 4) return SMR_ERR_INVALID_ARGUMENT;
+    try {
+        std::vector<int> owner;
+        std::vector<uint32_t> list;
+        smr::plan_tiles_core(reinterpret_cast<const smr::TileLayerBox *>(boxes), (int)n_layers, (int)width, (int)height, sorted != 0, owner, list);
+        *n_tiles = (uint32_t)list.size();
+        if (owner_layer) {
+            if (owner_cap < owner.size()) return SMR_ERR_BUFFER_TOO_SMALL;
+            for (size_t i = 0; i < owner.size(); i++) owner_layer[i] = owner[i];
+        }
+        if (tiles) {
+            if (tiles_cap < list.size()) return SMR_ERR_BUFFER_TOO_SMALL;
+            memcpy(tiles, list.data(), sizeof(uint32_t) * list.size());
+        }
+        return SMR_OK;
+    } catch (...) { return SMR_ERR_OUT_OF_MEMORY; }
+}
 smr_status smr_output_plane_sizes(uint32_t w, uint32_t h, int32_t fmt, size_t sizes[3]) {
     if (!sizes) return SMR_ERR_INVALID_ARGUMENT;
     if (fmt < SMR_OUT_PLANAR_YUV420 || fmt > SMR_OUT_NV12) return SMR_ERR_UNSUPPORTED;

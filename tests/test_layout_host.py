@@ -443,3 +443,76 @@ def test_set_layouts_flattened_boundary_round_trip():
     b.update_scene("output_1", RES, s.OutputFrameFormat.PlanarYuv420Bytes, V(background_color=BG))
     ls3, _ = b.debug_layouts("output_1")
     assert len(ls3) == 1 and ls3[0].type == 1
+
+
+def test_tile_plan_of_the_composite():
+    """Renderer::plan_tiles' geometric core through smr_debug_tile_plan (device-free), against a restatement in Python:
+    a tile is finished by the resample kernel (direct) iff its TOPMOST intersecting layer covers it with one of its
+    exact-interior bars and has a fused job (one layer per job); every other tile appears exactly once in the list, most
+    expensive first (per intersecting layer 1 inside a bar, 8 otherwise, walking down until an opaque interior)."""
+    import ctypes as C
+    import numpy as np
+    from smelter_b200 import _ffi as F
+    lib = F.lib()
+    TW, TH = 128, 16
+
+    def plan(boxes, W, H, sort=1):
+        b = np.ascontiguousarray(np.array(boxes, np.int32).reshape(-1, 14))
+        tx_n, ty_n = (W + TW - 1) // TW, (H + TH - 1) // TH
+        owner = (C.c_int32 * (tx_n * ty_n))()
+        tiles = (C.c_uint32 * (tx_n * ty_n))()
+        n = C.c_uint32()
+        st = lib.smr_debug_tile_plan(b.ctypes.data_as(C.POINTER(C.c_int32)), len(b), W, H, sort, owner, tx_n * ty_n, tiles, tx_n * ty_n, C.byref(n))
+        assert st == 0
+        return list(owner), [(t & 0xffff, t >> 16) for t in tiles[:n.value]]
+
+    def ref(boxes, W, H):
+        tx_n, ty_n = (W + TW - 1) // TW, (H + TH - 1) // TH
+        owner, cost, job_layer = {}, {}, {}
+        for ty in range(ty_n):
+            for tx in range(tx_n):
+                x0, y0, x1, y1 = tx * TW, ty * TH, min(tx * TW + TW, W), min(ty * TH + TH, H)
+                hits = [li for li in range(len(boxes) - 1, -1, -1)
+                        if not (boxes[li][0] >= x1 or boxes[li][1] <= x0 or boxes[li][2] >= y1 or boxes[li][3] <= y0)]
+                inside = lambda L: (x0 >= L[4] and x1 <= L[5] and y0 >= L[6] and y1 <= L[7]) or (x0 >= L[8] and x1 <= L[9] and y0 >= L[10] and y1 <= L[11])
+                own = -1
+                if hits:
+                    L = boxes[hits[0]]
+                    if inside(L) and L[13] >= 0 and job_layer.setdefault(L[13], hits[0]) == hits[0]:
+                        own = hits[0]
+                owner[(tx, ty)] = own
+                c = 0
+                for li in hits:
+                    c += 1 if inside(boxes[li]) else 8
+                    if inside(boxes[li]) and boxes[li][12]:
+                        break
+                cost[(tx, ty)] = c
+        return owner, cost
+
+    def layer(x0, y0, w, h, margin, opaque, job):   # a child rect with interior bars `margin` inside it (corner squares cut out)
+        return [x0, x0 + w, y0, y0 + h, x0 + margin, x0 + w - margin, y0 + 2, y0 + h - 2, x0 + 2, x0 + w - 2, y0 + margin, y0 + h - margin, opaque, job]
+
+    W, H = 3840, 2160
+    bg = [0, W, 0, H, 0, W, 0, H, 0, W, 0, H, 1, -1]
+    grid = [layer(960 * (i % 4), 540 * (i // 4), 960, 540, 34, 1, i) for i in range(16)]
+    overlay = [1120, 2720, 1680, 2040, 1170, 2670, 1682, 2038, 1122, 2718, 1730, 1990, 0, -1]
+    rng = np.random.default_rng(7)
+    random_scene = [bg] + [layer(int(rng.integers(0, W - 700)) & ~1, int(rng.integers(0, H - 400)) & ~1, int(rng.integers(300, 700)), int(rng.integers(100, 400)),
+                                 int(rng.integers(2, 40)), int(rng.integers(0, 2)), int(rng.integers(-1, 6))) for _ in range(24)]
+    for boxes, w, h in (([bg] + grid + [overlay], W, H), (random_scene, W, H), ([bg] + grid[:4], 1000, 250), ([], 640, 360)):
+        owner, tiles = plan(boxes, w, h)
+        ro, rc = ref(boxes, w, h)
+        tx_n = (w + TW - 1) // TW
+        assert {k: v for k, v in ro.items()} == {(i % tx_n, i // tx_n): o for i, o in enumerate(owner)}
+        left = [k for k, v in ro.items() if v < 0]
+        assert sorted(tiles) == sorted(left) and len(set(tiles)) == len(tiles)           # every tile exactly once
+        costs = [rc[t] for t in tiles]
+        assert costs == sorted(costs, reverse=True)                                       # most expensive first ...
+        for a, b in zip(tiles, tiles[1:]):
+            if rc[a] == rc[b]:
+                assert (a[1], a[0]) < (b[1], b[0])                                        # ... row-major among equals
+        _, unsorted = plan(boxes, w, h, sort=0)
+        assert unsorted == sorted(left, key=lambda t: (t[1], t[0]))
+    # BASELINE config 3: 70 % of the 4 050 tiles are direct
+    owner, tiles = plan([bg] + grid + [overlay], W, H)
+    assert 0.65 < sum(o >= 0 for o in owner) / len(owner) < 0.78
